@@ -1,0 +1,65 @@
+/* TEST INFRASTRUCTURE -- CPU oracle for the DVB-S2 decode stage (plain C restatement).
+ *
+ * This directory restates, function by function, what the reference's hot path computes
+ * (SURVEY.md section 8a); every function cites the reference file:line it follows.  It is the
+ * checker for tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg ONLY.  The product
+ * (sdrpp-dvbs-demodulator_b200/) never includes, links or calls anything from here.
+ *
+ * Pinning: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md
+ * section 4).  The restatement is therefore pinned by differential runs against the reference's
+ * own sources compiled unmodified into oracle/_ref/libdvbs2_ref.so (tests/test_oracle_vs_ref.py,
+ * run wherever that library exists) and by the committed outputs of those runs under
+ * tests/golden/ (made by tools/make_golden.py).  The demapper additionally depends on a
+ * 20-line stand-in for SDR++ core's complex_t (oracle/shim): that part is "parity unpinned"
+ * against the real SDR++ header.
+ */
+#ifndef DVBS2_ORACLE_H
+#define DVBS2_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* rate uses the reference's dvbs2_code_rate_t numbering (dvbs2/dvbs2.h:11-25):
+ * 0=1/4 1=1/3 2=2/5 3=1/2 4=3/5 5=2/3 6=3/4 7=4/5 8=5/6 9=7/8(no table) 10=8/9 11=9/10 */
+int orc_code_params(int shortframe, int rate, int* N, int* K, int* kbch, int* bch_t, int* q, int* links_total);
+
+/* LDPCDecoder::operator() through BBFrameLDPC::decode (bbframe_ldpc.cpp:123-139,
+ * layered_decoder.hh:121-133): llr[N] in place; returns iterations executed (0..max), or -1. */
+int orc_ldpc_decode(int shortframe, int rate, int8_t* llr, int max_trials);
+/* LDPCEncoder (encoder.hh:37-52), bit domain: K data bits in -> N code bits out. */
+int orc_ldpc_encode_bits(int shortframe, int rate, const uint8_t* data_bits, uint8_t* code_bits);
+/* layered schedule dump: pos[R*CNL] (layered_decoder.hh:95-119), cnc[q]; returns CNL */
+int orc_ldpc_schedule(int shortframe, int rate, uint16_t* pos, uint8_t* cnc);
+
+/* module_dvbs2_demod.cpp:357-360: bit i = (llr[i] < 0), MSB first, nbits bits */
+void orc_repack(const int8_t* llr, int nbits, uint8_t* bytes);
+/* BBFrameBCH::decode (bbframe_bch.cpp:380-405) -> BoseChaudhuriHocquenghemDecoder::operator() */
+int orc_bch_decode(int shortframe, int rate, uint8_t* frame);
+/* systematic BCH encode of kbch bits -> appends parity (same codeword as bbframe_bch.cpp:407-456) */
+int orc_bch_encode(int shortframe, int rate, uint8_t* frame);
+/* BBFrameDescrambler::work (bbframe_descramble.cpp:122-143) */
+int orc_descramble(int shortframe, int rate, uint8_t* frame);
+/* whole A3..A10 chain for one frame: llr[N] in (modified), bb[kbch/8] out */
+int orc_decode_frame(int shortframe, int rate, int8_t* llr, int max_trials, uint8_t* bb, int* ldpc_iters, int* bch_corr);
+
+/* constellation types follow dsp::constellation_type_t (constellation.h:9-16): 1=QPSK 3=8PSK 4=16APSK 5=32APSK */
+typedef struct orc_constellation orc_constellation;
+orc_constellation* orc_const_create(int type, float g1, float g2); /* ctor + make_lut(256) */
+void orc_const_destroy(orc_constellation* c);
+int orc_const_bits(const orc_constellation* c);
+const int8_t* orc_const_lut(const orc_constellation* c); /* [256][256][bits] (x major), NULL for 32APSK */
+void orc_const_points(const orc_constellation* c, float* re_im); /* constellation[] incl. const_amp */
+void orc_demod_soft_calc(const orc_constellation* c, float re, float im, int8_t* bits);
+void orc_demod_soft_lut(const orc_constellation* c, float re, float im, int8_t* bits);
+void orc_mod(const orc_constellation* c, int symbol, float* re_im);
+/* S2Deinterleaver::deinterleave (s2_deinterleaver.cpp:72-136); constellation 0=QPSK 1=8PSK 2=16APSK 3=32APSK */
+void orc_deinterleave(int constellation, int shortframe, int rate, const int8_t* in, int8_t* out);
+/* S2BBToSoft::process (dvbs2_bb_to_soft.cpp:7-33), pilots off: plframe = 90 header symbols + payload */
+int orc_bb_to_soft(const orc_constellation* c, int constellation, int shortframe, int rate,
+                   const float* plframe, int8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

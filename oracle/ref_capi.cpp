@@ -1,0 +1,234 @@
+// TEST INFRASTRUCTURE -- C API around the UNMODIFIED reference sources under /root/reference.
+// Built by oracle/Makefile into oracle/_ref/libdvbs2_ref.so (git-ignored, travels with gpurun).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load it.  Nothing here is product code; no reference source is copied, only #included from
+// where it lies.
+//
+// Call discipline: one BBFrameLDPC::decode per frame (lane-0 semantics, note N1),
+// decoder objects are created once per (framesize, rate) and never destroyed (note N5: GF tables
+// hang off static pointers nulled by the destructor).
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "dvbs2/codings/bbframe_ldpc.h"
+#include "dvbs2/codings/bbframe_bch.h"
+#include "dvbs2/codings/bbframe_descramble.h"
+#include "dvbs2/codings/s2_deinterleaver.h"
+#include "dvbs2/codings/xdsopl-ldpc-pabr/dvb_s2_tables.hh"
+#include "common/dsp/demod/constellation.h"
+
+using namespace dsp::dvbs2;
+
+namespace {
+struct RefSet {
+    BBFrameLDPC* ldpc;
+    BBFrameBCH* bch;
+    BBFrameDescrambler* descr;
+};
+std::mutex g_mu;
+std::map<int, RefSet> g_sets;
+
+RefSet& get_set(int shortframe, int rate) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int key = shortframe * 100 + rate;
+    auto it = g_sets.find(key);
+    if (it != g_sets.end()) return it->second;
+    dvbs2_framesize_t fs = shortframe ? FECFRAME_SHORT : FECFRAME_NORMAL;
+    RefSet s;
+    s.ldpc = new BBFrameLDPC(fs, (dvbs2_code_rate_t)rate);
+    s.bch = new BBFrameBCH(fs, (dvbs2_code_rate_t)rate);
+    s.descr = new BBFrameDescrambler(fs, (dvbs2_code_rate_t)rate);
+    return g_sets.emplace(key, s).first->second;
+}
+
+// "Fair SIMD" use of the vendored library: one frame per SIMD lane, blocks = lanes, the way
+// upstream xdsopl/LDPC drives it (SURVEY.md 8d CPU baseline (b)).
+struct Simd16 {
+    LDPCInterface* ldpc;
+    LDPCDecoder<simd_type, algorithm_type> dec;
+    simd_type* buf;
+    int N, K;
+};
+std::map<int, Simd16*> g_simd;
+
+LDPCInterface* make_table(int shortframe, int rate) {
+    if (!shortframe) {
+        switch (rate) {
+        case C1_4: return new LDPC<DVB_S2_TABLE_B1>();
+        case C1_3: return new LDPC<DVB_S2_TABLE_B2>();
+        case C2_5: return new LDPC<DVB_S2_TABLE_B3>();
+        case C1_2: return new LDPC<DVB_S2_TABLE_B4>();
+        case C3_5: return new LDPC<DVB_S2_TABLE_B5>();
+        case C2_3: return new LDPC<DVB_S2_TABLE_B6>();
+        case C3_4: return new LDPC<DVB_S2_TABLE_B7>();
+        case C4_5: return new LDPC<DVB_S2_TABLE_B8>();
+        case C5_6: return new LDPC<DVB_S2_TABLE_B9>();
+        case C8_9: return new LDPC<DVB_S2_TABLE_B10>();
+        case C9_10: return new LDPC<DVB_S2_TABLE_B11>();
+        default: return nullptr;
+        }
+    }
+    switch (rate) {
+    case C1_4: return new LDPC<DVB_S2_TABLE_C1>();
+    case C1_3: return new LDPC<DVB_S2_TABLE_C2>();
+    case C2_5: return new LDPC<DVB_S2_TABLE_C3>();
+    case C1_2: return new LDPC<DVB_S2_TABLE_C4>();
+    case C3_5: return new LDPC<DVB_S2_TABLE_C5>();
+    case C2_3: return new LDPC<DVB_S2_TABLE_C6>();
+    case C3_4: return new LDPC<DVB_S2_TABLE_C7>();
+    case C4_5: return new LDPC<DVB_S2_TABLE_C8>();
+    case C5_6: return new LDPC<DVB_S2_TABLE_C9>();
+    case C8_9: return new LDPC<DVB_S2_TABLE_C10>();
+    default: return nullptr;
+    }
+}
+} // namespace
+
+extern "C" {
+
+int ref_simd_lanes() { return simd_type::SIZE; }
+
+// BBFrameLDPC::decode (bbframe_ldpc.cpp:123-139): N int8 LLRs in place; returns iterations or -1.
+int ref_ldpc_decode(int shortframe, int rate, int8_t* frame, int max_trials) {
+    return get_set(shortframe, rate).ldpc->decode(frame, max_trials);
+}
+int ref_ldpc_data_size(int shortframe, int rate) { return get_set(shortframe, rate).ldpc->dataSize(); }
+
+// LDPCDecoder::operator()(..., blocks = lanes) on `lanes` frames at once (frames: lanes x N int8,
+// frame-major).  iters_out[l] is what a per-lane caller would see only when all lanes stop together;
+// the SIMD decoder stops when every lane is clean, so a single return value applies to the group.
+int ref_ldpc_decode_simd(int shortframe, int rate, int8_t* frames, int max_trials) {
+    Simd16* s;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int key = shortframe * 100 + rate;
+        auto it = g_simd.find(key);
+        if (it == g_simd.end()) {
+            s = new Simd16();
+            s->ldpc = make_table(shortframe, rate);
+            if (!s->ldpc) return -2;
+            s->dec.init(s->ldpc);
+            s->N = s->ldpc->code_len();
+            s->K = s->ldpc->data_len();
+            s->buf = new simd_type[s->N];
+            g_simd[key] = s;
+        } else {
+            s = it->second;
+        }
+    }
+    const int L = simd_type::SIZE;
+    for (int l = 0; l < L; ++l)
+        for (int i = 0; i < s->N; ++i)
+            reinterpret_cast<code_type*>(s->buf + i)[l] = frames[(size_t)l * s->N + i];
+    int trials = s->dec(s->buf, s->buf + s->K, max_trials, L);
+    for (int l = 0; l < L; ++l)
+        for (int i = 0; i < s->N; ++i)
+            frames[(size_t)l * s->N + i] = reinterpret_cast<code_type*>(s->buf + i)[l];
+    return trials < 0 ? trials : max_trials - trials;
+}
+
+// LDPCEncoder<int8_t> (encoder.hh:37-52) with the decoder's own convention: bit 1 <-> negative.
+// bits: K 0/1 bytes in, N 0/1 bytes out (systematic).
+int ref_ldpc_encode_bits(int shortframe, int rate, const uint8_t* data_bits, uint8_t* code_bits) {
+    LDPCInterface* t = make_table(shortframe, rate);
+    if (!t) return -1;
+    LDPCEncoder<int8_t> enc;
+    enc.init(t);
+    int N = t->code_len(), K = t->data_len();
+    std::vector<int8_t> soft(N);
+    for (int i = 0; i < K; ++i) soft[i] = data_bits[i] ? -1 : 1;
+    enc(soft.data(), soft.data() + K);
+    for (int i = 0; i < N; ++i) code_bits[i] = soft[i] < 0;
+    delete t;
+    return 0;
+}
+
+// Dump of LDPCDecoder::init's expansion, re-derived through the public LDPC<TABLE> iterator
+// (ldpc.hh:25-109): for data bit j, its check indices.  out must hold LINKS_TOTAL ints; returns
+// number of (bit, check) pairs written as bit*65536... no: pairs are written as two arrays.
+int ref_ldpc_links(int shortframe, int rate, int* bit_of_link, int* check_of_link, int cap) {
+    LDPCInterface* t = make_table(shortframe, rate);
+    if (!t) return -1;
+    int K = t->data_len(), n = 0;
+    t->first_bit();
+    for (int j = 0; j < K; ++j) {
+        int* acc = t->acc_pos();
+        int deg = t->bit_deg();
+        for (int d = 0; d < deg; ++d) {
+            if (n < cap) { bit_of_link[n] = j; check_of_link[n] = acc[d]; }
+            ++n;
+        }
+        t->next_bit();
+    }
+    delete t;
+    return n;
+}
+
+// BBFrameBCH (bbframe_bch.cpp:380-456): nbch/8 bytes in place.
+int ref_bch_decode(int shortframe, int rate, uint8_t* frame) { return get_set(shortframe, rate).bch->decode(frame); }
+int ref_bch_encode(int shortframe, int rate, uint8_t* frame) { return get_set(shortframe, rate).bch->encode(frame); }
+int ref_bch_data_size(int shortframe, int rate) { return get_set(shortframe, rate).bch->dataSize(); }
+
+// BBFrameDescrambler::work (bbframe_descramble.cpp:138-143): kbch/8 bytes in place.
+int ref_descramble(int shortframe, int rate, uint8_t* frame) { return get_set(shortframe, rate).descr->work(frame); }
+
+// S2Deinterleaver (s2_deinterleaver.cpp:72-202).
+void ref_deinterleave(int constellation, int shortframe, int rate, int8_t* in, int8_t* out) {
+    S2Deinterleaver d((dvbs2_constellation_t)constellation, shortframe ? FECFRAME_SHORT : FECFRAME_NORMAL,
+                      (dvbs2_code_rate_t)rate);
+    d.deinterleave(in, out);
+}
+void ref_interleave(int constellation, int shortframe, int rate, uint8_t* in, uint8_t* out) {
+    S2Deinterleaver d((dvbs2_constellation_t)constellation, shortframe ? FECFRAME_SHORT : FECFRAME_NORMAL,
+                      (dvbs2_code_rate_t)rate);
+    d.interleave(in, out);
+}
+
+// constellation_t (constellation.cpp): type is dsp::constellation_type_t (QPSK=1, PSK8=3, APSK16=4,
+// APSK32=5).  Objects are cached per (type, g1, g2) with make_lut(256) done once, as
+// DVBS2Demod::init does (module_dvbs2_demod.cpp:70-71).
+struct RefConst {
+    dsp::constellation_t* c;
+};
+static std::map<std::vector<float>, dsp::constellation_t*> g_const;
+static dsp::constellation_t* get_const(int type, float g1, float g2) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::vector<float> key{(float)type, g1, g2};
+    auto it = g_const.find(key);
+    if (it != g_const.end()) return it->second;
+    auto* c = new dsp::constellation_t((dsp::constellation_type_t)type, g1, g2);
+    c->make_lut(256);
+    g_const[key] = c;
+    return c;
+}
+// S2BBToSoft::process' demap loop (dvbs2_bb_to_soft.cpp:11-16), pilots off: nsym symbols starting
+// at `sym` (i.e. the caller passes &plframe[90]); out gets nsym*bits int8 in symbol order.
+int ref_demap(int type, float g1, float g2, const float* sym, int nsym, int8_t* out) {
+    dsp::constellation_t* c = get_const(type, g1, g2);
+    int bits = c->getBitsCnt();
+    for (int i = 0; i < nsym; ++i)
+        c->demod_soft_lut(dsp::complex_t{sym[2 * i], sym[2 * i + 1]}, &out[i * bits]);
+    return bits;
+}
+// constellation_t::demod_soft_calc direct (used by the 32APSK path and by make_lut).
+void ref_demap_calc(int type, float g1, float g2, const float* sym, int nsym, int8_t* out) {
+    dsp::constellation_t* c = get_const(type, g1, g2);
+    int bits = c->getBitsCnt();
+    for (int i = 0; i < nsym; ++i)
+        c->demod_soft_calc(dsp::complex_t{sym[2 * i], sym[2 * i + 1]}, &out[i * bits]);
+}
+// constellation_t::mod (constellation.cpp:156-158).
+void ref_mod(int type, float g1, float g2, const uint8_t* symbols, int nsym, float* out) {
+    dsp::constellation_t* c = get_const(type, g1, g2);
+    for (int i = 0; i < nsym; ++i) {
+        dsp::complex_t v = c->mod(symbols[i]);
+        out[2 * i] = v.re;
+        out[2 * i + 1] = v.im;
+    }
+}
+
+} // extern "C"
