@@ -1,0 +1,123 @@
+/* dvbs2fec -- C ABI of the B200 DVB-S2 decode stage (libdvbs2fec.so).
+ *
+ * This is the drop-in boundary for the decode stage of the SDR++ dvbs_demodulator module: the
+ * calls below replace the five host objects DVBS2Demod::process drives at
+ * src/demod/dvbs2/module_dvbs2_demod.cpp:334-367 (S2BBToSoft, BBFrameLDPC, the repack loop,
+ * BBFrameBCH, BBFrameDescrambler).  Plain C types only, opaque handle, caller-owned buffers,
+ * negative return = error (never an exception), one handle per demodulator instance; handles are
+ * independent and may be used from different threads concurrently (one thread per handle).
+ *
+ * Every entry point cites the reference interface it stands in for (paths relative to the
+ * reference's src/demod/).  INTEGRATION.md shows the ~30-line patch that binds them.
+ */
+#ifndef DVBS2FEC_H
+#define DVBS2FEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVBS2FEC_OK 0
+#define DVBS2FEC_EINVAL (-22)   /* bad argument / unsupported MODCOD+frame-size (reference: get_dvbs2_cfg throws,
+                                   codings/modcod_to_cfg.cpp:10-11,134-135; no LDPC table: bbframe_ldpc.cpp:67-68,105-106) */
+#define DVBS2FEC_ENODEV (-19)   /* no usable CUDA device / kernels missing: the library never falls back to the CPU */
+#define DVBS2FEC_ECUDA (-5)     /* a CUDA call failed; dvbs2fec_last_error() has the text */
+#define DVBS2FEC_EAGAIN (-11)   /* queue full (submit) */
+
+#define DVBS2FEC_FLAG_LDPC_FAIL 1u /* LDPC never met all parity checks (BBFrameLDPC::decode returned -1) */
+#define DVBS2FEC_FLAG_BCH_FAIL 2u  /* BBFrameBCH::decode returned -1 */
+
+typedef struct dvbs2fec_handle dvbs2fec_handle;
+
+typedef struct {
+    int32_t n_devices;      /* 0 = device 0 only; otherwise devices[0..n_devices) share the frames of every batch */
+    int32_t devices[8];
+    int32_t max_batch;      /* frames per kernel launch and per device (default 1024) */
+    int32_t max_latency_us; /* submit/collect queue: launch a partial batch after this long (default 2000) */
+    int32_t max_trials;     /* default LDPC iteration cap (reference: DVBS2_DEMOD_LDPC_RETRIES, main.cpp:65) */
+    int32_t reserved[4];
+} dvbs2fec_config;
+
+/* Per-frame outcome; mirrors the fields DVBS2Demod exposes to the GUI (module_dvbs2_demod.h:86-87). */
+typedef struct {
+    uint64_t tag;        /* caller's tag (submit) or frame index (batch calls) */
+    int16_t ldpc_iters;  /* iterations executed, 0 = input already a codeword, -1 = not converged (bbframe_ldpc.cpp:135-138) */
+    int16_t bch_corr;    /* corrected bit errors, -1 = uncorrectable (bose_chaudhuri_hocquenghem_decoder.hh:116-142) */
+    uint32_t flags;      /* DVBS2FEC_FLAG_* */
+} dvbs2fec_result;
+
+/* ctor/dtor of the decoder objects (DVBS2Demod::init, module_dvbs2_demod.cpp:7-91).  cfg may be NULL. */
+int dvbs2fec_create(const dvbs2fec_config* cfg, dvbs2fec_handle** out);
+void dvbs2fec_destroy(dvbs2fec_handle* h);
+const char* dvbs2fec_last_error(void);
+
+/* DVBS2Demod::setDemodParams (module_dvbs2_demod.h:60, .cpp:118-168) + get_dvbs2_cfg
+ * (codings/modcod_to_cfg.cpp:5-140): modcod 1..28.  Queued frames of the previous MODCOD are
+ * decoded and kept for collect() first.  max_trials <= 0 keeps the configured default. */
+int dvbs2fec_set_modcod(dvbs2fec_handle* h, int modcod, int shortframes, int pilots, int max_trials);
+
+/* getKBCH (module_dvbs2_demod.h:80), BBFrameLDPC::dataSize (codings/bbframe_ldpc.h:48), frame length. Bits. */
+int dvbs2fec_kbch(const dvbs2fec_handle* h);
+int dvbs2fec_kldpc(const dvbs2fec_handle* h);
+int dvbs2fec_nldpc(const dvbs2fec_handle* h);
+/* complex samples per PLFRAME handed to the demapper: 90 header + payload (+ pilot blocks) */
+int dvbs2fec_plframe_symbols(const dvbs2fec_handle* h);
+
+/* ---- stage-level calls: one-to-one with the reference objects, HOST buffers, synchronous ---- */
+
+/* S2BBToSoft::process (dvbs2/dvbs2_bb_to_soft.cpp:7-33): n PLFRAMEs of dvbs2fec_plframe_symbols()
+ * complex floats each (header at [0,90), PL-descrambled) -> n x N int8 LLRs, deinterleaved. */
+int dvbs2fec_bb_to_soft(dvbs2fec_handle* h, const float* plframes, int n, int8_t* llr_out);
+/* BBFrameLDPC::decode (codings/bbframe_ldpc.cpp:123-139), once per frame: n x N LLRs are replaced by the
+ * posterior LLRs; iters[i] = its return value for frame i. */
+int dvbs2fec_ldpc_decode(dvbs2fec_handle* h, int8_t* frames, int n, int max_trials, int16_t* iters);
+/* BBFrameBCH::decode (codings/bbframe_bch.cpp:380-405): n x (K_ldpc/8) bytes corrected in place. */
+int dvbs2fec_bch_decode(dvbs2fec_handle* h, uint8_t* frames, int n, int16_t* corrections);
+/* BBFrameDescrambler::work (codings/bbframe_descramble.cpp:138-143): first kbch/8 bytes of each
+ * stride-byte frame XORed in place. */
+int dvbs2fec_descramble(dvbs2fec_handle* h, uint8_t* frames, int stride, int n);
+
+/* ---- whole decode stage, synchronous (module_dvbs2_demod.cpp:349-366 for n frames) ---- */
+
+/* n x N int8 LLRs (host) -> n x kbch/8 BBFRAME bytes (host) + per-frame results.  This is the parity
+ * boundary: bit-exact with the reference decoder applied to each frame. */
+int dvbs2fec_decode_batch(dvbs2fec_handle* h, const int8_t* llr, int n, uint8_t* bb_out, dvbs2fec_result* results);
+/* same, starting from PLFRAME symbols (module_dvbs2_demod.cpp:334-366) */
+int dvbs2fec_decode_plframes(dvbs2fec_handle* h, const float* plframes, int n, uint8_t* bb_out,
+                             dvbs2fec_result* results);
+/* device-resident variant on the handle's first device: all pointers are device pointers, work is
+ * enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) and NOT synchronised. */
+int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n, uint8_t* d_bb_out,
+                                 dvbs2fec_result* d_results, void* cuda_stream);
+/* number of kernel launches the last decode_batch* call on this handle enqueued */
+int dvbs2fec_last_launch_count(const dvbs2fec_handle* h);
+
+/* ---- frame-batching queue between PL sync and the decoder (replaces simd_packer,
+ *      module_dvbs2_demod.cpp:343-347): frames come back in submission order ---- */
+int dvbs2fec_submit_llr(dvbs2fec_handle* h, const int8_t* llr, uint64_t tag);
+int dvbs2fec_submit_plframe(dvbs2fec_handle* h, const float* plframe, int nsym, uint64_t tag);
+/* up to max frames; bb_out receives kbch/8 bytes per frame.  timeout_us: 0 = poll, <0 = wait for one. */
+int dvbs2fec_collect(dvbs2fec_handle* h, uint8_t* bb_out, dvbs2fec_result* results, int max, int timeout_us);
+/* force the partial batch through (DVBS2Demod::reset / tempStop) */
+int dvbs2fec_flush(dvbs2fec_handle* h);
+
+/* pinned host memory for zero-staging transfers (optional) */
+void* dvbs2fec_alloc_pinned(size_t bytes);
+void dvbs2fec_free_pinned(void* p);
+
+/* ---- in-tree transmitter for synthetic input (not part of the reference's decode path) ---- */
+/* bbframe: kbch/8 bytes -> code_bits: N bytes of 0/1 (BB scramble, BCH, LDPC; EN 302 307 5.2-5.3) */
+int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits);
+/* code_bits -> PLFRAME symbols (90 zero header symbols, bit interleave, mapping; pilots as 0+0j) */
+int dvbs2fec_modulate(int modcod, int shortframes, int pilots, const uint8_t* code_bits, float* plframe);
+/* static facts about a MODCOD: returns 0 or DVBS2FEC_EINVAL */
+int dvbs2fec_modcod_info(int modcod, int shortframes, int pilots, int* nldpc, int* kldpc, int* kbch, int* bch_t,
+                         int* bits_per_symbol, int* plframe_symbols, int* links_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVBS2FEC_H */

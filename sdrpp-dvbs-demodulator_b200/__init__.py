@@ -1,0 +1,302 @@
+"""Host-side mirror of the SDR++ dvbs_demodulator decode-stage objects over libdvbs2fec.so.
+
+The compute path is the CUDA library only (csrc/, built in-tree for sm_100a by ``build()``); this
+module is a thin ctypes binding whose class and method names follow the reference objects that
+``DVBS2Demod::process`` drives (src/demod/dvbs2/module_dvbs2_demod.cpp:334-367):
+
+    S2BBToSoft.process        dvbs2/dvbs2_bb_to_soft.h:19
+    BBFrameLDPC.decode        dvbs2/codings/bbframe_ldpc.h:48-53
+    BBFrameBCH.decode         dvbs2/codings/bbframe_bch.h:81-85
+    BBFrameDescrambler.work   dvbs2/codings/bbframe_descramble.h:42
+    DVBS2Decoder              the whole stage (setDemodParams + batch decode + queue)
+
+There is no CPU fallback: if the shared library is missing or no B200 is visible every call raises.
+The directory name contains hyphens; import it with ``importlib.import_module("sdrpp-dvbs-demodulator_b200")``.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdvbs2fec.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "dvbs2fec.h")
+
+EINVAL, ENODEV, ECUDA, EAGAIN = -22, -19, -5, -11
+FLAG_LDPC_FAIL, FLAG_BCH_FAIL = 1, 2
+
+# reference dvbs2_code_rate_t numbering (dvbs2/dvbs2.h:11-25)
+RATE_NAMES = {0: "1/4", 1: "1/3", 2: "2/5", 3: "1/2", 4: "3/5", 5: "2/3", 6: "3/4", 7: "4/5", 8: "5/6", 10: "8/9", 11: "9/10"}
+
+
+class DVBS2FecError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("dvbs2fec error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("n_devices", C.c_int32), ("devices", C.c_int32 * 8), ("max_batch", C.c_int32),
+                ("max_latency_us", C.c_int32), ("max_trials", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+class Result(C.Structure):
+    _fields_ = [("tag", C.c_uint64), ("ldpc_iters", C.c_int16), ("bch_corr", C.c_int16), ("flags", C.c_uint32)]
+
+
+RESULT_DTYPE = np.dtype([("tag", np.uint64), ("ldpc_iters", np.int16), ("bch_corr", np.int16), ("flags", np.uint32)])
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libdvbs2fec.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", _HERE, "-j8"], stdout=out)
+    return LIB_PATH
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built -- there is nothing to fall back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DVBS2FecError(ENODEV, "%s is missing: run build() / `make -C %s` first" % (LIB_PATH, _HERE))
+    L = C.CDLL(LIB_PATH)
+    vp, ip = C.c_void_p, C.POINTER(C.c_int)
+    L.dvbs2fec_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.dvbs2fec_destroy.argtypes = [vp]
+    L.dvbs2fec_destroy.restype = None
+    L.dvbs2fec_last_error.restype = C.c_char_p
+    L.dvbs2fec_set_modcod.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    for f in ("dvbs2fec_kbch", "dvbs2fec_kldpc", "dvbs2fec_nldpc", "dvbs2fec_plframe_symbols", "dvbs2fec_last_launch_count",
+              "dvbs2fec_flush"):
+        getattr(L, f).argtypes = [vp]
+    L.dvbs2fec_bb_to_soft.argtypes = [vp, vp, C.c_int, vp]
+    L.dvbs2fec_ldpc_decode.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.dvbs2fec_bch_decode.argtypes = [vp, vp, C.c_int, vp]
+    L.dvbs2fec_descramble.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.dvbs2fec_decode_batch.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.dvbs2fec_decode_plframes.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.dvbs2fec_decode_batch_device.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.dvbs2fec_submit_llr.argtypes = [vp, vp, C.c_uint64]
+    L.dvbs2fec_submit_plframe.argtypes = [vp, vp, C.c_int, C.c_uint64]
+    L.dvbs2fec_collect.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+    L.dvbs2fec_alloc_pinned.argtypes = [C.c_size_t]
+    L.dvbs2fec_alloc_pinned.restype = vp
+    L.dvbs2fec_free_pinned.argtypes = [vp]
+    L.dvbs2fec_free_pinned.restype = None
+    L.dvbs2fec_encode_fecframe.argtypes = [C.c_int, C.c_int, vp, vp]
+    L.dvbs2fec_modulate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
+    L.dvbs2fec_modcod_info.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip, ip]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise DVBS2FecError(rc, lib().dvbs2fec_last_error().decode(errors="replace"))
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def modcod_info(modcod, shortframes=False, pilots=False):
+    """MODCOD facts (get_dvbs2_cfg, codings/modcod_to_cfg.cpp:5-140, plus code parameters)."""
+    v = [C.c_int() for _ in range(7)]
+    _check(lib().dvbs2fec_modcod_info(modcod, int(shortframes), int(pilots), *[C.byref(x) for x in v]))
+    keys = ("nldpc", "kldpc", "kbch", "bch_t", "bits", "plframe_symbols", "links_total")
+    return dict(zip(keys, (x.value for x in v)))
+
+
+def encode_fecframe(modcod, shortframes, bbframe):
+    """In-tree transmitter: kbch/8 payload bytes -> N code bits (uint8 0/1)."""
+    info = modcod_info(modcod, shortframes)
+    bb = np.ascontiguousarray(bbframe, np.uint8)
+    assert bb.size == info["kbch"] // 8
+    out = np.zeros(info["nldpc"], np.uint8)
+    _check(lib().dvbs2fec_encode_fecframe(modcod, int(shortframes), _ptr(bb), _ptr(out)))
+    return out
+
+
+def modulate(modcod, shortframes, pilots, code_bits):
+    """In-tree transmitter: N code bits -> PLFRAME complex64 (header and pilots left at 0)."""
+    info = modcod_info(modcod, shortframes, pilots)
+    bits = np.ascontiguousarray(code_bits, np.uint8)
+    out = np.zeros(info["plframe_symbols"] * 2, np.float32)
+    _check(lib().dvbs2fec_modulate(modcod, int(shortframes), int(pilots), _ptr(bits), _ptr(out)))
+    return out.view(np.complex64)
+
+
+class DVBS2Decoder:
+    """One decode-stage instance (== one DVBS2Demod's FEC objects).  ``devices`` shards every batch by frame."""
+
+    def __init__(self, devices=None, max_batch=1024, max_latency_us=2000, max_trials=25):
+        cfg = Config()
+        if devices:
+            cfg.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                cfg.devices[i] = d
+        cfg.max_batch, cfg.max_latency_us, cfg.max_trials = max_batch, max_latency_us, max_trials
+        self._h = C.c_void_p()
+        _check(lib().dvbs2fec_create(C.byref(cfg), C.byref(self._h)))
+        self.configured = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dvbs2fec_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # DVBS2Demod::setDemodParams (module_dvbs2_demod.h:60)
+    def setDemodParams(self, modcod, shortframes=False, pilots=False, max_ldpc_trials=0):
+        _check(lib().dvbs2fec_set_modcod(self._h, modcod, int(shortframes), int(pilots), max_ldpc_trials))
+        self.modcod, self.shortframes, self.pilots = modcod, bool(shortframes), bool(pilots)
+        self.N = lib().dvbs2fec_nldpc(self._h)
+        self.K = lib().dvbs2fec_kldpc(self._h)
+        self.kbch = lib().dvbs2fec_kbch(self._h)
+        self.plframe_symbols = lib().dvbs2fec_plframe_symbols(self._h)
+        self.configured = True
+        return self
+
+    set_modcod = setDemodParams
+
+    def getKBCH(self):
+        return self.kbch
+
+    # ---- stage-level (host numpy arrays) ----
+    def bb_to_soft(self, plframes):
+        x = np.ascontiguousarray(plframes).view(np.float32).reshape(-1, self.plframe_symbols * 2)
+        out = np.zeros((x.shape[0], self.N), np.int8)
+        _check(lib().dvbs2fec_bb_to_soft(self._h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def ldpc_decode(self, frames, max_trials=0):
+        """frames: (n, N) int8, decoded IN PLACE like BBFrameLDPC::decode; returns int16 iterations per frame."""
+        assert frames.dtype == np.int8 and frames.flags.c_contiguous and frames.shape[-1] == self.N
+        n = frames.size // self.N
+        iters = np.zeros(n, np.int16)
+        _check(lib().dvbs2fec_ldpc_decode(self._h, _ptr(frames), n, max_trials, _ptr(iters)))
+        return iters
+
+    def bch_decode(self, frames):
+        """frames: (n, K/8) uint8 corrected IN PLACE like BBFrameBCH::decode; returns int16 corrections per frame."""
+        assert frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.shape[-1] == self.K // 8
+        n = frames.size // (self.K // 8)
+        corr = np.zeros(n, np.int16)
+        _check(lib().dvbs2fec_bch_decode(self._h, _ptr(frames), n, _ptr(corr)))
+        return corr
+
+    def descramble(self, frames):
+        assert frames.dtype == np.uint8 and frames.flags.c_contiguous and frames.ndim == 2
+        _check(lib().dvbs2fec_descramble(self._h, _ptr(frames), frames.shape[1], frames.shape[0]))
+        return frames
+
+    # ---- whole stage ----
+    def decode_batch(self, llr):
+        x = np.ascontiguousarray(llr, np.int8).reshape(-1, self.N)
+        bb = np.zeros((x.shape[0], self.kbch // 8), np.uint8)
+        res = np.zeros(x.shape[0], RESULT_DTYPE)
+        _check(lib().dvbs2fec_decode_batch(self._h, _ptr(x), x.shape[0], _ptr(bb), _ptr(res)))
+        return bb, res
+
+    def decode_plframes(self, plframes):
+        x = np.ascontiguousarray(plframes).view(np.float32).reshape(-1, self.plframe_symbols * 2)
+        bb = np.zeros((x.shape[0], self.kbch // 8), np.uint8)
+        res = np.zeros(x.shape[0], RESULT_DTYPE)
+        _check(lib().dvbs2fec_decode_plframes(self._h, _ptr(x), x.shape[0], _ptr(bb), _ptr(res)))
+        return bb, res
+
+    def decode_batch_raw(self, llr_ptr, n, bb_ptr, res_ptr):
+        """Host pointers (e.g. pinned buffers); synchronous."""
+        _check(lib().dvbs2fec_decode_batch(self._h, llr_ptr, n, bb_ptr, res_ptr))
+
+    def decode_batch_device(self, d_llr_ptr, n, d_bb_ptr, d_res_ptr, stream_ptr=0):
+        """Device pointers on this decoder's first device; enqueues on ``stream_ptr`` and returns."""
+        _check(lib().dvbs2fec_decode_batch_device(self._h, d_llr_ptr, n, d_bb_ptr, d_res_ptr, stream_ptr))
+
+    def last_launch_count(self):
+        return lib().dvbs2fec_last_launch_count(self._h)
+
+    # ---- queue ----
+    def submit_llr(self, llr, tag):
+        x = np.ascontiguousarray(llr, np.int8)
+        assert x.size == self.N
+        _check(lib().dvbs2fec_submit_llr(self._h, _ptr(x), tag))
+
+    def submit_plframe(self, plframe, tag):
+        x = np.ascontiguousarray(plframe).view(np.float32)
+        _check(lib().dvbs2fec_submit_plframe(self._h, _ptr(x), x.size // 2, tag))
+
+    def collect(self, max_frames, timeout_us=0):
+        bb = np.zeros((max_frames, self.kbch // 8), np.uint8)
+        res = np.zeros(max_frames, RESULT_DTYPE)
+        n = _check(lib().dvbs2fec_collect(self._h, _ptr(bb), _ptr(res), max_frames, timeout_us))
+        return bb[:n], res[:n]
+
+    def flush(self):
+        _check(lib().dvbs2fec_flush(self._h))
+
+
+class _StageObject:
+    """Common part of the per-stage mirrors: each owns a decoder configured for (framesize, rate)."""
+
+    # first MODCOD that uses a given rate (any constellation gives the same FEC objects)
+    _MODCOD_OF_RATE = {0: 1, 1: 2, 2: 3, 3: 4, 4: 5, 5: 6, 6: 7, 7: 8, 8: 9, 10: 10, 11: 11}
+
+    def __init__(self, framesize_short, rate, decoder=None, max_trials=25):
+        if rate not in self._MODCOD_OF_RATE:
+            raise DVBS2FecError(EINVAL, "code rate %r has no DVB-S2 LDPC table" % (rate,))
+        self.dec = decoder or DVBS2Decoder(max_trials=max_trials)
+        self.dec.setDemodParams(self._MODCOD_OF_RATE[rate], bool(framesize_short), False)
+
+
+class BBFrameLDPC(_StageObject):
+    """codings/bbframe_ldpc.h:32-60"""
+
+    def dataSize(self):
+        return self.dec.K
+
+    def decode(self, frame, max_trials):
+        """frame: N int8 LLRs, replaced in place by the posterior LLRs; returns iterations or -1."""
+        f = frame.reshape(1, -1)
+        return int(self.dec.ldpc_decode(f, max_trials)[0])
+
+
+class BBFrameBCH(_StageObject):
+    """codings/bbframe_bch.h:33-88"""
+
+    def dataSize(self):
+        return self.dec.kbch
+
+    def decode(self, frame):
+        """frame: K_ldpc/8 bytes corrected in place; returns corrections or -1."""
+        return int(self.dec.bch_decode(frame.reshape(1, -1))[0])
+
+
+class BBFrameDescrambler(_StageObject):
+    """codings/bbframe_descramble.h:28-44"""
+
+    def work(self, frame):
+        self.dec.descramble(frame.reshape(1, -1))
+        return 0
+
+
+class S2BBToSoft:
+    """dvbs2/dvbs2_bb_to_soft.h:16-48: PLFRAME symbols -> deinterleaved int8 LLRs."""
+
+    def __init__(self, modcod, shortframes=False, pilots=False, decoder=None):
+        self.dec = decoder or DVBS2Decoder()
+        self.dec.setDemodParams(modcod, shortframes, pilots)
+
+    def process(self, plframe):
+        return self.dec.bb_to_soft(plframe)[0]

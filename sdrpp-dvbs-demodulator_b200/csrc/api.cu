@@ -1,0 +1,798 @@
+// C ABI of libdvbs2fec.so (include/dvbs2fec.h): handle, per-GPU contexts, the frame-batching
+// queue and the by-frame multi-GPU dispatcher.  Everything that computes runs in the CUDA kernels
+// (ldpc_decoder.cu, bch_decoder.cu, demapper.cu); there is no CPU fallback -- without a device every
+// compute entry point returns DVBS2FEC_ENODEV.
+#include "../../include/dvbs2fec.h"
+
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "bch_decoder.cuh"
+#include "demapper.cuh"
+#include "host_tables.h"
+#include "ldpc_decoder.cuh"
+#include "s2_codes.h"
+
+using namespace s2;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(DVBS2FEC_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kSlots = 2;  // double buffering per device: copy of batch k+1 overlaps kernels of batch k
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf<int8_t> llr;
+    DevBuf<float> sym;
+    DevBuf<uint8_t> hard;
+    DevBuf<int16_t> iters;
+    DevBuf<int16_t> corr;
+    DevBuf<uint8_t> bb;
+    DevBuf<dvbs2fec_result> res;
+    DevBuf<uint8_t> workspace;
+    DevBuf<unsigned int> counter;
+    PinBuf<uint8_t> h_in;
+    PinBuf<uint8_t> h_bb;
+    PinBuf<dvbs2fec_result> h_res;
+    // pending copy-out of a staged batch
+    uint8_t* user_bb = nullptr;
+    dvbs2fec_result* user_res = nullptr;
+    int pending = 0;
+    uint64_t tag_base = 0;
+};
+
+struct CodeDev {  // per (device, LDPC code)
+    DevBuf<uint8_t> row_level;
+};
+struct BchTabDev {
+    DevBuf<uint16_t> crc, basis;
+};
+
+struct DevCtx {
+    int device = 0;
+    int sms = 0;
+    Slot slot[kSlots];
+    std::map<int, CodeDev> codes;
+    std::map<int, BchTabDev> bch;           // key m*100+t
+    DevBuf<uint16_t> gf_log[2], gf_exp[2];  // [0]: m=14, [1]: m=16
+    DevBuf<uint8_t> prbs;
+    std::map<int, DevBuf<uint32_t>> luts;   // key modcod constellation/gamma: modcod number
+    // current configuration
+    LdpcDev ldpc{};
+    BchDev bchd{};
+    DemapDev demap{};
+    int grid = 0;
+};
+
+}  // namespace
+
+struct dvbs2fec_handle {
+    dvbs2fec_config cfg{};
+    std::vector<std::unique_ptr<DevCtx>> devs;
+    ModcodCfg mc{};
+    const LdpcCode* code = nullptr;
+    int max_trials = 25;
+    int hard_stride = 0;
+    int plsyms = 0;
+    int last_launches = 0;
+    bool configured = false;
+    // host copies of the layer tables referenced by LdpcDev (host pointers)
+    std::vector<uint32_t> h_links;
+    // ---- queue
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::thread worker;
+    bool stop = false, flush_req = false, busy = false;
+    std::vector<int8_t> q_llr;          // pending LLR frames
+    std::vector<float> q_sym;           // pending PLFRAMEs
+    std::vector<uint64_t> q_tags;
+    bool q_is_sym = false;
+    std::chrono::steady_clock::time_point q_first;
+    struct Done {
+        std::vector<uint8_t> bb;
+        dvbs2fec_result r;
+    };
+    std::deque<Done> done;
+};
+
+namespace {
+
+int setup_device_tables(dvbs2fec_handle* h, DevCtx& d) {
+    CU(cudaSetDevice(d.device));
+    const LdpcCode& c = *h->code;
+    // --- LDPC
+    CodeDev& cd = d.codes[c.index];
+    if (!cd.row_level.p) {
+        CU(cd.row_level.reserve(c.row_level.size()));
+        CU(cudaMemcpy(cd.row_level.p, c.row_level.data(), c.row_level.size(), cudaMemcpyHostToDevice));
+    }
+    LdpcDev& L = d.ldpc;
+    L.N = c.N; L.K = c.K; L.R = c.R; L.q = c.q;
+    L.ngroups = c.K / kGroup;
+    L.max_cnt = c.max_cnt;
+    L.sg = ldpc_slot_groups(c.max_cnt);
+    if (!L.sg) return fail(DVBS2FEC_EINVAL, "no LDPC kernel for %d links per row", c.max_cnt);
+    L.links = h->h_links.data();
+    L.layer_off = c.layer_off.data();
+    L.layer_nlev = c.layer_nlev.data();
+    L.row_level = cd.row_level.p;
+    int per_sm = ldpc_max_ctas_per_sm(L);
+    if (per_sm <= 0) return fail(DVBS2FEC_ENODEV, "LDPC kernel does not fit on device %d (%s)", d.device,
+                                 cudaGetErrorString(cudaGetLastError()));
+    d.grid = d.sms * per_sm;
+    // --- BCH
+    const int m = c.bch_m, t = c.bch_t, fi = (m == 16);
+    const GfHost& gf = gf_host(m);
+    if (!d.gf_log[fi].p) {
+        CU(d.gf_log[fi].reserve(gf.log.size()));
+        CU(d.gf_exp[fi].reserve(gf.exp.size()));
+        CU(cudaMemcpy(d.gf_log[fi].p, gf.log.data(), gf.log.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.gf_exp[fi].p, gf.exp.data(), gf.exp.size() * 2, cudaMemcpyHostToDevice));
+    }
+    BchTabDev& bt = d.bch[m * 100 + t];
+    if (!bt.crc.p) {
+        const BchHost& bh = bch_host(m, t);
+        CU(bt.crc.reserve(bh.crc.size()));
+        CU(bt.basis.reserve(bh.basis.size()));
+        CU(cudaMemcpy(bt.crc.p, bh.crc.data(), bh.crc.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(bt.basis.p, bh.basis.data(), bh.basis.size() * 2, cudaMemcpyHostToDevice));
+    }
+    if (!d.prbs.p) {
+        const auto& seq = bb_prbs();
+        CU(d.prbs.reserve(seq.size()));
+        CU(cudaMemcpy(d.prbs.p, seq.data(), seq.size(), cudaMemcpyHostToDevice));
+    }
+    BchDev& B = d.bchd;
+    B.gf.m = m; B.gf.N = gf.N; B.gf.log = d.gf_log[fi].p; B.gf.exp = d.gf_exp[fi].p;
+    B.t = t; B.nbch = c.K; B.kbch = c.kbch;
+    B.prefix = gf.N - c.K;
+    B.crc = bt.crc.p; B.basis = bt.basis.p; B.prbs = d.prbs.p;
+    // --- demapper
+    const ModcodCfg& mc = h->mc;
+    DemapDev& D = d.demap;
+    ConstellationHost ch = make_constellation(mc.constellation, mc.g1, mc.g2);
+    D.constellation = (int)mc.constellation;
+    D.bits = mc.bits;
+    D.N = c.N;
+    D.nsym = c.N / mc.bits;
+    D.reversed_cols = (mc.constellation == PSK8 && mc.rate == R3_5);
+    D.pilots = mc.pilots;
+    D.plframe_syms = h->plsyms;
+    D.amp = ch.amp; D.prescale = ch.prescale; D.sca = ch.sca;
+    for (int i = 0; i < 32; ++i) {
+        D.pts[2 * i] = i < ch.states ? ch.re[i] : 0.f;
+        D.pts[2 * i + 1] = i < ch.states ? ch.im[i] : 0.f;
+    }
+    D.lut = nullptr;
+    if (mc.constellation != APSK32) {
+        int key = (mc.constellation == APSK16) ? mc.modcod : (int)mc.constellation;  // 16APSK: one LUT per gamma
+        DevBuf<uint32_t>& lut = d.luts[key];
+        if (!lut.p) {
+            std::vector<uint32_t> tab = demap_lut(ch);
+            CU(lut.reserve(tab.size()));
+            CU(cudaMemcpy(lut.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        }
+        D.lut = lut.p;
+    }
+    return 0;
+}
+
+int reserve_slot(dvbs2fec_handle* h, DevCtx& d, Slot& s, int nframes, bool with_sym, bool host_staging) {
+    const LdpcCode& c = *h->code;
+    CU(cudaSetDevice(d.device));
+    CU(s.llr.reserve((size_t)nframes * c.N));
+    if (with_sym) CU(s.sym.reserve((size_t)nframes * h->plsyms * 2));
+    CU(s.hard.reserve((size_t)nframes * h->hard_stride));
+    CU(s.iters.reserve(nframes));
+    CU(s.corr.reserve(nframes));
+    CU(s.bb.reserve((size_t)nframes * (c.kbch / 8)));
+    CU(s.res.reserve(nframes));
+    CU(s.workspace.reserve((size_t)d.grid * ldpc_workspace_bytes(d.ldpc)));
+    CU(s.counter.reserve(1));
+    if (host_staging) {
+        size_t in_bytes = with_sym ? (size_t)nframes * h->plsyms * 8 : (size_t)nframes * c.N;
+        CU(s.h_in.reserve(in_bytes));
+        CU(s.h_bb.reserve((size_t)nframes * (c.kbch / 8)));
+        CU(s.h_res.reserve(nframes));
+    }
+    return 0;
+}
+
+// enqueue demap (optional) + LDPC + BCH/descramble for n frames already on the device
+int enqueue_chain(dvbs2fec_handle* h, DevCtx& d, Slot& s, const float* d_sym, const int8_t* d_llr, int n,
+                  uint8_t* d_bb, dvbs2fec_result* d_res, cudaStream_t st, int* launches, uint64_t tag_base = 0) {
+    const int8_t* llr = d_llr;
+    if (d_sym) {
+        int e = demap_launch(d.demap, d_sym, n, s.llr.p, st);
+        if (e) return fail(DVBS2FEC_ECUDA, "demap launch: %s", cudaGetErrorString((cudaError_t)e));
+        llr = s.llr.p;
+        ++*launches;
+    }
+    CU(cudaMemsetAsync(s.counter.p, 0, sizeof(unsigned int), st));
+    LdpcArgs la{};
+    la.code = d.ldpc;
+    la.llr_in = llr;
+    la.nframes = n;
+    la.max_trials = h->max_trials;
+    la.hard_out = s.hard.p;
+    la.hard_stride = h->hard_stride;
+    la.iters_out = s.iters.p;
+    la.llr_out = nullptr;
+    la.workspace = s.workspace.p;
+    la.work_counter = s.counter.p;
+    int grid = std::min(d.grid, (n + 1) / 2);
+    int e = ldpc_launch(la, grid, st);
+    if (e) return fail(DVBS2FEC_ECUDA, "ldpc launch: %s", cudaGetErrorString((cudaError_t)e));
+    ++*launches;
+    BchArgs ba{};
+    ba.code = d.bchd;
+    ba.hard = s.hard.p;
+    ba.hard_stride = h->hard_stride;
+    ba.nframes = n;
+    ba.ldpc_iters = s.iters.p;
+    ba.tags = nullptr;
+    ba.tag_base = tag_base;
+    ba.bb_out = d_bb;
+    ba.results = d_res;
+    ba.corr_out = nullptr;
+    ba.descramble = 1;
+    e = bch_launch(ba, st);
+    if (e) return fail(DVBS2FEC_ECUDA, "bch launch: %s", cudaGetErrorString((cudaError_t)e));
+    ++*launches;
+    return 0;
+}
+
+int finish_slot(dvbs2fec_handle* h, Slot& s) {
+    if (!s.pending) return 0;
+    CU(cudaEventSynchronize(s.done));
+    const size_t kb = h->code->kbch / 8;
+    if (s.user_bb && s.user_bb != s.h_bb.p) memcpy(s.user_bb, s.h_bb.p, (size_t)s.pending * kb);
+    if (s.user_res) {
+        for (int i = 0; i < s.pending; ++i) {
+            s.user_res[i] = s.h_res.p[i];
+            s.user_res[i].tag = s.tag_base + i;
+        }
+    }
+    s.pending = 0;
+    return 0;
+}
+
+// frames [0, n) of one device's share, host buffers in and out
+int run_device_share(dvbs2fec_handle* h, DevCtx& d, const int8_t* llr, const float* sym, int n, uint8_t* bb,
+                     dvbs2fec_result* res, uint64_t tag0, int* launches) {
+    if (n <= 0) return 0;
+    CU(cudaSetDevice(d.device));
+    const LdpcCode& c = *h->code;
+    const size_t kb = c.kbch / 8;
+    const size_t in_frame_bytes = sym ? (size_t)h->plsyms * 8 : (size_t)c.N;
+    const uint8_t* in = sym ? reinterpret_cast<const uint8_t*>(sym) : reinterpret_cast<const uint8_t*>(llr);
+    const int chunk = std::min(h->cfg.max_batch, n);
+    for (int k = 0; k < kSlots; ++k) {
+        int rc = reserve_slot(h, d, d.slot[k], chunk, sym != nullptr, true);
+        if (rc) return rc;
+    }
+    int which = 0, rc = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, which ^= 1) {
+        Slot& s = d.slot[which];
+        const int m = std::min(chunk, n - f0);
+        if ((rc = finish_slot(h, s))) return rc;
+        // stage through pinned memory (the caller's buffers are ordinary pageable memory)
+        memcpy(s.h_in.p, in + (size_t)f0 * in_frame_bytes, (size_t)m * in_frame_bytes);
+        void* dst = sym ? (void*)s.sym.p : (void*)s.llr.p;
+        CU(cudaMemcpyAsync(dst, s.h_in.p, (size_t)m * in_frame_bytes, cudaMemcpyHostToDevice, s.stream));
+        rc = enqueue_chain(h, d, s, sym ? s.sym.p : nullptr, sym ? nullptr : s.llr.p, m, s.bb.p, s.res.p, s.stream,
+                           launches);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(s.h_bb.p, s.bb.p, (size_t)m * kb, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_res.p, s.res.p, (size_t)m * sizeof(dvbs2fec_result), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaEventRecord(s.done, s.stream));
+        s.user_bb = bb ? bb + (size_t)f0 * kb : nullptr;
+        s.user_res = res ? res + f0 : nullptr;
+        s.tag_base = tag0 + f0;
+        s.pending = m;
+    }
+    for (int k = 0; k < kSlots; ++k)
+        if ((rc = finish_slot(h, d.slot[k]))) return rc;
+    return 0;
+}
+
+int decode_host(dvbs2fec_handle* h, const int8_t* llr, const float* sym, int n, uint8_t* bb, dvbs2fec_result* res) {
+    if (!h || !h->configured) return fail(DVBS2FEC_EINVAL, "set_modcod has not been called");
+    if (n < 0 || (!llr && !sym)) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (h->devs.empty()) return fail(DVBS2FEC_ENODEV, "no CUDA device");
+    const int nd = (int)h->devs.size();
+    const size_t kb = h->code->kbch / 8;
+    const size_t in_stride = sym ? (size_t)h->plsyms * 2 : (size_t)h->code->N;
+    h->last_launches = 0;
+    if (nd == 1) {
+        int launches = 0;
+        int rc = run_device_share(h, *h->devs[0], llr, sym, n, bb, res, 0, &launches);
+        h->last_launches = launches;
+        return rc;
+    }
+    // by-frame sharding: contiguous shares, one host thread per GPU, no cross-GPU exchange
+    std::vector<std::thread> th;
+    std::vector<int> rcs(nd, 0), ln(nd, 0);
+    std::vector<std::string> errs(nd);
+    int per = (n + nd - 1) / nd;
+    for (int k = 0; k < nd; ++k) {
+        int f0 = std::min(n, k * per), f1 = std::min(n, f0 + per);
+        th.emplace_back([=, &rcs, &ln, &errs] {
+            rcs[k] = run_device_share(h, *h->devs[k], llr ? llr + (size_t)f0 * in_stride : nullptr,
+                                      sym ? sym + (size_t)f0 * in_stride : nullptr, f1 - f0,
+                                      bb ? bb + (size_t)f0 * kb : nullptr, res ? res + f0 : nullptr, (uint64_t)f0, &ln[k]);
+            if (rcs[k]) errs[k] = g_err;
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int k = 0; k < nd; ++k) {
+        h->last_launches += ln[k];
+        if (rcs[k]) return fail(rcs[k], "device %d: %s", h->devs[k]->device, errs[k].c_str());
+    }
+    return 0;
+}
+
+void worker_main(dvbs2fec_handle* h) {
+    std::unique_lock<std::mutex> lk(h->mu);
+    for (;;) {
+        const size_t batch = (size_t)h->cfg.max_batch * h->devs.size();
+        while (!h->stop) {
+            size_t pending = h->q_tags.size();
+            if (pending >= batch || (pending && h->flush_req)) break;
+            if (pending) {
+                auto deadline = h->q_first + std::chrono::microseconds(h->cfg.max_latency_us);
+                if (std::chrono::steady_clock::now() >= deadline) break;
+                h->cv_work.wait_until(lk, deadline);
+            } else {
+                h->flush_req = false;
+                h->cv_done.notify_all();
+                h->cv_work.wait(lk);
+            }
+        }
+        if (h->stop) return;
+        std::vector<int8_t> llr;
+        std::vector<float> sym;
+        std::vector<uint64_t> tags;
+        llr.swap(h->q_llr);
+        sym.swap(h->q_sym);
+        tags.swap(h->q_tags);
+        const bool is_sym = h->q_is_sym;
+        h->busy = true;
+        lk.unlock();
+        const int n = (int)tags.size();
+        const size_t kb = h->code->kbch / 8;
+        std::vector<uint8_t> bb((size_t)n * kb);
+        std::vector<dvbs2fec_result> res(n);
+        int rc = decode_host(h, is_sym ? nullptr : llr.data(), is_sym ? sym.data() : nullptr, n, bb.data(), res.data());
+        lk.lock();
+        for (int i = 0; i < n; ++i) {
+            dvbs2fec_handle::Done d;
+            d.bb.assign(bb.begin() + (size_t)i * kb, bb.begin() + (size_t)(i + 1) * kb);
+            d.r = res[i];
+            d.r.tag = tags[i];
+            if (rc) {
+                d.r.ldpc_iters = -1;
+                d.r.bch_corr = -1;
+                d.r.flags = DVBS2FEC_FLAG_LDPC_FAIL | DVBS2FEC_FLAG_BCH_FAIL;
+            }
+            h->done.push_back(std::move(d));
+        }
+        h->busy = false;
+        h->cv_done.notify_all();
+    }
+}
+
+void drain_queue(dvbs2fec_handle* h) {
+    std::unique_lock<std::mutex> lk(h->mu);
+    if (!h->worker.joinable()) return;
+    h->flush_req = true;
+    h->cv_work.notify_all();
+    h->cv_done.wait(lk, [h] { return h->q_tags.empty() && !h->busy; });
+    h->flush_req = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dvbs2fec_last_error(void) { return g_err; }
+
+int dvbs2fec_create(const dvbs2fec_config* cfg, dvbs2fec_handle** out) {
+    if (!out) return fail(DVBS2FEC_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(DVBS2FEC_ENODEV, "no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    std::unique_ptr<dvbs2fec_handle> h(new dvbs2fec_handle());
+    if (cfg) h->cfg = *cfg;
+    if (h->cfg.max_batch <= 0) h->cfg.max_batch = 1024;
+    if (h->cfg.max_latency_us <= 0) h->cfg.max_latency_us = 2000;
+    if (h->cfg.max_trials <= 0) h->cfg.max_trials = 25;
+    h->max_trials = h->cfg.max_trials;
+    std::vector<int> ids;
+    if (h->cfg.n_devices <= 0) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        ids.push_back(cur);
+    } else {
+        for (int i = 0; i < h->cfg.n_devices && i < 8; ++i) ids.push_back(h->cfg.devices[i]);
+    }
+    for (int id : ids) {
+        if (id < 0 || id >= ndev) return fail(DVBS2FEC_EINVAL, "device %d out of range (%d present)", id, ndev);
+        std::unique_ptr<DevCtx> d(new DevCtx());
+        d->device = id;
+        CU(cudaSetDevice(id));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, id));
+        if (prop.major < 10)
+            return fail(DVBS2FEC_ENODEV, "device %d is sm_%d%d; this library carries sm_100a code only", id, prop.major,
+                        prop.minor);
+        d->sms = prop.multiProcessorCount;
+        for (int k = 0; k < kSlots; ++k) {
+            CU(cudaStreamCreateWithFlags(&d->slot[k].stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&d->slot[k].done, cudaEventDisableTiming));
+        }
+        h->devs.push_back(std::move(d));
+    }
+    *out = h.release();
+    return 0;
+}
+
+void dvbs2fec_destroy(dvbs2fec_handle* h) {
+    if (!h) return;
+    {
+        std::unique_lock<std::mutex> lk(h->mu);
+        h->stop = true;
+        h->cv_work.notify_all();
+    }
+    if (h->worker.joinable()) h->worker.join();
+    for (auto& dp : h->devs) {
+        DevCtx& d = *dp;
+        cudaSetDevice(d.device);
+        for (int k = 0; k < kSlots; ++k) {
+            Slot& s = d.slot[k];
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.llr.release(); s.sym.release(); s.hard.release(); s.iters.release(); s.corr.release();
+            s.bb.release(); s.res.release(); s.workspace.release(); s.counter.release();
+            s.h_in.release(); s.h_bb.release(); s.h_res.release();
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+        for (auto& kv : d.codes) kv.second.row_level.release();
+        for (auto& kv : d.bch) { kv.second.crc.release(); kv.second.basis.release(); }
+        for (auto& kv : d.luts) kv.second.release();
+        for (int i = 0; i < 2; ++i) { d.gf_log[i].release(); d.gf_exp[i].release(); }
+        d.prbs.release();
+    }
+    delete h;
+}
+
+int dvbs2fec_set_modcod(dvbs2fec_handle* h, int modcod, int shortframes, int pilots, int max_trials) {
+    if (!h) return fail(DVBS2FEC_EINVAL, "handle is NULL");
+    ModcodCfg mc;
+    if (!modcod_config(modcod, shortframes != 0, pilots != 0, &mc))
+        return fail(DVBS2FEC_EINVAL, "MODCOD %d is outside 1..28", modcod);
+    if (mc.code < 0)
+        return fail(DVBS2FEC_EINVAL, "MODCOD %d has no %s-frame LDPC code in EN 302 307", modcod,
+                    shortframes ? "short" : "normal");
+    drain_queue(h);
+    h->mc = mc;
+    h->code = &ldpc_code(mc.code);
+    if (max_trials > 0) h->max_trials = max_trials;
+    h->hard_stride = ((h->code->K / 8) + 15) & ~15;
+    const int nsym = h->code->N / mc.bits;
+    h->plsyms = 90 + nsym + (mc.pilots ? 36 * ((nsym - 1) / 1440) : 0);
+    h->h_links.clear();
+    for (const LayerLink& l : h->code->links) h->h_links.push_back(((uint32_t)l.group << 16) | l.shift);
+    for (auto& d : h->devs) {
+        int rc = setup_device_tables(h, *d);
+        if (rc) return rc;
+    }
+    h->configured = true;
+    return 0;
+}
+
+int dvbs2fec_kbch(const dvbs2fec_handle* h) { return (h && h->configured) ? h->code->kbch : DVBS2FEC_EINVAL; }
+int dvbs2fec_kldpc(const dvbs2fec_handle* h) { return (h && h->configured) ? h->code->K : DVBS2FEC_EINVAL; }
+int dvbs2fec_nldpc(const dvbs2fec_handle* h) { return (h && h->configured) ? h->code->N : DVBS2FEC_EINVAL; }
+int dvbs2fec_plframe_symbols(const dvbs2fec_handle* h) { return (h && h->configured) ? h->plsyms : DVBS2FEC_EINVAL; }
+int dvbs2fec_last_launch_count(const dvbs2fec_handle* h) { return h ? h->last_launches : 0; }
+
+int dvbs2fec_bb_to_soft(dvbs2fec_handle* h, const float* plframes, int n, int8_t* llr_out) {
+    if (!h || !h->configured || !plframes || !llr_out || n < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    DevCtx& d = *h->devs[0];
+    Slot& s = d.slot[0];
+    int rc = reserve_slot(h, d, s, n, true, false);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s.sym.p, plframes, (size_t)n * h->plsyms * 8, cudaMemcpyHostToDevice, s.stream));
+    int e = demap_launch(d.demap, s.sym.p, n, s.llr.p, s.stream);
+    if (e) return fail(DVBS2FEC_ECUDA, "demap launch: %s", cudaGetErrorString((cudaError_t)e));
+    CU(cudaMemcpyAsync(llr_out, s.llr.p, (size_t)n * h->code->N, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+int dvbs2fec_ldpc_decode(dvbs2fec_handle* h, int8_t* frames, int n, int max_trials, int16_t* iters) {
+    if (!h || !h->configured || !frames || n < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    DevCtx& d = *h->devs[0];
+    Slot& s = d.slot[0];
+    int rc = reserve_slot(h, d, s, n, false, false);
+    if (rc) return rc;
+    const size_t bytes = (size_t)n * h->code->N;
+    CU(cudaMemcpyAsync(s.llr.p, frames, bytes, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemsetAsync(s.counter.p, 0, sizeof(unsigned int), s.stream));
+    LdpcArgs la{};
+    la.code = d.ldpc;
+    la.llr_in = s.llr.p;
+    la.nframes = n;
+    la.max_trials = max_trials > 0 ? max_trials : h->max_trials;
+    la.hard_out = s.hard.p;
+    la.hard_stride = h->hard_stride;
+    la.iters_out = s.iters.p;
+    la.llr_out = s.llr.p;  // in place, like BBFrameLDPC::decode
+    la.workspace = s.workspace.p;
+    la.work_counter = s.counter.p;
+    int e = ldpc_launch(la, std::min(d.grid, (n + 1) / 2), s.stream);
+    if (e) return fail(DVBS2FEC_ECUDA, "ldpc launch: %s", cudaGetErrorString((cudaError_t)e));
+    CU(cudaMemcpyAsync(frames, s.llr.p, bytes, cudaMemcpyDeviceToHost, s.stream));
+    if (iters) CU(cudaMemcpyAsync(iters, s.iters.p, (size_t)n * 2, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+int dvbs2fec_bch_decode(dvbs2fec_handle* h, uint8_t* frames, int n, int16_t* corrections) {
+    if (!h || !h->configured || !frames || n < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    DevCtx& d = *h->devs[0];
+    Slot& s = d.slot[0];
+    int rc = reserve_slot(h, d, s, n, false, false);
+    if (rc) return rc;
+    const size_t nb = h->code->K / 8;
+    CU(cudaMemsetAsync(s.hard.p, 0, (size_t)n * h->hard_stride, s.stream));
+    CU(cudaMemcpy2DAsync(s.hard.p, h->hard_stride, frames, nb, nb, n, cudaMemcpyHostToDevice, s.stream));
+    BchArgs ba{};
+    ba.code = d.bchd;
+    ba.hard = s.hard.p;
+    ba.hard_stride = h->hard_stride;
+    ba.nframes = n;
+    ba.corr_out = s.corr.p;
+    int e = bch_launch(ba, s.stream);
+    if (e) return fail(DVBS2FEC_ECUDA, "bch launch: %s", cudaGetErrorString((cudaError_t)e));
+    CU(cudaMemcpy2DAsync(frames, nb, s.hard.p, h->hard_stride, nb, n, cudaMemcpyDeviceToHost, s.stream));
+    if (corrections) CU(cudaMemcpyAsync(corrections, s.corr.p, (size_t)n * 2, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+int dvbs2fec_descramble(dvbs2fec_handle* h, uint8_t* frames, int stride, int n) {
+    if (!h || !h->configured || !frames || n < 0 || stride < h->code->kbch / 8) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    DevCtx& d = *h->devs[0];
+    Slot& s = d.slot[0];
+    CU(cudaSetDevice(d.device));
+    CU(s.bb.reserve((size_t)n * stride));
+    CU(cudaMemcpyAsync(s.bb.p, frames, (size_t)n * stride, cudaMemcpyHostToDevice, s.stream));
+    int e = descramble_launch(s.bb.p, stride, n, h->code->kbch, d.prbs.p, s.stream);
+    if (e) return fail(DVBS2FEC_ECUDA, "descramble launch: %s", cudaGetErrorString((cudaError_t)e));
+    CU(cudaMemcpyAsync(frames, s.bb.p, (size_t)n * stride, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+int dvbs2fec_decode_batch(dvbs2fec_handle* h, const int8_t* llr, int n, uint8_t* bb_out, dvbs2fec_result* results) {
+    return decode_host(h, llr, nullptr, n, bb_out, results);
+}
+int dvbs2fec_decode_plframes(dvbs2fec_handle* h, const float* plframes, int n, uint8_t* bb_out,
+                             dvbs2fec_result* results) {
+    return decode_host(h, nullptr, plframes, n, bb_out, results);
+}
+
+int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n, uint8_t* d_bb_out,
+                                 dvbs2fec_result* d_results, void* cuda_stream) {
+    if (!h || !h->configured || !d_llr || n < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    DevCtx& d = *h->devs[0];
+    Slot& s = d.slot[0];
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int chunk = std::min(n, std::max(h->cfg.max_batch, 1));
+    int rc = reserve_slot(h, d, s, chunk, false, false);
+    if (rc) return rc;
+    const size_t kb = h->code->kbch / 8;
+    h->last_launches = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk) {
+        int m = std::min(chunk, n - f0);
+        rc = enqueue_chain(h, d, s, nullptr, d_llr + (size_t)f0 * h->code->N, m, d_bb_out ? d_bb_out + (size_t)f0 * kb : nullptr,
+                           d_results ? d_results + f0 : nullptr, st, &h->last_launches, (uint64_t)f0);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym, uint64_t tag) {
+    if (!h || !h->configured) return fail(DVBS2FEC_EINVAL, "set_modcod has not been called");
+    std::unique_lock<std::mutex> lk(h->mu);
+    if (!h->worker.joinable()) h->worker = std::thread(worker_main, h);
+    const bool is_sym = sym != nullptr;
+    if (!h->q_tags.empty() && h->q_is_sym != is_sym) {  // mixed kinds: push the pending ones through first
+        lk.unlock();
+        drain_queue(h);
+        lk.lock();
+    }
+    if (h->q_tags.size() >= (size_t)h->cfg.max_batch * h->devs.size() * 4) return fail(DVBS2FEC_EAGAIN, "queue full");
+    if (h->q_tags.empty()) h->q_first = std::chrono::steady_clock::now();
+    h->q_is_sym = is_sym;
+    if (is_sym)
+        h->q_sym.insert(h->q_sym.end(), sym, sym + (size_t)h->plsyms * 2);
+    else
+        h->q_llr.insert(h->q_llr.end(), llr, llr + h->code->N);
+    h->q_tags.push_back(tag);
+    h->cv_work.notify_all();
+    return 0;
+}
+
+int dvbs2fec_submit_llr(dvbs2fec_handle* h, const int8_t* llr, uint64_t tag) {
+    if (!llr) return fail(DVBS2FEC_EINVAL, "llr is NULL");
+    return submit_common(h, llr, nullptr, tag);
+}
+int dvbs2fec_submit_plframe(dvbs2fec_handle* h, const float* plframe, int nsym, uint64_t tag) {
+    if (!plframe || !h || !h->configured || nsym != h->plsyms)
+        return fail(DVBS2FEC_EINVAL, "plframe must hold dvbs2fec_plframe_symbols() complex samples");
+    return submit_common(h, nullptr, plframe, tag);
+}
+
+int dvbs2fec_collect(dvbs2fec_handle* h, uint8_t* bb_out, dvbs2fec_result* results, int max, int timeout_us) {
+    if (!h || !h->configured || max < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    std::unique_lock<std::mutex> lk(h->mu);
+    if (h->done.empty() && timeout_us != 0) {
+        auto ready = [h] { return !h->done.empty(); };
+        if (timeout_us < 0)
+            h->cv_done.wait(lk, ready);
+        else
+            h->cv_done.wait_for(lk, std::chrono::microseconds(timeout_us), ready);
+    }
+    int n = 0;
+    const size_t kb = h->code->kbch / 8;
+    while (n < max && !h->done.empty()) {
+        auto& d = h->done.front();
+        if (bb_out) memcpy(bb_out + (size_t)n * kb, d.bb.data(), std::min(kb, d.bb.size()));
+        if (results) results[n] = d.r;
+        h->done.pop_front();
+        ++n;
+    }
+    return n;
+}
+
+int dvbs2fec_flush(dvbs2fec_handle* h) {
+    if (!h) return fail(DVBS2FEC_EINVAL, "handle is NULL");
+    drain_queue(h);
+    return 0;
+}
+
+void* dvbs2fec_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void dvbs2fec_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits) {
+    ModcodCfg mc;
+    if (!bbframe || !code_bits || !modcod_config(modcod, shortframes != 0, false, &mc) || mc.code < 0)
+        return fail(DVBS2FEC_EINVAL, "unsupported MODCOD/frame size");
+    const LdpcCode& c = ldpc_code(mc.code);
+    std::vector<uint8_t> frame(c.K / 8, 0);
+    const auto& prbs = bb_prbs();
+    for (int i = 0; i < c.kbch / 8; ++i) frame[i] = bbframe[i] ^ prbs[i];
+    bch_encode(bch_host(c.bch_m, c.bch_t), frame.data(), c.kbch);
+    std::vector<uint8_t> bits(c.K);
+    for (int i = 0; i < c.K; ++i) bits[i] = (frame[i >> 3] >> (7 - (i & 7))) & 1;
+    ldpc_encode_bits(mc.code, bits.data(), code_bits);
+    return 0;
+}
+
+int dvbs2fec_modulate(int modcod, int shortframes, int pilots, const uint8_t* code_bits, float* plframe) {
+    ModcodCfg mc;
+    if (!code_bits || !plframe || !modcod_config(modcod, shortframes != 0, pilots != 0, &mc) || mc.code < 0)
+        return fail(DVBS2FEC_EINVAL, "unsupported MODCOD/frame size");
+    const LdpcCode& c = ldpc_code(mc.code);
+    ConstellationHost ch = make_constellation(mc.constellation, mc.g1, mc.g2);
+    const int nsym = c.N / mc.bits;
+    const int total = 90 + nsym + (mc.pilots ? 36 * ((nsym - 1) / 1440) : 0);
+    memset(plframe, 0, (size_t)total * 8);
+    std::vector<uint8_t> tx(c.N);
+    for (int n = 0; n < c.N; ++n) tx[interleaved_position(mc, n)] = code_bits[n] & 1;
+    for (int s = 0; s < nsym; ++s) {
+        int raw = 90 + s + (mc.pilots ? 36 * (s / 1440) : 0);
+        map_symbol(ch, &tx[(size_t)s * mc.bits], &plframe[2 * raw]);
+    }
+    return 0;
+}
+
+int dvbs2fec_modcod_info(int modcod, int shortframes, int pilots, int* nldpc, int* kldpc, int* kbch, int* bch_t,
+                         int* bits_per_symbol, int* plframe_symbols, int* links_total) {
+    ModcodCfg mc;
+    if (!modcod_config(modcod, shortframes != 0, pilots != 0, &mc) || mc.code < 0)
+        return fail(DVBS2FEC_EINVAL, "unsupported MODCOD/frame size");
+    const LdpcCode& c = ldpc_code(mc.code);
+    const int nsym = c.N / mc.bits;
+    if (nldpc) *nldpc = c.N;
+    if (kldpc) *kldpc = c.K;
+    if (kbch) *kbch = c.kbch;
+    if (bch_t) *bch_t = c.bch_t;
+    if (bits_per_symbol) *bits_per_symbol = mc.bits;
+    if (plframe_symbols) *plframe_symbols = 90 + nsym + (mc.pilots ? 36 * ((nsym - 1) / 1440) : 0);
+    if (links_total) *links_total = c.links_total;
+    return 0;
+}
+
+}  // extern "C"

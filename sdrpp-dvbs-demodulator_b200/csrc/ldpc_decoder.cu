@@ -1,0 +1,453 @@
+// K2 -- see ldpc_decoder.cuh for the design.  Reference semantics: SURVEY.md spec S-LDPC
+// (layered_decoder.hh:23-74,121-133; algorithms.hh:235-256,261-276; bbframe_ldpc.cpp:123-139).
+#include "ldpc_decoder.cuh"
+
+#include <cstdio>
+
+namespace s2 {
+namespace {
+
+// Layer tables ride in the kernel parameter (constant bank): uniform, indexed by layer.
+constexpr int kMaxLinks = 656;   // B5 (n3/5) has 648 table entries, the largest
+constexpr int kMaxLayers = 136;  // B1 (n1/4) has q = 135
+struct LdpcParams {
+    int N, K, R, q, ngroups, sg;
+    int nframes, max_trials, hard_stride, pad_;
+    const int8_t* llr_in;
+    uint8_t* hard_out;
+    int16_t* iters_out;
+    int8_t* llr_out;
+    uint8_t* workspace;
+    unsigned long long ws_stride;
+    unsigned int* work_counter;
+    const uint8_t* row_level;
+    uint16_t layer_off[kMaxLayers + 1];
+    uint8_t layer_nlev[kMaxLayers];
+    uint32_t links[kMaxLinks];
+};
+static_assert(sizeof(LdpcParams) <= 4096, "kernel parameter block must stay within the 4 KB constant window");
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// two int8 (bytes 0,1 / bytes 2,3 of w) -> sign-extended s16x2
+__device__ __forceinline__ uint32_t unpack01(uint32_t w) { return prmt(w, 0, 0x9180); }
+__device__ __forceinline__ uint32_t unpack23(uint32_t w) { return prmt(w, 0, 0xB3A2); }
+// s16x2 holding int8-range values -> two bytes in the low half
+__device__ __forceinline__ uint32_t pack1(uint32_t x) { return prmt(x, 0, 0x4420); }
+__device__ __forceinline__ uint32_t pack2(uint32_t x0, uint32_t x1) { return prmt(x0, x1, 0x6420); }
+
+constexpr uint32_t kM128 = 0xFF80FF80u, kP127 = 0x007F007Fu, kP32 = 0x00200020u, kP31 = 0x001F001Fu;
+constexpr uint32_t kM1 = 0xFFFFFFFFu, kBig = 0x7FFF7FFFu;
+
+__device__ __forceinline__ uint32_t sat8x2(uint32_t x) { return __vmins2(__vmaxs2(x, kM128), kP127); }
+
+// per-byte "is zero" of a packed pair: bit 7 (frame A) / bit 15 (frame B) set iff that byte == 0
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t w) {
+    return ~(((w & 0x7F7Fu) + 0x7F7Fu) | w) & 0x8080u;
+}
+
+// bits [o, o+32) of the 360-periodic extension of a 360-bit vector stored in 12 words (+1 zero word)
+__device__ __forceinline__ uint32_t win360(const uint32_t* H, int o) {
+    int w = o >> 5, s = o & 31;
+    uint32_t r = __funnelshift_r(H[w], H[w + 1], s);
+    int over = o + 32 - 360;
+    if (over > 0) r |= H[0] << (32 - over);
+    return r;
+}
+
+// One check row for both frames of the pair.
+//   msg[]  : this row's CNT+2 message slots as packed bytes, two slots per word (in/out)
+//   pown   : packed parity LLR pty[i][j]              (in/out)
+//   psec   : packed parity LLR of the second link     (in/out, ignored when !has2)
+// LIVE: 3 = both frames active, 1 = only frame A, 2 = only frame B (a finished frame keeps its LLRs)
+template <int CNT, int LIVE>
+__device__ __forceinline__ void row_update(uint16_t* __restrict__ vdata, const uint32_t* __restrict__ L, int cnt,
+                                           int j, uint32_t (&msg)[(CNT + 3) / 2], uint32_t& pown, uint32_t& psec,
+                                           bool has2) {
+    uint32_t t[CNT + 2];
+    int addr[CNT];
+    uint32_t min0 = kBig, min1 = kBig, sx = 0;
+#pragma unroll
+    for (int c = 0; c < CNT + 2; ++c) {
+        uint32_t v;
+        if (c < CNT) {
+            if (c >= cnt) continue;
+            uint32_t lk = L[c];
+            int m = j - (int)(lk & 0xFFFFu);
+            m += (m < 0) ? 360 : 0;
+            addr[c] = (int)(lk >> 16) * 360 + m;
+            v = unpack01(vdata[addr[c]]);
+        } else if (c == CNT) {
+            v = unpack01(pown);
+        } else {
+            if (!has2) continue;
+            v = unpack01(psec);
+        }
+        uint32_t mw = msg[c >> 1];
+        uint32_t m = (c & 1) ? unpack23(mw) : unpack01(mw);
+        uint32_t tt = sat8x2(__vsub2(v, m));                 // t = sat8(link - msg)
+        t[c] = tt;
+        uint32_t mg = __viaddmax_s16x2(tt, kM1, ~tt);        // max(t-1, -t-1) = |t|-1 (>= -1)
+        min1 = __vmins2(min1, __vmaxs2(min0, mg));
+        min0 = __vmins2(min0, mg);
+        sx ^= tt;
+    }
+    // offset-min-sum magnitudes, clamped to the message range straight away (order-preserving)
+    uint32_t m0c = __vmins2(__vmaxs2(min0, 0u), kP32);
+    uint32_t m1c = __vmins2(__vmaxs2(min1, 0u), kP32);
+    uint32_t sc = __vadd2(m0c, m1c);
+#pragma unroll
+    for (int c = 0; c < CNT + 2; ++c) {
+        if (c < CNT && c >= cnt) continue;
+        if (c == CNT + 1 && !has2) continue;
+        uint32_t tt = t[c];
+        uint32_t mg = __viaddmax_s16x2(tt, kM1, ~tt);
+        // exclusive minimum: min1 where this link holds the minimum, else min0
+        uint32_t om = __vmins2(m1c, __viaddmax_s16x2(sc, __vsub2(0u, mg), m0c));
+        uint32_t neg = prmt(sx ^ tt, 0, 0xBB99);             // 0xFFFF in lanes where the sign product is -
+        uint32_t mo = __vmins2(__vsub2(om ^ neg, neg), kP31);  // +-om, clamped to [-32, 31]
+        uint32_t vn = sat8x2(__vadd2(tt, mo));
+        uint32_t pk = pack1(vn);
+        if (c < CNT) {
+            if (LIVE == 3)
+                vdata[addr[c]] = (uint16_t)pk;
+            else if (LIVE == 1)
+                reinterpret_cast<uint8_t*>(vdata)[2 * addr[c]] = (uint8_t)pk;
+            else
+                reinterpret_cast<uint8_t*>(vdata)[2 * addr[c] + 1] = (uint8_t)(pk >> 8);
+        } else {
+            uint32_t& dst = (c == CNT) ? pown : psec;
+            if (LIVE == 3)
+                dst = pk;
+            else if (LIVE == 1)
+                dst = (dst & 0xFF00u) | (pk & 0x00FFu);
+            else
+                dst = (dst & 0x00FFu) | (pk & 0xFF00u);
+        }
+        // new message into its slot
+        uint32_t mp = pack1(mo);
+        if (c & 1)
+            msg[c >> 1] = (msg[c >> 1] & 0x0000FFFFu) | (mp << 16);
+        else
+            msg[c >> 1] = (msg[c >> 1] & 0xFFFF0000u) | mp;
+    }
+}
+
+template <int CNT>
+__global__ void __launch_bounds__(kLdpcThreads) ldpc_pair_kernel(const __grid_constant__ LdpcParams p) {
+    constexpr int SLOTS = CNT + 2;
+    constexpr int MW = (SLOTS + 1) / 2;     // message words per row in registers
+    constexpr int SG = (SLOTS + 7) / 8;     // uint4 groups per row in the workspace
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint16_t* vdata = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* HD = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.K * 2);  // [2][ngroups][13]
+    uint32_t* HP = HD + 2 * p.ngroups * kBitWords;                           // [2][q][13]
+    __shared__ unsigned int s_pair;
+    __shared__ int s_bad[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int j = tid;
+    const bool active = j < 360;
+    const int q = p.q, K = p.K, N = p.N, R = p.R;
+    uint4* wmsg = reinterpret_cast<uint4*>(p.workspace + (size_t)blockIdx.x * p.ws_stride);
+    uint16_t* wpty = reinterpret_cast<uint16_t*>(p.workspace + (size_t)blockIdx.x * p.ws_stride +
+                                                 (size_t)q * SG * 360 * 16);
+    const int npairs = (p.nframes + 1) >> 1;
+
+    // zero the pad words of the bit planes once
+    for (int x = tid; x < 2 * (p.ngroups + q); x += kLdpcThreads) HD[x * kBitWords + 12] = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_pair = atomicAdd(p.work_counter, 1u);
+        __syncthreads();
+        const unsigned pair = s_pair;
+        if (pair >= (unsigned)npairs) break;
+        const int fa = 2 * pair, fb = 2 * pair + 1;
+        const bool hasB = fb < p.nframes;
+        const int8_t* inA = p.llr_in + (size_t)fa * N;
+        const int8_t* inB = p.llr_in + (size_t)(hasB ? fb : fa) * N;
+
+        // ---- load: systematic LLRs -> shared (A in even bytes, B in odd), parity LLRs -> workspace,
+        //      permuted to layered order pty[360 i + j] = v[K + q j + i] (layered_decoder.hh:124-126)
+        for (int x = tid; x < K / 8; x += kLdpcThreads) {
+            uint2 a = __ldg(reinterpret_cast<const uint2*>(inA) + x);
+            uint2 b = __ldg(reinterpret_cast<const uint2*>(inB) + x);
+            uint4 o;
+            o.x = prmt(a.x, b.x, 0x5140);
+            o.y = prmt(a.x, b.x, 0x7362);
+            o.z = prmt(a.y, b.y, 0x5140);
+            o.w = prmt(a.y, b.y, 0x7362);
+            reinterpret_cast<uint4*>(vdata)[x] = o;
+        }
+        for (int x = tid; x < R; x += kLdpcThreads) {
+            uint32_t a = (uint8_t)__ldg(inA + K + x), b = (uint8_t)__ldg(inB + K + x);
+            int jj = x / q, ii = x - jj * q;
+            __stcg(&wpty[360 * ii + jj], (uint16_t)(a | (b << 8)));
+        }
+        __syncthreads();
+
+        int live = hasB ? 3 : 1;      // bit f set: frame f still iterating
+        int resA = -1, resB = -1;
+        uint32_t zacc = 0;            // zero-LLR flags gathered since the last syndrome test
+        // hard decisions + zero flags of the parity part, straight from the workspace (initial state)
+        for (int task = wid; task < q * 12; task += kLdpcThreads / 32) {
+            int ii = task / 12, w = task - ii * 12;
+            int jj = 32 * w + lane;
+            uint32_t v = (jj < 360) ? (uint32_t)__ldcg(&wpty[360 * ii + jj]) : 0x0101u;
+            unsigned mA = __ballot_sync(0xFFFFFFFFu, v & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, v & 0x8000u);
+            zacc |= zero_bytes(v);
+            if (lane == 0) {
+                HP[ii * kBitWords + w] = mA;
+                HP[(q + ii) * kBitWords + w] = mB;
+            }
+        }
+
+        for (int n = 0;; ++n) {
+            // ---- hard decisions + zero flags of the systematic part
+            for (int task = wid; task < p.ngroups * 12; task += kLdpcThreads / 32) {
+                int g = task / 12, w = task - g * 12;
+                int m = 32 * w + lane;
+                uint32_t v = (m < 360) ? (uint32_t)vdata[360 * g + m] : 0x0101u;
+                unsigned mA = __ballot_sync(0xFFFFFFFFu, v & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, v & 0x8000u);
+                zacc |= zero_bytes(v);
+                if (lane == 0) {
+                    HD[g * kBitWords + w] = mA;
+                    HD[(p.ngroups + g) * kBitWords + w] = mB;
+                }
+            }
+            if (tid < 2) s_bad[tid] = 0;
+            __syncthreads();
+            // ---- LDPCDecoder::bad (layered_decoder.hh:28-45) on bit planes: a row is bad when its sign
+            //      product is not positive, i.e. odd parity of hard decisions or any zero LLR
+            if (zacc & 0x80u) atomicOr(&s_bad[0], 1);
+            if (zacc & 0x8000u) atomicOr(&s_bad[1], 1);
+            zacc = 0;
+            for (int task = tid; task < q * 12; task += kLdpcThreads) {
+                int ii = task / 12, w = task - ii * 12;
+                const uint32_t* L = &p.links[p.layer_off[ii]];
+                int cnt = p.layer_off[ii + 1] - p.layer_off[ii];
+                uint32_t sA = HP[ii * kBitWords + w], sB = HP[(q + ii) * kBitWords + w];
+                if (ii > 0) {
+                    sA ^= HP[(ii - 1) * kBitWords + w];
+                    sB ^= HP[(q + ii - 1) * kBitWords + w];
+                } else {  // row (0,j) uses pty[q-1][j-1], row (0,0) has no second parity link
+                    const uint32_t* ta = &HP[(q - 1) * kBitWords];
+                    const uint32_t* tb = &HP[(2 * q - 1) * kBitWords];
+                    sA ^= (ta[w] << 1) | (w ? ta[w - 1] >> 31 : 0u);
+                    sB ^= (tb[w] << 1) | (w ? tb[w - 1] >> 31 : 0u);
+                }
+                for (int c = 0; c < cnt; ++c) {
+                    uint32_t lk = L[c];
+                    int o = 32 * w - (int)(lk & 0xFFFFu);
+                    o += (o < 0) ? 360 : 0;
+                    int g = lk >> 16;
+                    sA ^= win360(&HD[g * kBitWords], o);
+                    sB ^= win360(&HD[(p.ngroups + g) * kBitWords], o);
+                }
+                if (w == 11) {
+                    sA &= 0xFFu;
+                    sB &= 0xFFu;
+                }
+                if (sA) atomicOr(&s_bad[0], 1);
+                if (sB) atomicOr(&s_bad[1], 1);
+            }
+            __syncthreads();
+            // ---- while (bad() && --trials >= 0) update();  (layered_decoder.hh:127-128), per frame
+            {
+                int badA = s_bad[0], badB = s_bad[1];
+                if ((live & 1) && !badA) { resA = n; live &= ~1; }
+                if ((live & 2) && !badB) { resB = n; live &= ~2; }
+                if (n == p.max_trials) live = 0;  // frames still bad after max_trials updates report -1
+            }
+            if (!live) break;
+
+            // ---- LDPCDecoder::update (layered_decoder.hh:46-74): one pass over all layers
+            uint32_t msg[MW];
+#pragma unroll
+            for (int x = 0; x < MW; ++x) msg[x] = 0;
+            uint4 nxt[SG];
+            uint32_t pown = 0, psec = 0, pnext = 0;
+            const bool first = (n == 0);
+            if (active) {
+                pown = __ldcg(&wpty[j]);
+                if (j > 0) psec = __ldcg(&wpty[360 * (q - 1) + j - 1]);
+                if (!first) {
+#pragma unroll
+                    for (int s = 0; s < SG; ++s) nxt[s] = __ldcg(&wmsg[(size_t)s * 360 + j]);
+                }
+            }
+            for (int i = 0; i < q; ++i) {
+                if (active) {
+                    if (!first) {
+#pragma unroll
+                        for (int s = 0; s < SG; ++s) {
+                            if (4 * s + 0 < MW) msg[4 * s + 0] = nxt[s].x;
+                            if (4 * s + 1 < MW) msg[4 * s + 1] = nxt[s].y;
+                            if (4 * s + 2 < MW) msg[4 * s + 2] = nxt[s].z;
+                            if (4 * s + 3 < MW) msg[4 * s + 3] = nxt[s].w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < MW; ++x) msg[x] = 0;
+                    }
+                    if (i + 1 < q) {  // prefetch the next layer's row while this one computes
+                        pnext = __ldcg(&wpty[360 * (i + 1) + j]);
+                        if (!first) {
+#pragma unroll
+                            for (int s = 0; s < SG; ++s)
+                                nxt[s] = __ldcg(&wmsg[((size_t)(i + 1) * SG + s) * 360 + j]);
+                        }
+                    }
+                }
+                const uint32_t* L = &p.links[p.layer_off[i]];
+                const int cnt = p.layer_off[i + 1] - p.layer_off[i];
+                const int nlev = p.layer_nlev[i];
+                const int mylev = (nlev > 1 && active) ? p.row_level[i * 360 + j] : 0;
+                const bool has2 = (i | j) != 0;
+                for (int lvl = 0; lvl < nlev; ++lvl) {
+                    if (active && mylev == lvl) {
+                        if (live == 3)
+                            row_update<CNT, 3>(vdata, L, cnt, j, msg, pown, psec, has2);
+                        else if (live == 1)
+                            row_update<CNT, 1>(vdata, L, cnt, j, msg, pown, psec, has2);
+                        else
+                            row_update<CNT, 2>(vdata, L, cnt, j, msg, pown, psec, has2);
+                    }
+                    __syncthreads();
+                }
+                // write the row's messages back; retire the parity LLR that just got its last update
+                if (active) {
+#pragma unroll
+                    for (int s = 0; s < SG; ++s) {
+                        uint4 o;
+                        o.x = (4 * s + 0 < MW) ? msg[4 * s + 0] : 0u;
+                        o.y = (4 * s + 1 < MW) ? msg[4 * s + 1] : 0u;
+                        o.z = (4 * s + 2 < MW) ? msg[4 * s + 2] : 0u;
+                        o.w = (4 * s + 3 < MW) ? msg[4 * s + 3] : 0u;
+                        __stcg(&wmsg[((size_t)i * SG + s) * 360 + j], o);
+                    }
+                    if (i == 0) {
+                        if (j > 0) __stcg(&wpty[360 * (q - 1) + j - 1], (uint16_t)psec);  // updated again in layer q-1
+                    } else {
+                        __stcg(&wpty[360 * (i - 1) + j], (uint16_t)psec);
+                    }
+                }
+                if (i > 0) {
+                    uint32_t fin = active ? psec : 0x0101u;
+                    unsigned mA = __ballot_sync(0xFFFFFFFFu, fin & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, fin & 0x8000u);
+                    zacc |= zero_bytes(fin);
+                    if (lane == 0) {
+                        HP[(i - 1) * kBitWords + wid] = mA;
+                        HP[(q + i - 1) * kBitWords + wid] = mB;
+                    }
+                }
+                psec = pown;
+                pown = pnext;
+            }
+            {   // pty[q-1][j]: its second link was served in layer 0, the own link just now -> final
+                uint32_t fin = active ? psec : 0x0101u;
+                if (active) __stcg(&wpty[360 * (q - 1) + j], (uint16_t)psec);
+                unsigned mA = __ballot_sync(0xFFFFFFFFu, fin & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, fin & 0x8000u);
+                zacc |= zero_bytes(fin);
+                if (lane == 0) {
+                    HP[(q - 1) * kBitWords + wid] = mA;
+                    HP[(2 * q - 1) * kBitWords + wid] = mB;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- results: iteration counts, MSB-first hard decisions of the K systematic bits
+        if (tid == 0) {
+            p.iters_out[fa] = (int16_t)resA;
+            if (hasB) p.iters_out[fb] = (int16_t)resB;
+        }
+        const int kbytes = K / 8;
+        for (int x = tid; x < 2 * kbytes; x += kLdpcThreads) {
+            int f = x >= kbytes, b = x - f * kbytes;
+            if (f && !hasB) break;
+            int g = b / 45, k = b - g * 45;
+            uint32_t word = HD[(f * p.ngroups + g) * kBitWords + (k >> 2)];
+            uint32_t byte = (word >> (8 * (k & 3))) & 0xFFu;
+            p.hard_out[(size_t)(f ? fb : fa) * p.hard_stride + b] = (uint8_t)(__brev(byte) >> 24);
+        }
+        if (p.llr_out) {
+            for (int x = tid; x < K; x += kLdpcThreads) {
+                uint32_t v = vdata[x];
+                p.llr_out[(size_t)fa * N + x] = (int8_t)(v & 0xFF);
+                if (hasB) p.llr_out[(size_t)fb * N + x] = (int8_t)(v >> 8);
+            }
+            for (int x = tid; x < R; x += kLdpcThreads) {
+                int jj = x / q, ii = x - jj * q;
+                uint32_t v = __ldcg(&wpty[360 * ii + jj]);
+                p.llr_out[(size_t)fa * N + K + x] = (int8_t)(v & 0xFF);
+                if (hasB) p.llr_out[(size_t)fb * N + K + x] = (int8_t)(v >> 8);
+            }
+        }
+    }
+}
+
+using KernelFn = void (*)(const LdpcParams);
+struct Variant {
+    int cnt;
+    KernelFn fn;
+};
+#define V(c) {c, ldpc_pair_kernel<c>}
+// one instantiation per distinct "max data links per row" among the 21 codes
+const Variant kVariants[] = {V(2), V(3), V(4), V(5), V(8), V(9), V(11), V(12), V(16), V(17), V(20), V(25), V(28)};
+#undef V
+
+const Variant* pick(int max_cnt) {
+    for (const Variant& v : kVariants)
+        if (v.cnt >= max_cnt) return &v;
+    return nullptr;
+}
+
+}  // namespace
+
+int ldpc_slot_groups(int max_cnt) {
+    const Variant* v = pick(max_cnt);
+    return v ? (v->cnt + 2 + 7) / 8 : 0;
+}
+
+int ldpc_max_ctas_per_sm(const LdpcDev& code) {
+    const Variant* v = pick(code.max_cnt);
+    if (!v) return 0;
+    size_t smem = ldpc_smem_bytes(code);
+    cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v->fn, kLdpcThreads, smem);
+    return n;
+}
+
+int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
+    const LdpcDev& c = a.code;
+    const Variant* v = pick(c.max_cnt);
+    if (!v || c.q > kMaxLayers) return (int)cudaErrorInvalidValue;
+    LdpcParams p;
+    p.N = c.N; p.K = c.K; p.R = c.R; p.q = c.q; p.ngroups = c.ngroups;
+    p.sg = (v->cnt + 2 + 7) / 8;
+    if (p.sg != c.sg) return (int)cudaErrorInvalidValue;
+    p.nframes = a.nframes; p.max_trials = a.max_trials; p.hard_stride = a.hard_stride; p.pad_ = 0;
+    p.llr_in = a.llr_in; p.hard_out = a.hard_out; p.iters_out = a.iters_out; p.llr_out = a.llr_out;
+    p.workspace = a.workspace;
+    p.ws_stride = ldpc_workspace_bytes(c);
+    p.work_counter = a.work_counter;
+    p.row_level = c.row_level;
+    const int nlinks = c.layer_off[c.q];
+    if (nlinks > kMaxLinks) return (int)cudaErrorInvalidValue;
+    for (int i = 0; i <= c.q; ++i) p.layer_off[i] = (uint16_t)c.layer_off[i];
+    for (int i = 0; i < c.q; ++i) p.layer_nlev[i] = c.layer_nlev[i];
+    for (int i = 0; i < nlinks; ++i) p.links[i] = c.links[i];
+    size_t smem = ldpc_smem_bytes(c);
+    cudaError_t e = cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    v->fn<<<grid, kLdpcThreads, smem, stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace s2

@@ -1,0 +1,264 @@
+"""Parity of the CUDA decode stage (through the C ABI) against the CPU oracle.  Needs a B200.
+
+Bit-exact bar: posterior LLR bytes + iteration counts (LDPC), corrected codeword bytes + correction
+counts (BCH), BBFRAME bytes (whole chain), int8 LLRs (LUT demapper).  32APSK demapping uses device
+expf/logf instead of glibc's: tolerance |diff| <= 1 LSB on at most 0.5 % of the LLRs (stated below)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orclib
+from fec import pkg, MODCODS, QPSK_MODCOD_OF_RATE
+from orclib import ALL_CODES, code_params
+
+pytestmark = pytest.mark.gpu
+
+_SNR = {0: -2.0, 1: -1.0, 2: 0.0, 3: 1.3, 4: 2.6, 5: 3.4, 6: 4.3, 7: 5.0, 8: 5.5, 10: 6.5, 11: 6.7}
+
+
+@pytest.fixture(scope="module")
+def dec():
+    d = pkg.DVBS2Decoder(max_batch=256, max_trials=25)
+    yield d
+    d.close()
+
+
+def make_llrs(short, rate, n, seed, spread=1.2):
+    """n frames around the code's threshold: converging, slow and failing ones, plus corner cases"""
+    p = code_params(short, rate)
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, p["N"]), np.int8)
+    for i in range(n):
+        _, code = orclib.encode_frame(short, rate, rng)
+        snr = _SNR[rate] + (0.4 if short else 0) + spread * (i / max(n - 1, 1) - 0.35)
+        out[i] = orclib.awgn_llr(code, snr, rng)
+    return out
+
+
+def oracle_ldpc(short, rate, llr, max_trials):
+    o = orclib.oracle()
+    post = llr.copy()
+    iters = np.zeros(len(llr), np.int16)
+    for i in range(len(llr)):
+        iters[i] = o.orc_ldpc_decode(short, rate, post[i], max_trials)
+    return post, iters
+
+
+@pytest.mark.parametrize("short,rate", ALL_CODES)
+def test_ldpc_bit_exact_all_codes(dec, short, rate):
+    dec.setDemodParams(QPSK_MODCOD_OF_RATE[rate], bool(short), False)
+    n = 7 if not short else 13  # odd: exercises the half-empty last pair
+    llr = make_llrs(short, rate, n, 17 + rate + 40 * short)
+    llr[1, ::97] = 0                      # zero LLRs keep rows "bad"
+    llr[2] = np.where(llr[2] < 0, -128, 127)  # saturated input
+    want_post, want_it = oracle_ldpc(short, rate, llr, 25)
+    got = llr.copy()
+    it = dec.ldpc_decode(got, 25)
+    assert np.array_equal(it, want_it), (it, want_it)
+    assert np.array_equal(got, want_post)
+    assert len(set(want_it.tolist())) >= 2
+
+
+@pytest.mark.parametrize("max_trials", [1, 3, 16])
+def test_ldpc_iteration_cap(dec, max_trials):
+    short, rate = 1, 3
+    dec.setDemodParams(4, True, False)
+    llr = make_llrs(short, rate, 8, 5)
+    want_post, want_it = oracle_ldpc(short, rate, llr, max_trials)
+    got = llr.copy()
+    it = dec.ldpc_decode(got, max_trials)
+    assert np.array_equal(it, want_it)
+    assert np.array_equal(got, want_post)
+
+
+def test_ldpc_random_and_codeword_inputs(dec):
+    short, rate = 1, 6
+    dec.setDemodParams(7, True, False)
+    p = code_params(short, rate)
+    rng = np.random.default_rng(3)
+    llr = rng.integers(-128, 128, (6, p["N"]), dtype=np.int8)
+    _, code = orclib.encode_frame(short, rate, rng)
+    llr[4] = np.where(code > 0, -9, 9)   # already a codeword: 0 iterations
+    llr[5] = 0                            # all-zero LLRs
+    want_post, want_it = oracle_ldpc(short, rate, llr, 25)
+    got = llr.copy()
+    it = dec.ldpc_decode(got, 25)
+    assert want_it[4] == 0
+    assert np.array_equal(it, want_it)
+    assert np.array_equal(got, want_post)
+
+
+@pytest.mark.parametrize("short,rate", [(0, 3), (0, 5), (0, 10), (1, 3), (1, 0)])
+def test_bch_bit_exact(dec, short, rate):
+    dec.setDemodParams(QPSK_MODCOD_OF_RATE[rate], bool(short), False)
+    o = orclib.oracle()
+    p = code_params(short, rate)
+    K, kbch, t = p["K"], p["kbch"], p["t"]
+    rng = np.random.default_rng(11 + rate)
+    nerrs = [0, 1, 2, 2, 2, 3, 5, t - 1, t, t, t + 1, t + 2, 30, 200]
+    frames = np.zeros((len(nerrs), K // 8), np.uint8)
+    for i, ne in enumerate(nerrs):
+        frames[i, : kbch // 8] = rng.integers(0, 256, kbch // 8, dtype=np.uint8)
+        assert o.orc_bch_encode(short, rate, frames[i]) == 0
+        where = rng.choice(K, ne, replace=False)
+        if i == 4:
+            where = np.array([K - 1, K - 2])  # last two parity bits
+        for e in where:
+            frames[i, e >> 3] ^= 0x80 >> (e & 7)
+    want = frames.copy()
+    want_c = np.array([o.orc_bch_decode(short, rate, want[i]) for i in range(len(nerrs))], np.int16)
+    got = frames.copy()
+    got_c = dec.bch_decode(got)
+    assert np.array_equal(got_c, want_c), (got_c, want_c)
+    assert np.array_equal(got, want)
+    assert (want_c[:10] == np.array(nerrs[:10])).all()
+
+
+def test_descrambler_bit_exact(dec):
+    dec.setDemodParams(4, False, False)
+    o = orclib.oracle()
+    rng = np.random.default_rng(2)
+    fr = rng.integers(0, 256, (3, dec.K // 8), dtype=np.uint8)
+    want = fr.copy()
+    for i in range(3):
+        o.orc_descramble(0, 3, want[i])
+    assert np.array_equal(dec.descramble(fr.copy()), want)
+
+
+@pytest.mark.parametrize("modcod,short", [(4, 0), (4, 1), (12, 0), (13, 0), (13, 1), (18, 0), (21, 1), (23, 0)])
+def test_demapper_lut_bit_exact(dec, modcod, short):
+    const, ctype, rate, g1, g2 = MODCODS[modcod]
+    dec.setDemodParams(modcod, bool(short), False)
+    o = orclib.oracle()
+    c = o.orc_const_create(ctype, g1, g2)
+    rng = np.random.default_rng(modcod)
+    n = 2
+    pl = np.zeros((n, dec.plframe_symbols, 2), np.float32)
+    for i in range(n):
+        bits = rng.integers(0, 2, dec.N, dtype=np.uint8)
+        pl[i] = pkg.modulate(modcod, bool(short), False, bits).view(np.float32).reshape(-1, 2)
+    pl += rng.normal(0, 0.15, pl.shape).astype(np.float32)
+    pl[0, 100:140] *= 30            # clipped by the LUT index clamp
+    pl[0, 150] = (np.nan, 0.3)
+    pl[0, 151] = (3e30, -3e30)
+    want = np.zeros((n, dec.N), np.int8)
+    for i in range(n):
+        o.orc_bb_to_soft(c, const, short, rate, np.ascontiguousarray(pl[i].reshape(-1)), want[i])
+    got = dec.bb_to_soft(pl)
+    assert np.array_equal(got, want)
+    o.orc_const_destroy(c)
+
+
+@pytest.mark.parametrize("modcod,short", [(24, 1), (28, 0)])
+def test_demapper_32apsk_within_one_lsb(dec, modcod, short):
+    const, ctype, rate, g1, g2 = MODCODS[modcod]
+    dec.setDemodParams(modcod, bool(short), False)
+    o = orclib.oracle()
+    c = o.orc_const_create(ctype, g1, g2)
+    rng = np.random.default_rng(modcod)
+    bits = rng.integers(0, 2, dec.N, dtype=np.uint8)
+    pl = pkg.modulate(modcod, bool(short), False, bits).view(np.float32).reshape(1, -1, 2).copy()
+    pl += rng.normal(0, 0.05, pl.shape).astype(np.float32)
+    want = np.zeros((1, dec.N), np.int8)
+    o.orc_bb_to_soft(c, const, short, rate, np.ascontiguousarray(pl.reshape(-1)), want[0])
+    got = dec.bb_to_soft(pl)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    # tolerance: device expf/logf vs glibc -> at most 1 LSB, on at most 0.5 % of the LLRs
+    assert diff.max() <= 1
+    assert (diff != 0).mean() <= 0.005
+    o.orc_const_destroy(c)
+
+
+def oracle_chain(short, rate, llr, max_trials):
+    o = orclib.oracle()
+    p = code_params(short, rate)
+    bb = np.zeros((len(llr), p["kbch"] // 8), np.uint8)
+    its = np.zeros(len(llr), np.int16)
+    cor = np.zeros(len(llr), np.int16)
+    for i in range(len(llr)):
+        a, b = C.c_int(), C.c_int()
+        o.orc_decode_frame(short, rate, llr[i].copy(), max_trials, bb[i], C.byref(a), C.byref(b))
+        its[i], cor[i] = a.value, b.value
+    return bb, its, cor
+
+
+@pytest.mark.parametrize("short,rate,n", [(0, 3, 24), (1, 3, 40), (0, 11, 6), (1, 10, 30)])
+def test_whole_stage_bit_exact(dec, short, rate, n):
+    dec.setDemodParams(QPSK_MODCOD_OF_RATE[rate], bool(short), False)
+    llr = make_llrs(short, rate, n, 99 + rate, spread=0.9)
+    want_bb, want_it, want_c = oracle_chain(short, rate, llr, 25)
+    bb, res = dec.decode_batch(llr)
+    assert np.array_equal(res["ldpc_iters"], want_it)
+    assert np.array_equal(res["bch_corr"], want_c)
+    assert np.array_equal(bb, want_bb)
+    assert np.array_equal(res["tag"], np.arange(n))
+    flags = (want_it < 0) * 1 + (want_c < 0) * 2
+    assert np.array_equal(res["flags"], flags)
+    assert dec.last_launch_count() >= 2
+
+
+def test_payload_round_trip_from_symbols(dec):
+    """transmit -> AWGN -> demap + LDPC + BCH + descramble returns the payload (config 3/4 style chain)"""
+    for modcod, short, sigma in [(4, 1, 0.45), (13, 0, 0.12), (18, 1, 0.05), (27, 1, 0.02)]:
+        dec.setDemodParams(modcod, bool(short), False)
+        rng = np.random.default_rng(modcod)
+        n = 4
+        payload = rng.integers(0, 256, (n, dec.kbch // 8), dtype=np.uint8)
+        pl = np.zeros((n, dec.plframe_symbols), np.complex64)
+        for i in range(n):
+            pl[i] = pkg.modulate(modcod, bool(short), False, pkg.encode_fecframe(modcod, bool(short), payload[i]))
+        noisy = pl.view(np.float32) + rng.normal(0, sigma, (n, dec.plframe_symbols * 2)).astype(np.float32)
+        bb, res = dec.decode_plframes(noisy)
+        assert (res["bch_corr"] >= 0).all(), (modcod, res)
+        assert np.array_equal(bb, payload), modcod
+
+
+def test_queue_returns_frames_in_submission_order(dec):
+    short, rate = 1, 3
+    dec.setDemodParams(4, True, False)
+    llr = make_llrs(short, rate, 21, 1234)
+    want_bb, want_it, want_c = oracle_chain(short, rate, llr, 25)
+    for i in range(len(llr)):
+        dec.submit_llr(llr[i], 1000 + i)
+    dec.flush()
+    bb, res = dec.collect(64, timeout_us=2_000_000)
+    assert len(res) == len(llr)
+    assert np.array_equal(res["tag"], 1000 + np.arange(len(llr)))
+    assert np.array_equal(bb, want_bb)
+    assert np.array_equal(res["ldpc_iters"], want_it)
+    assert np.array_equal(res["bch_corr"], want_c)
+
+
+def test_modcod_switch_and_errors(dec):
+    with pytest.raises(pkg.DVBS2FecError):
+        dec.setDemodParams(0)
+    with pytest.raises(pkg.DVBS2FecError):
+        dec.setDemodParams(29)
+    with pytest.raises(pkg.DVBS2FecError):
+        dec.setDemodParams(11, True)      # short 9/10 does not exist (reference leaves ldpc uninitialised)
+    dec.setDemodParams(6, False, False)
+    assert (dec.N, dec.K, dec.kbch) == (64800, 43200, 43040)
+    dec.setDemodParams(1, True, True)
+    assert (dec.N, dec.K, dec.kbch) == (16200, 3240, 3072)
+    assert dec.plframe_symbols == 90 + 8100 + 36 * 5
+
+
+def test_stage_objects_mirror_reference_interface():
+    rng = np.random.default_rng(8)
+    ldpc = pkg.BBFrameLDPC(True, 3)
+    bch = pkg.BBFrameBCH(True, 3, decoder=ldpc.dec)
+    descr = pkg.BBFrameDescrambler(True, 3, decoder=ldpc.dec)
+    assert ldpc.dataSize() == 7200 and bch.dataSize() == 7032
+    payload, code = orclib.encode_frame(1, 3, rng)
+    frame = orclib.awgn_llr(code, 3.0, rng)
+    want = frame.copy()
+    want_it = orclib.oracle().orc_ldpc_decode(1, 3, want, 16)
+    assert ldpc.decode(frame, 16) == want_it
+    assert np.array_equal(frame, want)
+    packed = np.packbits((frame[:7200] < 0).astype(np.uint8))
+    assert bch.decode(packed) == 0
+    descr.work(packed)
+    orclib.oracle().orc_descramble(1, 3, payload_copy := np.concatenate([payload, np.zeros(21, np.uint8)]))
+    assert np.array_equal(packed[: 7032 // 8], payload_copy[: 7032 // 8])
+    ldpc.dec.close()
