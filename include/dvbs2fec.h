@@ -94,6 +94,11 @@ int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n,
                                  dvbs2fec_result* d_results, void* cuda_stream);
 /* number of kernel launches the last decode_batch* call on this handle enqueued */
 int dvbs2fec_last_launch_count(const dvbs2fec_handle* h);
+/* measurement aid: with profiling on, every kernel launch of decode_batch_device is bracketed by CUDA
+ * events on its stream; kernel_times() waits for them and returns the summed device time per kernel
+ * (ms) and the number of launches since the previous call. */
+int dvbs2fec_set_profiling(dvbs2fec_handle* h, int on);
+int dvbs2fec_kernel_times(dvbs2fec_handle* h, float* demap_ms, float* ldpc_ms, float* bch_ms, int* launches);
 
 /* ---- frame-batching queue between PL sync and the decoder (replaces simd_packer,
  *      module_dvbs2_demod.cpp:343-347): frames come back in submission order ---- */

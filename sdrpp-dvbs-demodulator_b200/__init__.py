@@ -81,6 +81,8 @@ def lib():
     L.dvbs2fec_decode_batch.argtypes = [vp, vp, C.c_int, vp, vp]
     L.dvbs2fec_decode_plframes.argtypes = [vp, vp, C.c_int, vp, vp]
     L.dvbs2fec_decode_batch_device.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.dvbs2fec_set_profiling.argtypes = [vp, C.c_int]
+    L.dvbs2fec_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), ip]
     L.dvbs2fec_submit_llr.argtypes = [vp, vp, C.c_uint64]
     L.dvbs2fec_submit_plframe.argtypes = [vp, vp, C.c_int, C.c_uint64]
     L.dvbs2fec_collect.argtypes = [vp, vp, vp, C.c_int, C.c_int]
@@ -223,6 +225,15 @@ class DVBS2Decoder:
     def decode_batch_device(self, d_llr_ptr, n, d_bb_ptr, d_res_ptr, stream_ptr=0):
         """Device pointers on this decoder's first device; enqueues on ``stream_ptr`` and returns."""
         _check(lib().dvbs2fec_decode_batch_device(self._h, d_llr_ptr, n, d_bb_ptr, d_res_ptr, stream_ptr))
+
+    def set_profiling(self, on):
+        _check(lib().dvbs2fec_set_profiling(self._h, int(on)))
+
+    def kernel_times(self):
+        """(demap_ms, ldpc_ms, bch_ms, launches) summed since the previous call; waits for the events."""
+        a, b, c, n = C.c_float(), C.c_float(), C.c_float(), C.c_int()
+        _check(lib().dvbs2fec_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return a.value, b.value, c.value, n.value
 
     def last_launch_count(self):
         return lib().dvbs2fec_last_launch_count(self._h)

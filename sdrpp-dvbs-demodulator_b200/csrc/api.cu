@@ -143,6 +143,9 @@ struct dvbs2fec_handle {
     int plsyms = 0;
     int last_launches = 0;
     bool configured = false;
+    bool profiling = false;
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> spans;
     // host copies of the layer tables referenced by LdpcDev (host pointers)
     std::vector<uint32_t> h_links;
     // ---- queue
@@ -269,8 +272,22 @@ int reserve_slot(dvbs2fec_handle* h, DevCtx& d, Slot& s, int nframes, bool with_
 int enqueue_chain(dvbs2fec_handle* h, DevCtx& d, Slot& s, const float* d_sym, const int8_t* d_llr, int n,
                   uint8_t* d_bb, dvbs2fec_result* d_res, cudaStream_t st, int* launches, uint64_t tag_base = 0) {
     const int8_t* llr = d_llr;
+    auto mark = [&](int kind, bool begin) {
+        if (!h->profiling) return;
+        if (begin) {
+            dvbs2fec_handle::Span sp{kind, nullptr, nullptr};
+            cudaEventCreate(&sp.a);
+            cudaEventCreate(&sp.b);
+            cudaEventRecord(sp.a, st);
+            h->spans.push_back(sp);
+        } else {
+            cudaEventRecord(h->spans.back().b, st);
+        }
+    };
     if (d_sym) {
+        mark(0, true);
         int e = demap_launch(d.demap, d_sym, n, s.llr.p, st);
+        mark(0, false);
         if (e) return fail(DVBS2FEC_ECUDA, "demap launch: %s", cudaGetErrorString((cudaError_t)e));
         llr = s.llr.p;
         ++*launches;
@@ -288,7 +305,9 @@ int enqueue_chain(dvbs2fec_handle* h, DevCtx& d, Slot& s, const float* d_sym, co
     la.workspace = s.workspace.p;
     la.work_counter = s.counter.p;
     int grid = std::min(d.grid, (n + 1) / 2);
+    mark(1, true);
     int e = ldpc_launch(la, grid, st);
+    mark(1, false);
     if (e) return fail(DVBS2FEC_ECUDA, "ldpc launch: %s", cudaGetErrorString((cudaError_t)e));
     ++*launches;
     BchArgs ba{};
@@ -303,7 +322,9 @@ int enqueue_chain(dvbs2fec_handle* h, DevCtx& d, Slot& s, const float* d_sym, co
     ba.results = d_res;
     ba.corr_out = nullptr;
     ba.descramble = 1;
+    mark(2, true);
     e = bch_launch(ba, st);
+    mark(2, false);
     if (e) return fail(DVBS2FEC_ECUDA, "bch launch: %s", cudaGetErrorString((cudaError_t)e));
     ++*launches;
     return 0;
@@ -564,6 +585,32 @@ int dvbs2fec_kldpc(const dvbs2fec_handle* h) { return (h && h->configured) ? h->
 int dvbs2fec_nldpc(const dvbs2fec_handle* h) { return (h && h->configured) ? h->code->N : DVBS2FEC_EINVAL; }
 int dvbs2fec_plframe_symbols(const dvbs2fec_handle* h) { return (h && h->configured) ? h->plsyms : DVBS2FEC_EINVAL; }
 int dvbs2fec_last_launch_count(const dvbs2fec_handle* h) { return h ? h->last_launches : 0; }
+
+int dvbs2fec_set_profiling(dvbs2fec_handle* h, int on) {
+    if (!h) return fail(DVBS2FEC_EINVAL, "handle is NULL");
+    h->profiling = on != 0;
+    return 0;
+}
+int dvbs2fec_kernel_times(dvbs2fec_handle* h, float* demap_ms, float* ldpc_ms, float* bch_ms, int* launches) {
+    if (!h) return fail(DVBS2FEC_EINVAL, "handle is NULL");
+    float acc[3] = {0, 0, 0};
+    int n = 0;
+    for (auto& sp : h->spans) {
+        float ms = 0;
+        CU(cudaEventSynchronize(sp.b));
+        CU(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        acc[sp.kind] += ms;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+        ++n;
+    }
+    h->spans.clear();
+    if (demap_ms) *demap_ms = acc[0];
+    if (ldpc_ms) *ldpc_ms = acc[1];
+    if (bch_ms) *bch_ms = acc[2];
+    if (launches) *launches = n;
+    return 0;
+}
 
 int dvbs2fec_bb_to_soft(dvbs2fec_handle* h, const float* plframes, int n, int8_t* llr_out) {
     if (!h || !h->configured || !plframes || !llr_out || n < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");

@@ -200,7 +200,7 @@ def test_whole_stage_bit_exact(dec, short, rate, n):
 
 def test_payload_round_trip_from_symbols(dec):
     """transmit -> AWGN -> demap + LDPC + BCH + descramble returns the payload (config 3/4 style chain)"""
-    for modcod, short, sigma in [(4, 1, 0.45), (13, 0, 0.12), (18, 1, 0.05), (27, 1, 0.02)]:
+    for modcod, short, sigma in [(4, 1, 0.10), (13, 0, 0.10), (18, 1, 0.05), (27, 1, 0.02)]:
         dec.setDemodParams(modcod, bool(short), False)
         rng = np.random.default_rng(modcod)
         n = 4
