@@ -286,7 +286,8 @@ def main():
     h_in = L.dvbs2fec_alloc_pinned(e2e_frames * N)
     h_bb = L.dvbs2fec_alloc_pinned(e2e_frames * (kbch // 8))
     h_res = L.dvbs2fec_alloc_pinned(e2e_frames * 16)
-    C.memmove(h_in, pool[:e2e_frames].cpu().numpy().ctypes.data, e2e_frames * N)
+    host_copy = pool[:e2e_frames].cpu().numpy()
+    C.memmove(h_in, host_copy.ctypes.data, e2e_frames * N)
     dec_e = pkg.DVBS2Decoder(devices=[local_rank], max_batch=512, max_trials=MAX_TRIALS)
     dec_e.setDemodParams(MODCOD, SHORT, False, MAX_TRIALS)
     for _ in range(2):

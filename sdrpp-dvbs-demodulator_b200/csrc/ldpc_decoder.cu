@@ -59,36 +59,33 @@ __device__ __forceinline__ uint32_t win360(const uint32_t* H, int o) {
 }
 
 // One check row for both frames of the pair.
+//   voff[] : byte offsets into the shared LLR array of this row's data links (hoisted out of the level loop)
 //   msg[]  : this row's CNT+2 message slots as packed bytes, two slots per word (in/out)
 //   pown   : packed parity LLR pty[i][j]              (in/out)
 //   psec   : packed parity LLR of the second link     (in/out, ignored when !has2)
-// LIVE: 3 = both frames active, 1 = only frame A, 2 = only frame B (a finished frame keeps its LLRs)
-template <int CNT, int LIVE>
-__device__ __forceinline__ void row_update(uint16_t* __restrict__ vdata, const uint32_t* __restrict__ L, int cnt,
-                                           int j, uint32_t (&msg)[(CNT + 3) / 2], uint32_t& pown, uint32_t& psec,
-                                           bool has2) {
+// EXACT: every one of the CNT data links exists (cnt == CNT); otherwise links c >= cnt are skipped.
+// BOTH : both frames still iterate; otherwise only frame `lf` (0/1) may change, the other keeps its LLRs.
+template <int CNT, bool EXACT, bool BOTH>
+__device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const int (&voff)[CNT], int cnt,
+                                           uint32_t (&msg)[(CNT + 3) / 2], uint32_t& pown, uint32_t& psec,
+                                           bool has2, int lf) {
     uint32_t t[CNT + 2];
-    int addr[CNT];
     uint32_t min0 = kBig, min1 = kBig, sx = 0;
 #pragma unroll
     for (int c = 0; c < CNT + 2; ++c) {
         uint32_t v;
         if (c < CNT) {
-            if (c >= cnt) continue;
-            uint32_t lk = L[c];
-            int m = j - (int)(lk & 0xFFFFu);
-            m += (m < 0) ? 360 : 0;
-            addr[c] = (int)(lk >> 16) * 360 + m;
-            v = unpack01(vdata[addr[c]]);
+            if (!EXACT && c >= cnt) continue;
+            v = unpack01(*reinterpret_cast<const uint16_t*>(vbytes + voff[c]));
         } else if (c == CNT) {
             v = unpack01(pown);
         } else {
-            if (!has2) continue;
             v = unpack01(psec);
         }
         uint32_t mw = msg[c >> 1];
         uint32_t m = (c & 1) ? unpack23(mw) : unpack01(mw);
         uint32_t tt = sat8x2(__vsub2(v, m));                 // t = sat8(link - msg)
+        if (c == CNT + 1 && !has2) tt = kP127;               // row (0,0): neutral stand-in (|t|-1 = 126, sign +)
         t[c] = tt;
         uint32_t mg = __viaddmax_s16x2(tt, kM1, ~tt);        // max(t-1, -t-1) = |t|-1 (>= -1)
         min1 = __vmins2(min1, __vmaxs2(min0, mg));
@@ -101,8 +98,7 @@ __device__ __forceinline__ void row_update(uint16_t* __restrict__ vdata, const u
     uint32_t sc = __vadd2(m0c, m1c);
 #pragma unroll
     for (int c = 0; c < CNT + 2; ++c) {
-        if (c < CNT && c >= cnt) continue;
-        if (c == CNT + 1 && !has2) continue;
+        if (!EXACT && c < CNT && c >= cnt) continue;
         uint32_t tt = t[c];
         uint32_t mg = __viaddmax_s16x2(tt, kM1, ~tt);
         // exclusive minimum: min1 where this link holds the minimum, else min0
@@ -112,32 +108,30 @@ __device__ __forceinline__ void row_update(uint16_t* __restrict__ vdata, const u
         uint32_t vn = sat8x2(__vadd2(tt, mo));
         uint32_t pk = pack1(vn);
         if (c < CNT) {
-            if (LIVE == 3)
-                vdata[addr[c]] = (uint16_t)pk;
-            else if (LIVE == 1)
-                reinterpret_cast<uint8_t*>(vdata)[2 * addr[c]] = (uint8_t)pk;
+            if (BOTH)
+                *reinterpret_cast<uint16_t*>(vbytes + voff[c]) = (uint16_t)pk;
             else
-                reinterpret_cast<uint8_t*>(vdata)[2 * addr[c] + 1] = (uint8_t)(pk >> 8);
+                vbytes[voff[c] + lf] = (uint8_t)(pk >> (8 * lf));
         } else {
             uint32_t& dst = (c == CNT) ? pown : psec;
-            if (LIVE == 3)
+            if (BOTH) {
                 dst = pk;
-            else if (LIVE == 1)
-                dst = (dst & 0xFF00u) | (pk & 0x00FFu);
-            else
-                dst = (dst & 0x00FFu) | (pk & 0xFF00u);
+            } else {
+                uint32_t keep = lf ? 0x00FFu : 0xFF00u;
+                dst = (dst & keep) | (pk & ~keep & 0xFFFFu);
+            }
         }
         // new message into its slot
         uint32_t mp = pack1(mo);
         if (c & 1)
-            msg[c >> 1] = (msg[c >> 1] & 0x0000FFFFu) | (mp << 16);
+            msg[c >> 1] = prmt(msg[c >> 1], mp, 0x5410);
         else
-            msg[c >> 1] = (msg[c >> 1] & 0xFFFF0000u) | mp;
+            msg[c >> 1] = prmt(msg[c >> 1], mp, 0x3254);
     }
 }
 
-template <int CNT>
-__global__ void __launch_bounds__(kLdpcThreads) ldpc_pair_kernel(const __grid_constant__ LdpcParams p) {
+template <int CNT, bool UNIFORM>
+__global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kernel(const __grid_constant__ LdpcParams p) {
     constexpr int SLOTS = CNT + 2;
     constexpr int MW = (SLOTS + 1) / 2;     // message words per row in registers
     constexpr int SG = (SLOTS + 7) / 8;     // uint4 groups per row in the workspace
@@ -303,19 +297,27 @@ __global__ void __launch_bounds__(kLdpcThreads) ldpc_pair_kernel(const __grid_co
                         }
                     }
                 }
-                const uint32_t* L = &p.links[p.layer_off[i]];
-                const int cnt = p.layer_off[i + 1] - p.layer_off[i];
+                const int loff = p.layer_off[i];
+                const int cnt = UNIFORM ? CNT : (int)p.layer_off[i + 1] - loff;
                 const int nlev = p.layer_nlev[i];
                 const int mylev = (nlev > 1 && active) ? p.row_level[i * 360 + j] : 0;
                 const bool has2 = (i | j) != 0;
+                int voff[CNT];   // byte offset of each data link's LLR pair: 2 * (360 g + (j - shift) mod 360)
+#pragma unroll
+                for (int c = 0; c < CNT; ++c) {
+                    uint32_t lk = p.links[loff + ((UNIFORM || c < cnt) ? c : 0)];
+                    int m = j - (int)(lk & 0xFFFFu);
+                    m += (m < 0) ? 360 : 0;
+                    voff[c] = 2 * ((int)(lk >> 16) * 360 + m);
+                }
+                uint8_t* vbytes = reinterpret_cast<uint8_t*>(vdata);
+                const int lf = (live == 2) ? 1 : 0;
                 for (int lvl = 0; lvl < nlev; ++lvl) {
                     if (active && mylev == lvl) {
                         if (live == 3)
-                            row_update<CNT, 3>(vdata, L, cnt, j, msg, pown, psec, has2);
-                        else if (live == 1)
-                            row_update<CNT, 1>(vdata, L, cnt, j, msg, pown, psec, has2);
+                            row_update<CNT, UNIFORM, true>(vbytes, voff, cnt, msg, pown, psec, has2, 0);
                         else
-                            row_update<CNT, 2>(vdata, L, cnt, j, msg, pown, psec, has2);
+                            row_update<CNT, UNIFORM, false>(vbytes, voff, cnt, msg, pown, psec, has2, lf);
                     }
                     __syncthreads();
                 }
@@ -394,17 +396,29 @@ __global__ void __launch_bounds__(kLdpcThreads) ldpc_pair_kernel(const __grid_co
 using KernelFn = void (*)(const LdpcParams);
 struct Variant {
     int cnt;
-    KernelFn fn;
+    KernelFn uniform;   // every layer has exactly cnt data links per row (all normal codes, 5 short ones)
+    KernelFn ragged;    // layers with fewer links exist (short 1/4, 1/2, 3/4, 4/5, 5/6)
 };
-#define V(c) {c, ldpc_pair_kernel<c>}
+#define VU(c) {c, ldpc_pair_kernel<c, true>, nullptr}
+#define VB(c) {c, ldpc_pair_kernel<c, true>, ldpc_pair_kernel<c, false>}
+#define VR(c) {c, nullptr, ldpc_pair_kernel<c, false>}
 // one instantiation per distinct "max data links per row" among the 21 codes
-const Variant kVariants[] = {V(2), V(3), V(4), V(5), V(8), V(9), V(11), V(12), V(16), V(17), V(20), V(25), V(28)};
-#undef V
+const Variant kVariants[] = {VB(2), VU(3), VU(4), VB(5), VU(8), VU(9), VR(11), VU(12), VU(16), VR(17), VU(20), VU(25), VU(28)};
+#undef VU
+#undef VB
+#undef VR
 
 const Variant* pick(int max_cnt) {
     for (const Variant& v : kVariants)
         if (v.cnt >= max_cnt) return &v;
     return nullptr;
+}
+KernelFn pick_fn(const LdpcDev& c) {
+    const Variant* v = pick(c.max_cnt);
+    if (!v) return nullptr;
+    bool uniform = v->cnt == c.max_cnt;
+    for (int i = 0; i < c.q && uniform; ++i) uniform = (c.layer_off[i + 1] - c.layer_off[i]) == v->cnt;
+    return (uniform && v->uniform) ? v->uniform : v->ragged;
 }
 
 }  // namespace
@@ -415,19 +429,20 @@ int ldpc_slot_groups(int max_cnt) {
 }
 
 int ldpc_max_ctas_per_sm(const LdpcDev& code) {
-    const Variant* v = pick(code.max_cnt);
-    if (!v) return 0;
+    KernelFn fn = pick_fn(code);
+    if (!fn) return 0;
     size_t smem = ldpc_smem_bytes(code);
-    cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v->fn, kLdpcThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kLdpcThreads, smem);
     return n;
 }
 
 int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
     const LdpcDev& c = a.code;
     const Variant* v = pick(c.max_cnt);
-    if (!v || c.q > kMaxLayers) return (int)cudaErrorInvalidValue;
+    KernelFn fn = pick_fn(c);
+    if (!v || !fn || c.q > kMaxLayers) return (int)cudaErrorInvalidValue;
     LdpcParams p;
     p.N = c.N; p.K = c.K; p.R = c.R; p.q = c.q; p.ngroups = c.ngroups;
     p.sg = (v->cnt + 2 + 7) / 8;
@@ -444,9 +459,9 @@ int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
     for (int i = 0; i < c.q; ++i) p.layer_nlev[i] = c.layer_nlev[i];
     for (int i = 0; i < nlinks; ++i) p.links[i] = c.links[i];
     size_t smem = ldpc_smem_bytes(c);
-    cudaError_t e = cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    v->fn<<<grid, kLdpcThreads, smem, stream>>>(p);
+    fn<<<grid, kLdpcThreads, smem, stream>>>(p);
     return (int)cudaGetLastError();
 }
 
