@@ -58,55 +58,81 @@ __device__ __forceinline__ uint32_t win360(const uint32_t* H, int o) {
     return r;
 }
 
+// ---- register formats of the row update -------------------------------------------------------
+// LLRs are kept OFFSET-BINARY everywhere inside the kernel (shared memory, workspace, registers):
+// u = llr + 128 in [0, 255], one frame per 16-bit lane.  With that bias the int8 saturation of the
+// reference (vqadd / vqsub) is the single instruction  max(min(a + b, 255), 0)  = VIADDMNMX.RELU.
+__device__ __forceinline__ uint32_t unpack_u01(uint32_t w) { return prmt(w, 0, 0x4140); }  // zero-extended bytes 0,1
+__device__ __forceinline__ uint32_t sat_add_u8x2(uint32_t u, uint32_t d) { return __viaddmin_s16x2_relu(u, d, 0x00FF00FFu); }
+
 // One check row for both frames of the pair.
 //   voff[] : byte offsets into the shared LLR array of this row's data links (hoisted out of the level loop)
-//   msg[]  : this row's CNT+2 message slots as packed bytes, two slots per word (in/out)
-//   pown   : packed parity LLR pty[i][j]              (in/out)
-//   psec   : packed parity LLR of the second link     (in/out, ignored when !has2)
+//   msg[]  : this row's CNT+2 message slots as packed int8, two slots per word (in/out)
+//   pown   : packed offset-binary parity LLR pty[i][j]          (in/out)
+//   psec   : packed offset-binary parity LLR of the second link (in/out, ignored when !has2)
 // EXACT: every one of the CNT data links exists (cnt == CNT); otherwise links c >= cnt are skipped.
 // BOTH : both frames still iterate; otherwise only frame `lf` (0/1) may change, the other keeps its LLRs.
+//
+// Maths (SURVEY.md spec S-LDPC, algorithms.hh:235-256,273-276), per 16-bit lane:
+//   t = sat8(link - msg)                        -> tu = t + 128
+//   a = |t|   (VABSDIFF4 against 128; the reference's  max(|max(t,-127)|-1, 0)  is a monotone function
+//              of a, so the two smallest are found on a itself and the "-1, >= 0, <= 32" is applied after)
+//   ex_k = min of a over the other links        (prefix/suffix minima; == "a_k == min0 ? min1 : min0")
+//   mag_k = clamp(ex_k - 1, 0, 32);  msg_k' = sign * mag_k limited to [-32, 31];  link' = sat8(t + msg_k')
 template <int CNT, bool EXACT, bool BOTH>
 __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const int (&voff)[CNT], int cnt,
                                            uint32_t (&msg)[(CNT + 3) / 2], uint32_t& pown, uint32_t& psec,
                                            bool has2, int lf) {
-    uint32_t t[CNT + 2];
-    uint32_t min0 = kBig, min1 = kBig, sx = 0;
+    constexpr int D = CNT + 2;
+    constexpr uint32_t kNeutralT = 0x00FF00FFu;   // t = +127: never the minimum that matters, sign +
+    uint32_t tu[D], a[D];
+    // sign bookkeeping: bit 7 of tu is set for t >= 0.  For link k the product of the OTHER signs is
+    // negative iff bit7(sx ^ tu_k) ^ parity(D + 1), sx = XOR of all tu (skipped links count as +).
+    uint32_t sx = ((D + 1) & 1) ? 0x00800080u : 0u;
 #pragma unroll
-    for (int c = 0; c < CNT + 2; ++c) {
-        uint32_t v;
+    for (int c = 0; c < D; ++c) {
+        uint32_t u;
+        bool present = true;
         if (c < CNT) {
-            if (!EXACT && c >= cnt) continue;
-            v = unpack01(*reinterpret_cast<const uint16_t*>(vbytes + voff[c]));
+            present = EXACT || c < cnt;
+            u = present ? unpack_u01(*reinterpret_cast<const uint16_t*>(vbytes + voff[c])) : 0u;
         } else if (c == CNT) {
-            v = unpack01(pown);
+            u = unpack_u01(pown);
         } else {
-            v = unpack01(psec);
+            present = has2;
+            u = unpack_u01(psec);
         }
         uint32_t mw = msg[c >> 1];
         uint32_t m = (c & 1) ? unpack23(mw) : unpack01(mw);
-        uint32_t tt = sat8x2(__vsub2(v, m));                 // t = sat8(link - msg)
-        if (c == CNT + 1 && !has2) tt = kP127;               // row (0,0): neutral stand-in (|t|-1 = 126, sign +)
-        t[c] = tt;
-        uint32_t mg = __viaddmax_s16x2(tt, kM1, ~tt);        // max(t-1, -t-1) = |t|-1 (>= -1)
-        min1 = __vmins2(min1, __vmaxs2(min0, mg));
-        min0 = __vmins2(min0, mg);
-        sx ^= tt;
+        uint32_t x = sat_add_u8x2(u, __vsub2(0u, m));        // t = sat8(link - msg), offset binary
+        if (!(EXACT && c < CNT) && c != CNT) x = present ? x : kNeutralT;
+        tu[c] = x;
+        a[c] = __vabsdiffu4(x, 0x00800080u);                 // |t| in [0, 128]
+        sx ^= x;
     }
-    // offset-min-sum magnitudes, clamped to the message range straight away (order-preserving)
-    uint32_t m0c = __vmins2(__vmaxs2(min0, 0u), kP32);
-    uint32_t m1c = __vmins2(__vmaxs2(min1, 0u), kP32);
-    uint32_t sc = __vadd2(m0c, m1c);
+    // exclusive minima of a[] by prefix/suffix scans
+    uint32_t suf[D];
+    suf[D - 1] = a[D - 1];
 #pragma unroll
-    for (int c = 0; c < CNT + 2; ++c) {
-        if (!EXACT && c < CNT && c >= cnt) continue;
-        uint32_t tt = t[c];
-        uint32_t mg = __viaddmax_s16x2(tt, kM1, ~tt);
-        // exclusive minimum: min1 where this link holds the minimum, else min0
-        uint32_t om = __vmins2(m1c, __viaddmax_s16x2(sc, __vsub2(0u, mg), m0c));
-        uint32_t neg = prmt(sx ^ tt, 0, 0xBB99);             // 0xFFFF in lanes where the sign product is -
-        uint32_t mo = __vmins2(__vsub2(om ^ neg, neg), kP31);  // +-om, clamped to [-32, 31]
-        uint32_t vn = sat8x2(__vadd2(tt, mo));
-        uint32_t pk = pack1(vn);
+    for (int c = D - 2; c >= 1; --c) suf[c] = __vminu2(suf[c + 1], a[c]);
+    uint32_t pre = a[0];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        uint32_t ex;
+        if (c == 0) {
+            ex = suf[1];
+        } else if (c == D - 1) {
+            ex = pre;
+        } else {
+            ex = __vminu2(pre, suf[c + 1]);
+            pre = __vminu2(pre, a[c]);
+        }
+        if (c < CNT && !EXACT && c >= cnt) continue;
+        const uint32_t x = tu[c];
+        uint32_t om = __viaddmin_s16x2_relu(ex, kM1, kP32);          // clamp(|t|min - 1, 0, 32)
+        uint32_t neg = prmt(sx ^ x, 0, 0xAA88);                      // 0xFFFF in lanes whose outgoing sign is -
+        uint32_t mo = __viaddmin_s16x2(om ^ neg, neg & 0x00010001u, kP31);  // +-om, limited to [-32, 31]
+        uint32_t pk = pack1(sat_add_u8x2(x, mo));                    // link' = sat8(t + msg')
         if (c < CNT) {
             if (BOTH)
                 *reinterpret_cast<uint16_t*>(vbytes + voff[c]) = (uint16_t)pk;
@@ -121,7 +147,7 @@ __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const i
                 dst = (dst & keep) | (pk & ~keep & 0xFFFFu);
             }
         }
-        // new message into its slot
+        // new message into its slot (two slots per word)
         uint32_t mp = pack1(mo);
         if (c & 1)
             msg[c >> 1] = prmt(msg[c >> 1], mp, 0x5410);
@@ -171,16 +197,16 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
             uint2 a = __ldg(reinterpret_cast<const uint2*>(inA) + x);
             uint2 b = __ldg(reinterpret_cast<const uint2*>(inB) + x);
             uint4 o;
-            o.x = prmt(a.x, b.x, 0x5140);
-            o.y = prmt(a.x, b.x, 0x7362);
-            o.z = prmt(a.y, b.y, 0x5140);
-            o.w = prmt(a.y, b.y, 0x7362);
+            o.x = prmt(a.x, b.x, 0x5140) ^ 0x80808080u;   // interleave A/B bytes, to offset binary
+            o.y = prmt(a.x, b.x, 0x7362) ^ 0x80808080u;
+            o.z = prmt(a.y, b.y, 0x5140) ^ 0x80808080u;
+            o.w = prmt(a.y, b.y, 0x7362) ^ 0x80808080u;
             reinterpret_cast<uint4*>(vdata)[x] = o;
         }
         for (int x = tid; x < R; x += kLdpcThreads) {
             uint32_t a = (uint8_t)__ldg(inA + K + x), b = (uint8_t)__ldg(inB + K + x);
             int jj = x / q, ii = x - jj * q;
-            __stcg(&wpty[360 * ii + jj], (uint16_t)(a | (b << 8)));
+            __stcg(&wpty[360 * ii + jj], (uint16_t)((a | (b << 8)) ^ 0x8080u));
         }
         __syncthreads();
 
@@ -191,7 +217,7 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
         for (int task = wid; task < q * 12; task += kLdpcThreads / 32) {
             int ii = task / 12, w = task - ii * 12;
             int jj = 32 * w + lane;
-            uint32_t v = (jj < 360) ? (uint32_t)__ldcg(&wpty[360 * ii + jj]) : 0x0101u;
+            uint32_t v = ((jj < 360) ? (uint32_t)__ldcg(&wpty[360 * ii + jj]) : 0x8181u) ^ 0x8080u;
             unsigned mA = __ballot_sync(0xFFFFFFFFu, v & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, v & 0x8000u);
             zacc |= zero_bytes(v);
             if (lane == 0) {
@@ -205,7 +231,7 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
             for (int task = wid; task < p.ngroups * 12; task += kLdpcThreads / 32) {
                 int g = task / 12, w = task - g * 12;
                 int m = 32 * w + lane;
-                uint32_t v = (m < 360) ? (uint32_t)vdata[360 * g + m] : 0x0101u;
+                uint32_t v = ((m < 360) ? (uint32_t)vdata[360 * g + m] : 0x8181u) ^ 0x8080u;
                 unsigned mA = __ballot_sync(0xFFFFFFFFu, v & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, v & 0x8000u);
                 zacc |= zero_bytes(v);
                 if (lane == 0) {
@@ -339,7 +365,7 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
                     }
                 }
                 if (i > 0) {
-                    uint32_t fin = active ? psec : 0x0101u;
+                    uint32_t fin = (active ? psec : 0x8181u) ^ 0x8080u;
                     unsigned mA = __ballot_sync(0xFFFFFFFFu, fin & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, fin & 0x8000u);
                     zacc |= zero_bytes(fin);
                     if (lane == 0) {
@@ -351,7 +377,7 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
                 pown = pnext;
             }
             {   // pty[q-1][j]: its second link was served in layer 0, the own link just now -> final
-                uint32_t fin = active ? psec : 0x0101u;
+                uint32_t fin = (active ? psec : 0x8181u) ^ 0x8080u;
                 if (active) __stcg(&wpty[360 * (q - 1) + j], (uint16_t)psec);
                 unsigned mA = __ballot_sync(0xFFFFFFFFu, fin & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, fin & 0x8000u);
                 zacc |= zero_bytes(fin);
@@ -379,13 +405,13 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
         }
         if (p.llr_out) {
             for (int x = tid; x < K; x += kLdpcThreads) {
-                uint32_t v = vdata[x];
+                uint32_t v = vdata[x] ^ 0x8080u;
                 p.llr_out[(size_t)fa * N + x] = (int8_t)(v & 0xFF);
                 if (hasB) p.llr_out[(size_t)fb * N + x] = (int8_t)(v >> 8);
             }
             for (int x = tid; x < R; x += kLdpcThreads) {
                 int jj = x / q, ii = x - jj * q;
-                uint32_t v = __ldcg(&wpty[360 * ii + jj]);
+                uint32_t v = __ldcg(&wpty[360 * ii + jj]) ^ 0x8080u;
                 p.llr_out[(size_t)fa * N + K + x] = (int8_t)(v & 0xFF);
                 if (hasB) p.llr_out[(size_t)fb * N + K + x] = (int8_t)(v >> 8);
             }
