@@ -58,6 +58,40 @@ __device__ __forceinline__ uint32_t win360(const uint32_t* H, int o) {
     return r;
 }
 
+
+// Hard decisions + zero test of 8 consecutive offset-binary LLR pairs (one uint4: A0 B0 A1 B1 ...).
+// Returns bits 0-7 = "A_k negative", bits 8-15 = "B_k negative"; clears bit 7+16f of every byte position in
+// nzacc that sees a zero LLR (nzacc is ANDed: bytes 0,2 belong to frame A, bytes 1,3 to frame B).
+__device__ __forceinline__ uint32_t harvest8(uint4 w, uint32_t& nzacc) {
+    const uint32_t k80 = 0x80808080u;
+    // |llr| per byte; +0x7F sets bit 7 of a byte iff |llr| >= 1 (|llr| <= 128: no carry between bytes)
+    nzacc &= __vabsdiffu4(w.x, k80) + 0x7F7F7F7Fu;
+    nzacc &= __vabsdiffu4(w.y, k80) + 0x7F7F7F7Fu;
+    nzacc &= __vabsdiffu4(w.z, k80) + 0x7F7F7F7Fu;
+    nzacc &= __vabsdiffu4(w.w, k80) + 0x7F7F7F7Fu;
+    // gather the four A bytes / four B bytes of two words, then movemask by multiplication
+    uint32_t a0 = prmt(w.x, w.y, 0x6420), b0 = prmt(w.x, w.y, 0x7531);
+    uint32_t a1 = prmt(w.z, w.w, 0x6420), b1 = prmt(w.z, w.w, 0x7531);
+    auto mask4 = [](uint32_t x) {   // bit k = (byte k of x is a negative LLR) = (offset-binary byte < 128)
+        return (((~x & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xFu;
+    };
+    return mask4(a0) | (mask4(a1) << 4) | (mask4(b0) << 8) | (mask4(b1) << 12);
+}
+// bit planes of n360 groups of 360 LLR pairs starting at src (shared or global, 16-byte aligned):
+// plane A at H[g*13 words], plane B at H[(gstride + g)*13 words], byte k of a group = bits 8k..8k+7
+template <bool GLOBAL>
+__device__ __forceinline__ void harvest_planes(const uint4* src, int n360, uint32_t* H, int gstride, int tid,
+                                               uint32_t& nzacc) {
+    uint8_t* Hb = reinterpret_cast<uint8_t*>(H);
+    for (int t = tid; t < n360 * 45; t += kLdpcThreads) {
+        uint4 w = GLOBAL ? __ldcg(src + t) : src[t];
+        uint32_t bits = harvest8(w, nzacc);
+        int g = t / 45, k = t - g * 45;
+        Hb[g * (kBitWords * 4) + k] = (uint8_t)bits;
+        Hb[(gstride + g) * (kBitWords * 4) + k] = (uint8_t)(bits >> 8);
+    }
+}
+
 // ---- register formats of the row update -------------------------------------------------------
 // LLRs are kept OFFSET-BINARY everywhere inside the kernel (shared memory, workspace, registers):
 // u = llr + 128 in [0, 255], one frame per 16-bit lane.  With that bias the int8 saturation of the
@@ -177,8 +211,8 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
                                                  (size_t)q * SG * 360 * 16);
     const int npairs = (p.nframes + 1) >> 1;
 
-    // zero the pad words of the bit planes once
-    for (int x = tid; x < 2 * (p.ngroups + q); x += kLdpcThreads) HD[x * kBitWords + 12] = 0;
+    // zero the bit planes once: bytes 45..51 of every 360-bit group are never written and must read as 0
+    for (int x = tid; x < 2 * (p.ngroups + q) * kBitWords; x += kLdpcThreads) HD[x] = 0;
 
     for (;;) {
         __syncthreads();
@@ -212,40 +246,20 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
 
         int live = hasB ? 3 : 1;      // bit f set: frame f still iterating
         int resA = -1, resB = -1;
-        uint32_t zacc = 0;            // zero-LLR flags gathered since the last syndrome test
-        // hard decisions + zero flags of the parity part, straight from the workspace (initial state)
-        for (int task = wid; task < q * 12; task += kLdpcThreads / 32) {
-            int ii = task / 12, w = task - ii * 12;
-            int jj = 32 * w + lane;
-            uint32_t v = ((jj < 360) ? (uint32_t)__ldcg(&wpty[360 * ii + jj]) : 0x8181u) ^ 0x8080u;
-            unsigned mA = __ballot_sync(0xFFFFFFFFu, v & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, v & 0x8000u);
-            zacc |= zero_bytes(v);
-            if (lane == 0) {
-                HP[ii * kBitWords + w] = mA;
-                HP[(q + ii) * kBitWords + w] = mB;
-            }
-        }
+        uint32_t nzacc = 0xFFFFFFFFu; // bit 7 of byte f (+16) cleared once frame f shows a zero LLR
+        // hard decisions + zero test of the parity part, straight from the workspace
+        harvest_planes<true>(reinterpret_cast<const uint4*>(wpty), q, HP, q, tid, nzacc);
 
         for (int n = 0;; ++n) {
-            // ---- hard decisions + zero flags of the systematic part
-            for (int task = wid; task < p.ngroups * 12; task += kLdpcThreads / 32) {
-                int g = task / 12, w = task - g * 12;
-                int m = 32 * w + lane;
-                uint32_t v = ((m < 360) ? (uint32_t)vdata[360 * g + m] : 0x8181u) ^ 0x8080u;
-                unsigned mA = __ballot_sync(0xFFFFFFFFu, v & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, v & 0x8000u);
-                zacc |= zero_bytes(v);
-                if (lane == 0) {
-                    HD[g * kBitWords + w] = mA;
-                    HD[(p.ngroups + g) * kBitWords + w] = mB;
-                }
-            }
+            // ---- hard decisions + zero test of the systematic part
+            harvest_planes<false>(reinterpret_cast<const uint4*>(vdata), p.ngroups, HD, p.ngroups, tid, nzacc);
             if (tid < 2) s_bad[tid] = 0;
             __syncthreads();
             // ---- LDPCDecoder::bad (layered_decoder.hh:28-45) on bit planes: a row is bad when its sign
             //      product is not positive, i.e. odd parity of hard decisions or any zero LLR
-            if (zacc & 0x80u) atomicOr(&s_bad[0], 1);
-            if (zacc & 0x8000u) atomicOr(&s_bad[1], 1);
-            zacc = 0;
+            if (~nzacc & 0x00800080u) atomicOr(&s_bad[0], 1);
+            if (~nzacc & 0x80008000u) atomicOr(&s_bad[1], 1);
+            nzacc = 0xFFFFFFFFu;
             for (int task = tid; task < q * 12; task += kLdpcThreads) {
                 int ii = task / 12, w = task - ii * 12;
                 const uint32_t* L = &p.links[p.layer_off[ii]];
@@ -300,6 +314,7 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
                     for (int s = 0; s < SG; ++s) nxt[s] = __ldcg(&wmsg[(size_t)s * 360 + j]);
                 }
             }
+            int mylev_next = (active && p.layer_nlev[0] > 1) ? p.row_level[j] : 0;
             for (int i = 0; i < q; ++i) {
                 if (active) {
                     if (!first) {
@@ -326,7 +341,9 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
                 const int loff = p.layer_off[i];
                 const int cnt = UNIFORM ? CNT : (int)p.layer_off[i + 1] - loff;
                 const int nlev = p.layer_nlev[i];
-                const int mylev = (nlev > 1 && active) ? p.row_level[i * 360 + j] : 0;
+                const int mylev = mylev_next;
+                if (i + 1 < q && active && p.layer_nlev[i + 1] > 1) mylev_next = p.row_level[(i + 1) * 360 + j];
+                else mylev_next = 0;
                 const bool has2 = (i | j) != 0;
                 int voff[CNT];   // byte offset of each data link's LLR pair: 2 * (360 g + (j - shift) mod 360)
 #pragma unroll
@@ -364,29 +381,14 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
                         __stcg(&wpty[360 * (i - 1) + j], (uint16_t)psec);
                     }
                 }
-                if (i > 0) {
-                    uint32_t fin = (active ? psec : 0x8181u) ^ 0x8080u;
-                    unsigned mA = __ballot_sync(0xFFFFFFFFu, fin & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, fin & 0x8000u);
-                    zacc |= zero_bytes(fin);
-                    if (lane == 0) {
-                        HP[(i - 1) * kBitWords + wid] = mA;
-                        HP[(q + i - 1) * kBitWords + wid] = mB;
-                    }
-                }
                 psec = pown;
                 pown = pnext;
             }
-            {   // pty[q-1][j]: its second link was served in layer 0, the own link just now -> final
-                uint32_t fin = (active ? psec : 0x8181u) ^ 0x8080u;
-                if (active) __stcg(&wpty[360 * (q - 1) + j], (uint16_t)psec);
-                unsigned mA = __ballot_sync(0xFFFFFFFFu, fin & 0x80u), mB = __ballot_sync(0xFFFFFFFFu, fin & 0x8000u);
-                zacc |= zero_bytes(fin);
-                if (lane == 0) {
-                    HP[(q - 1) * kBitWords + wid] = mA;
-                    HP[(2 * q - 1) * kBitWords + wid] = mB;
-                }
-            }
+            // pty[q-1][j]: its second link was served in layer 0, the own link just now -> final
+            if (active) __stcg(&wpty[360 * (q - 1) + j], (uint16_t)psec);
             __syncthreads();
+            // hard decisions + zero test of the parity part after this pass
+            harvest_planes<true>(reinterpret_cast<const uint4*>(wpty), q, HP, q, tid, nzacc);
         }
 
         // ---- results: iteration counts, MSB-first hard decisions of the K systematic bits
