@@ -281,14 +281,14 @@ def main():
     fer = float((res["bch_corr"] < 0).mean())
 
     # ---- e2e: public host API, pinned host buffers, copies inside the timed region
-    e2e_frames = min(args.pool, 2048)
+    e2e_frames = min(args.pool, 4096)
     L = pkg.lib()
     h_in = L.dvbs2fec_alloc_pinned(e2e_frames * N)
     h_bb = L.dvbs2fec_alloc_pinned(e2e_frames * (kbch // 8))
     h_res = L.dvbs2fec_alloc_pinned(e2e_frames * 16)
     host_copy = pool[:e2e_frames].cpu().numpy()
     C.memmove(h_in, host_copy.ctypes.data, e2e_frames * N)
-    dec_e = pkg.DVBS2Decoder(devices=[local_rank], max_batch=512, max_trials=MAX_TRIALS)
+    dec_e = pkg.DVBS2Decoder(devices=[local_rank], max_batch=1024, max_trials=MAX_TRIALS)
     dec_e.setDemodParams(MODCOD, SHORT, False, MAX_TRIALS)
     for _ in range(2):
         dec_e.decode_batch_raw(h_in, e2e_frames, h_bb, h_res)

@@ -105,6 +105,7 @@ struct Slot {
     uint8_t* user_bb = nullptr;
     dvbs2fec_result* user_res = nullptr;
     int pending = 0;
+    bool staged_out = true;
     uint64_t tag_base = 0;
 };
 
@@ -330,17 +331,22 @@ int enqueue_chain(dvbs2fec_handle* h, DevCtx& d, Slot& s, const float* d_sym, co
     return 0;
 }
 
+bool is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int finish_slot(dvbs2fec_handle* h, Slot& s) {
     if (!s.pending) return 0;
     CU(cudaEventSynchronize(s.done));
     const size_t kb = h->code->kbch / 8;
-    if (s.user_bb && s.user_bb != s.h_bb.p) memcpy(s.user_bb, s.h_bb.p, (size_t)s.pending * kb);
-    if (s.user_res) {
-        for (int i = 0; i < s.pending; ++i) {
-            s.user_res[i] = s.h_res.p[i];
-            s.user_res[i].tag = s.tag_base + i;
-        }
-    }
+    if (s.user_bb && s.staged_out) memcpy(s.user_bb, s.h_bb.p, (size_t)s.pending * kb);
+    if (s.user_res && s.staged_out) memcpy(s.user_res, s.h_res.p, (size_t)s.pending * sizeof(dvbs2fec_result));
     s.pending = 0;
     return 0;
 }
@@ -359,23 +365,32 @@ int run_device_share(dvbs2fec_handle* h, DevCtx& d, const int8_t* llr, const flo
         int rc = reserve_slot(h, d, d.slot[k], chunk, sym != nullptr, true);
         if (rc) return rc;
     }
+    // caller buffers that are already page-locked are used directly; pageable ones are staged
+    const bool pin_in = is_pinned(in);
+    const bool pin_out = (!bb || is_pinned(bb)) && (!res || is_pinned(res));
     int which = 0, rc = 0;
     for (int f0 = 0; f0 < n; f0 += chunk, which ^= 1) {
         Slot& s = d.slot[which];
         const int m = std::min(chunk, n - f0);
         if ((rc = finish_slot(h, s))) return rc;
-        // stage through pinned memory (the caller's buffers are ordinary pageable memory)
-        memcpy(s.h_in.p, in + (size_t)f0 * in_frame_bytes, (size_t)m * in_frame_bytes);
+        const uint8_t* src = in + (size_t)f0 * in_frame_bytes;
+        if (!pin_in) {
+            memcpy(s.h_in.p, src, (size_t)m * in_frame_bytes);
+            src = s.h_in.p;
+        }
         void* dst = sym ? (void*)s.sym.p : (void*)s.llr.p;
-        CU(cudaMemcpyAsync(dst, s.h_in.p, (size_t)m * in_frame_bytes, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(dst, src, (size_t)m * in_frame_bytes, cudaMemcpyHostToDevice, s.stream));
         rc = enqueue_chain(h, d, s, sym ? s.sym.p : nullptr, sym ? nullptr : s.llr.p, m, s.bb.p, s.res.p, s.stream,
-                           launches);
+                           launches, tag0 + f0);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(s.h_bb.p, s.bb.p, (size_t)m * kb, cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaMemcpyAsync(s.h_res.p, s.res.p, (size_t)m * sizeof(dvbs2fec_result), cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaEventRecord(s.done, s.stream));
         s.user_bb = bb ? bb + (size_t)f0 * kb : nullptr;
         s.user_res = res ? res + f0 : nullptr;
+        s.staged_out = !pin_out;
+        if (bb) CU(cudaMemcpyAsync(pin_out ? s.user_bb : s.h_bb.p, s.bb.p, (size_t)m * kb, cudaMemcpyDeviceToHost, s.stream));
+        if (res)
+            CU(cudaMemcpyAsync(pin_out ? (void*)s.user_res : (void*)s.h_res.p, s.res.p, (size_t)m * sizeof(dvbs2fec_result),
+                               cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaEventRecord(s.done, s.stream));
         s.tag_base = tag0 + f0;
         s.pending = m;
     }

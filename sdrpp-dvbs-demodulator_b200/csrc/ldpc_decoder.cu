@@ -119,7 +119,7 @@ __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const i
                                            bool has2, int lf) {
     constexpr int D = CNT + 2;
     constexpr uint32_t kNeutralT = 0x00FF00FFu;   // t = +127: never the minimum that matters, sign +
-    uint32_t tu[D], a[D];
+    uint32_t tu[D], a[D], mo_keep[D];
     // sign bookkeeping: bit 7 of tu is set for t >= 0.  For link k the product of the OTHER signs is
     // negative iff bit7(sx ^ tu_k) ^ parity(D + 1), sx = XOR of all tu (skipped links count as +).
     uint32_t sx = ((D + 1) & 1) ? 0x00800080u : 0u;
@@ -181,12 +181,15 @@ __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const i
                 dst = (dst & keep) | (pk & ~keep & 0xFFFFu);
             }
         }
-        // new message into its slot (two slots per word)
-        uint32_t mp = pack1(mo);
-        if (c & 1)
-            msg[c >> 1] = prmt(msg[c >> 1], mp, 0x5410);
-        else
-            msg[c >> 1] = prmt(msg[c >> 1], mp, 0x3254);
+        mo_keep[c] = mo;
+    }
+    // new messages go back two slots per word, packed pairwise
+#pragma unroll
+    for (int c = 0; c < D; c += 2) {
+        bool ok0 = EXACT || c >= CNT || c < cnt;
+        bool ok1 = (c + 1 < D) && (EXACT || c + 1 >= CNT || c + 1 < cnt);
+        uint32_t lo = ok0 ? mo_keep[c] : 0u, hi = ok1 ? mo_keep[c + 1 < D ? c + 1 : c] : 0u;
+        msg[c >> 1] = pack2(lo, hi);
     }
 }
 

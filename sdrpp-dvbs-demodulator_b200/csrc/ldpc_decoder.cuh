@@ -58,7 +58,7 @@ struct LdpcArgs {
 };
 
 inline size_t ldpc_workspace_bytes(const LdpcDev& c) {
-    return (size_t)c.q * c.sg * 360 * 16 + (size_t)c.R * 2 + 256;
+    return (((size_t)c.q * c.sg * 360 * 16 + (size_t)c.R * 2) + 255) & ~(size_t)255;
 }
 inline size_t ldpc_smem_bytes(const LdpcDev& c) {
     return (size_t)c.K * 2 + (size_t)2 * (c.ngroups + c.q) * kBitWords * 4 + 64;
