@@ -318,10 +318,8 @@ def main():
         latency[str(b)] = round(sorted(ts)[2], 4)
 
     # ---- reduce over ranks
-    t = torch.tensor([ms, e2e_s * 1e3, ldpc_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, ldpc_ms_max = [float(x) for x in t.tolist()]
+    dispatch = importlib.import_module("sdrpp-dvbs-demodulator_b200.dispatch")
+    ms_max, e2e_ms_max, ldpc_ms_max = dispatch.reduce_max([ms, e2e_s * 1e3, ldpc_ms], device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -1,0 +1,109 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the reference's own code compiled unmodified (oracle/_ref).
+
+The reference ships no tests or vectors for its decode stage; these fixtures are
+outputs of the reference itself, run in the build container:
+
+    make -C oracle ref && python tools/make_golden.py
+
+Each fixture holds seeded inputs and what the reference produced for them.  tests/test_golden.py checks
+the C oracle against them on the CPU and the CUDA library against them on the GPU box (where
+/root/reference does not exist)."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import orclib  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+SNR = {0: -2.0, 1: -1.0, 2: 0.0, 3: 1.3, 4: 2.6, 5: 3.4, 6: 4.3, 7: 5.0, 8: 5.5, 10: 6.5, 11: 6.7}
+
+
+def ldpc_chain_fixture(short, rate, nframes, seed):
+    r = orclib.ref()
+    p = orclib.code_params(short, rate)
+    rng = np.random.default_rng(seed)
+    llr = np.zeros((nframes, p["N"]), np.int8)
+    for i in range(nframes):
+        _, code = orclib.encode_frame(short, rate, rng)
+        llr[i] = orclib.awgn_llr(code, SNR[rate] + (0.4 if short else 0.0) + 0.9 * (i / max(1, nframes - 1) - 0.4), rng)
+    llr[0, ::131] = 0
+    post = llr.copy()
+    iters = np.zeros(nframes, np.int16)
+    corr = np.zeros(nframes, np.int16)
+    bb = np.zeros((nframes, p["kbch"] // 8), np.uint8)
+    for i in range(nframes):
+        iters[i] = r.ref_ldpc_decode(short, rate, post[i], 25)
+        packed = np.packbits((post[i, : p["K"]] < 0).astype(np.uint8))
+        corr[i] = r.ref_bch_decode(short, rate, packed)
+        r.ref_descramble(short, rate, packed)
+        bb[i] = packed[: p["kbch"] // 8]
+    return dict(short=short, rate=rate, max_trials=25, llr=llr, post_sha=np.frombuffer(
+        b"".join(hashlib.sha256(post[i].tobytes()).digest() for i in range(nframes)), np.uint8).reshape(nframes, 32),
+        iters=iters, corr=corr, bb=bb)
+
+
+def bch_fixture(short, rate, seed):
+    r = orclib.ref()
+    p = orclib.code_params(short, rate)
+    rng = np.random.default_rng(seed)
+    K, kbch, t = p["K"], p["kbch"], p["t"]
+    nerrs = [0, 1, 2, 3, t - 1, t, t + 1, t + 4, 60]
+    frames = np.zeros((len(nerrs), K // 8), np.uint8)
+    for i, ne in enumerate(nerrs):
+        frames[i, : kbch // 8] = rng.integers(0, 256, kbch // 8, dtype=np.uint8)
+        r.ref_bch_encode(short, rate, frames[i])
+        for e in rng.choice(K, ne, replace=False):
+            frames[i, e >> 3] ^= 0x80 >> (e & 7)
+    out = frames.copy()
+    corr = np.array([r.ref_bch_decode(short, rate, out[i]) for i in range(len(nerrs))], np.int16)
+    return dict(short=short, rate=rate, frames=frames, corrected=out, corr=corr)
+
+
+def demap_fixture(ctype, const, short, rate, g1, g2, seed):
+    r = orclib.ref()
+    bits = {1: 2, 3: 3, 4: 4, 5: 5}[ctype]
+    n = 16200 if short else 64800
+    nsym = n // bits
+    rng = np.random.default_rng(seed)
+    labels = rng.integers(0, 1 << bits, nsym).astype(np.uint8)
+    pts = np.zeros(2 * nsym, np.float32)
+    r.ref_mod(ctype, g1, g2, labels, nsym, pts)
+    sym = pts + rng.normal(0, 0.08, pts.shape).astype(np.float32)
+    soft = np.zeros(nsym * bits, np.int8)
+    if ctype == 5:
+        r.ref_demap_calc(ctype, g1, g2, sym, nsym, soft)
+    else:
+        r.ref_demap(ctype, g1, g2, sym, nsym, soft)
+    out = np.zeros(n, np.int8)
+    r.ref_deinterleave(const, short, rate, soft.copy(), out)
+    pl = np.zeros(2 * (90 + nsym), np.float32)
+    pl[180:] = sym
+    return dict(ctype=ctype, const=const, short=short, rate=rate, g1=g1, g2=g2, plframe=pl, llr=out)
+
+
+def main():
+    if not orclib.have_ref():
+        raise SystemExit("oracle/_ref/libdvbs2_ref.so is missing: run `make -C oracle ref` in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    for name, (short, rate, n) in {"chain_s1_2": (1, 3, 6), "chain_s8_9": (1, 10, 4), "chain_s1_4": (1, 0, 4),
+                                   "chain_n1_2": (0, 3, 2)}.items():
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **ldpc_chain_fixture(short, rate, n, 4242 + rate))
+    np.savez_compressed(os.path.join(OUT, "bch_n12.npz"), **bch_fixture(0, 3, 1))
+    np.savez_compressed(os.path.join(OUT, "bch_n10.npz"), **bch_fixture(0, 5, 2))
+    np.savez_compressed(os.path.join(OUT, "bch_n8.npz"), **bch_fixture(0, 10, 3))
+    np.savez_compressed(os.path.join(OUT, "bch_s12.npz"), **bch_fixture(1, 3, 4))
+    np.savez_compressed(os.path.join(OUT, "demap_qpsk.npz"), **demap_fixture(1, 0, 1, 3, 0.0, 0.0, 5))
+    np.savez_compressed(os.path.join(OUT, "demap_8psk35.npz"), **demap_fixture(3, 1, 1, 4, 0.0, 0.0, 6))
+    np.savez_compressed(os.path.join(OUT, "demap_16apsk.npz"), **demap_fixture(4, 2, 1, 5, 3.15, 0.0, 7))
+    np.savez_compressed(os.path.join(OUT, "demap_32apsk.npz"), **demap_fixture(5, 3, 1, 6, 2.84, 5.27, 8))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
