@@ -34,7 +34,8 @@ def test_round_trip_qpsk_half_normal_batch():
     ok = res["bch_corr"] >= 0
     assert ok.mean() > 0.995
     assert np.array_equal(bb[ok], payload[ok])
-    assert (res["ldpc_iters"][ok] >= 0).all() and res["ldpc_iters"].max() <= 25
+    # (a frame may run out of LDPC iterations with a few residual errors that BCH then removes: -1 with corr >= 0)
+    assert res["ldpc_iters"].min() >= -1 and res["ldpc_iters"].max() <= 25 and (res["ldpc_iters"] >= 0).mean() > 0.99
     assert np.array_equal(res["tag"], np.arange(n))
     # oracle spot check, iteration counts included
     o = orclib.oracle()
@@ -108,3 +109,114 @@ def test_in_process_multi_gpu_sharding_matches_single_gpu():
     assert np.array_equal(bb1, bb2) and np.array_equal(r1, r2)
     one.close()
     two.close()
+
+
+# ---- the other BASELINE.json configurations as parity cases -------------------------------------------
+
+def _symbols_batch(modcod, short, n, sigma, seed):
+    rng = np.random.default_rng(seed)
+    info = pkg.modcod_info(modcod, short)
+    payload = rng.integers(0, 256, (n, info["kbch"] // 8), dtype=np.uint8)
+    pl = np.stack([pkg.modulate(modcod, short, False, pkg.encode_fecframe(modcod, short, payload[i])) for i in range(n)])
+    noisy = pl.view(np.float32) + rng.normal(0, sigma, (n, info["plframe_symbols"] * 2)).astype(np.float32)
+    return noisy, payload
+
+
+def _oracle_from_symbols(modcod, short, noisy, max_trials):
+    from fec import MODCODS
+    const, ctype, rate, g1, g2 = MODCODS[modcod]
+    o = orclib.oracle()
+    c = o.orc_const_create(ctype, g1, g2)
+    info = pkg.modcod_info(modcod, short)
+    out = []
+    for i in range(len(noisy)):
+        llr = np.zeros(info["nldpc"], np.int8)
+        o.orc_bb_to_soft(c, const, int(short), rate, np.ascontiguousarray(noisy[i]), llr)
+        bb = np.zeros(info["kbch"] // 8, np.uint8)
+        it, co = C.c_int(), C.c_int()
+        o.orc_decode_frame(int(short), rate, llr, max_trials, bb, C.byref(it), C.byref(co))
+        out.append((bb, it.value, co.value))
+    o.orc_const_destroy(c)
+    return out
+
+
+def test_config2_8psk_3_5_normal_high_iteration_regime():
+    """8PSK 3/5 normal frames from int8 LLRs near threshold: many iterations, some failures; vs oracle."""
+    dec = pkg.DVBS2Decoder(max_batch=64, max_trials=25)
+    dec.setDemodParams(12, False, False)
+    o = orclib.oracle()
+    rng = np.random.default_rng(12)
+    n = 10
+    llr = np.zeros((n, 64800), np.int8)
+    for i in range(n):
+        _, code = orclib.encode_frame(0, 4, rng)
+        llr[i] = orclib.awgn_llr(code, 2.45 + 0.04 * i, rng)   # per-dimension BPSK-equivalent LLRs around the 3/5 threshold
+    bb, res = dec.decode_batch(llr)
+    its = []
+    for i in range(n):
+        want = np.zeros(dec.kbch // 8, np.uint8)
+        it, co = C.c_int(), C.c_int()
+        o.orc_decode_frame(0, 4, llr[i].copy(), 25, want, C.byref(it), C.byref(co))
+        assert (res["ldpc_iters"][i], res["bch_corr"][i]) == (it.value, co.value)
+        assert np.array_equal(bb[i], want)
+        its.append(it.value if it.value >= 0 else 25)
+    assert np.mean(its) > 10   # high-iteration regime
+    dec.close()
+
+
+@pytest.mark.parametrize("modcod,sigma", [(18, 0.03), (28, 0.012)])
+def test_config4_apsk_normal_full_chain_from_symbols(modcod, sigma):
+    """16APSK 2/3 and 32APSK 9/10 normal frames: demap + LDPC + BCH + descramble from PLFRAME symbols."""
+    dec = pkg.DVBS2Decoder(max_batch=16)
+    dec.setDemodParams(modcod, False, False)
+    noisy, payload = _symbols_batch(modcod, False, 3, sigma, modcod)
+    bb, res = dec.decode_plframes(noisy)
+    assert (res["bch_corr"] >= 0).all()
+    assert np.array_equal(bb, payload)
+    if modcod == 18:   # LUT demapper: the whole chain is bit-exact with the oracle
+        for i, (wbb, wit, wco) in enumerate(_oracle_from_symbols(modcod, False, noisy, 25)):
+            assert (res["ldpc_iters"][i], res["bch_corr"][i]) == (wit, wco)
+            assert np.array_equal(bb[i], wbb)
+    dec.close()
+
+
+def test_config3_short_frame_modcod_sweep_from_symbols():
+    """all ten short-frame QPSK codes (1/4 ... 8/9) with the fused demapper, against the oracle chain"""
+    dec = pkg.DVBS2Decoder(max_batch=16)
+    for modcod in range(1, 11):
+        dec.setDemodParams(modcod, True, False)
+        noisy, payload = _symbols_batch(modcod, True, 3, 0.09, 100 + modcod)
+        bb, res = dec.decode_plframes(noisy)
+        for i, (wbb, wit, wco) in enumerate(_oracle_from_symbols(modcod, True, noisy, 25)):
+            assert (res["ldpc_iters"][i], res["bch_corr"][i]) == (wit, wco), modcod
+            assert np.array_equal(bb[i], wbb), modcod
+        assert np.array_equal(bb, payload), modcod
+    dec.close()
+
+
+def test_config5_mixed_modcod_transponders_in_submission_order():
+    """several logical transponders (one handle each, different MODCODs) fed round-robin through the queue"""
+    specs = [(4, False), (6, True), (13, False), (4, True)]
+    decs, frames, want = [], [], []
+    rng = np.random.default_rng(55)
+    for modcod, short in specs:
+        d = pkg.DVBS2Decoder(max_batch=8, max_latency_us=500)
+        d.setDemodParams(modcod, short, False)
+        decs.append(d)
+        info = pkg.modcod_info(modcod, short)
+        pay = rng.integers(0, 256, (5, info["kbch"] // 8), dtype=np.uint8)
+        llr = np.stack([np.where(pkg.encode_fecframe(modcod, short, pay[i]) > 0, -12, 12).astype(np.int8) for i in range(5)])
+        flips = rng.integers(0, info["nldpc"], (5, 40))
+        for i in range(5):
+            llr[i, flips[i]] = -llr[i, flips[i]]
+        frames.append(llr)
+        want.append(pay)
+    for i in range(5):
+        for t, d in enumerate(decs):
+            d.submit_llr(frames[t][i], 10 * t + i)
+    for t, d in enumerate(decs):
+        d.flush()
+        bb, res = d.collect(16, timeout_us=5_000_000)
+        assert np.array_equal(res["tag"], 10 * t + np.arange(5))
+        assert np.array_equal(bb, want[t])
+        d.close()
