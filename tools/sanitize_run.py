@@ -1,0 +1,33 @@
+#!/usr/bin/env python3
+"""Small whole-stage run for compute-sanitizer (memcheck / racecheck): a few short and normal frames."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("sdrpp-dvbs-demodulator_b200")
+rng = np.random.default_rng(0)
+dec = pkg.DVBS2Decoder(max_batch=8, max_trials=6)
+for modcod, short, n in ((4, True, 5), (13, True, 3), (4, False, 3)):
+    dec.setDemodParams(modcod, short, False, 6)
+    pay = rng.integers(0, 256, (n, dec.kbch // 8), dtype=np.uint8)
+    pl = np.stack([pkg.modulate(modcod, short, False, pkg.encode_fecframe(modcod, short, pay[i])) for i in range(n)])
+    noisy = pl.view(np.float32) + rng.normal(0, 0.08, (n, dec.plframe_symbols * 2)).astype(np.float32)
+    bb, res = dec.decode_plframes(noisy)
+    print(modcod, short, (bb == pay).all(), res["ldpc_iters"].tolist(), res["bch_corr"].tolist())
+# LLR path near threshold: several LDPC iterations, level-scheduled layers, frozen-lane path, BCH corrections
+for modcod, short, esn0 in ((4, True, 1.6), (5, True, 3.2), (4, False, 1.6)):
+    dec.setDemodParams(modcod, short, False, 6)
+    n = 5
+    a = 1 / np.sqrt(2.0)
+    sigma2 = 1.0 / (2.0 * 10 ** (esn0 / 10.0))
+    codes = np.stack([pkg.encode_fecframe(modcod, short, rng.integers(0, 256, dec.kbch // 8, dtype=np.uint8)) for _ in range(n)])
+    y = (1.0 - 2.0 * codes.astype(np.float32)) * a + rng.normal(0, np.sqrt(sigma2), codes.shape).astype(np.float32)
+    llr = np.clip(np.rint(4.0 * 2.0 * a * y / sigma2), -127, 127).astype(np.int8)
+    llr[0, :40] = -llr[0, :40]
+    bb, res = dec.decode_batch(llr)
+    print(modcod, short, res["ldpc_iters"].tolist(), res["bch_corr"].tolist())
+dec.close()
