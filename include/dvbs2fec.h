@@ -29,6 +29,8 @@ extern "C" {
 
 #define DVBS2FEC_FLAG_LDPC_FAIL 1u /* LDPC never met all parity checks (BBFrameLDPC::decode returned -1) */
 #define DVBS2FEC_FLAG_BCH_FAIL 2u  /* BBFrameBCH::decode returned -1 */
+#define DVBS2FEC_FLAG_BBHEADER_CRC_FAIL 4u /* CRC-8 over the 80 BBHEADER bits is non-zero: BBFrameTSParser::work would
+                                              drop this frame (dvbs2/bbframe_ts_parser.cpp:66-80,121-134) */
 
 typedef struct dvbs2fec_handle dvbs2fec_handle;
 

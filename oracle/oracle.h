@@ -40,6 +40,9 @@ int orc_bch_decode(int shortframe, int rate, uint8_t* frame);
 int orc_bch_encode(int shortframe, int rate, uint8_t* frame);
 /* BBFrameDescrambler::work (bbframe_descramble.cpp:122-143) */
 int orc_descramble(int shortframe, int rate, uint8_t* frame);
+/* BBFrameTSParser::check_crc8(bbf, 80) (dvbs2/bbframe_ts_parser.cpp:66-80): 0 = BBHEADER valid.  Restated only:
+ * the parser needs SDR++ core headers and is not part of the oracle/_ref build (parity unpinned by execution). */
+unsigned orc_bbheader_crc8(const uint8_t* bbframe);
 /* whole A3..A10 chain for one frame: llr[N] in (modified), bb[kbch/8] out */
 int orc_decode_frame(int shortframe, int rate, int8_t* llr, int max_trials, uint8_t* bb, int* ldpc_iters, int* bch_corr);
 

@@ -375,3 +375,16 @@ int orc_decode_frame(int shortframe, int rate, int8_t* llr, int max_trials, uint
     if (bch_corr) *bch_corr = corr;
     return 0;
 }
+
+/* BBFrameTSParser::check_crc8 (dvbs2/bbframe_ts_parser.cpp:66-80) over the 80 BBHEADER bits */
+unsigned orc_bbheader_crc8(const uint8_t* bbframe)
+{
+    unsigned crc = 0;
+    for (int n = 0; n < 80; ++n) {
+        unsigned b = (unsigned)get_bit(bbframe, n) ^ (crc & 1u);
+        crc >>= 1;
+        if (b)
+            crc ^= 0xAB;
+    }
+    return crc;
+}

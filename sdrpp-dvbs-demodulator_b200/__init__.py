@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_HERE, "libdvbs2fec.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "dvbs2fec.h")
 
 EINVAL, ENODEV, ECUDA, EAGAIN = -22, -19, -5, -11
-FLAG_LDPC_FAIL, FLAG_BCH_FAIL = 1, 2
+FLAG_LDPC_FAIL, FLAG_BCH_FAIL, FLAG_BBHEADER_CRC_FAIL = 1, 2, 4
 
 # reference dvbs2_code_rate_t numbering (dvbs2/dvbs2.h:11-25)
 RATE_NAMES = {0: "1/4", 1: "1/3", 2: "2/5", 3: "1/2", 4: "3/5", 5: "2/3", 6: "3/4", 7: "4/5", 8: "5/6", 10: "8/9", 11: "9/10"}

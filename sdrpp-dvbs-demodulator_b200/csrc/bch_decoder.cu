@@ -272,6 +272,18 @@ __global__ void __launch_bounds__(kWarps * 32) bch_kernel(const __grid_constant_
                 rr.ldpc_iters = (short)it;
                 rr.bch_corr = (short)corr;
                 rr.flags = (it < 0 ? 1u : 0u) | (corr < 0 ? 2u : 0u);
+                if (a.descramble) {
+                    // BBHEADER CRC-8 as the downstream parser checks it (bbframe_ts_parser.cpp:66-80): bit-serial,
+                    // MSB first, reflected polynomial 0xAB over the first 80 descrambled bits; valid iff it ends at 0
+                    uint32_t crc = 0;
+                    for (int n = 0; n < 80; ++n) {
+                        uint32_t byte = fr[n >> 3] ^ c.prbs[n >> 3];
+                        uint32_t b = ((byte >> (7 - (n & 7))) & 1u) ^ (crc & 1u);
+                        crc >>= 1;
+                        if (b) crc ^= 0xABu;
+                    }
+                    if (crc) rr.flags |= 4u;
+                }
                 reinterpret_cast<ResultRec*>(a.results)[frame] = rr;
             }
         }

@@ -48,6 +48,8 @@ def oracle():
         lib.orc_bch_decode.argtypes = [C.c_int, C.c_int, _u8p]
         lib.orc_bch_encode.argtypes = [C.c_int, C.c_int, _u8p]
         lib.orc_descramble.argtypes = [C.c_int, C.c_int, _u8p]
+        lib.orc_bbheader_crc8.argtypes = [_u8p]
+        lib.orc_bbheader_crc8.restype = C.c_uint
         lib.orc_decode_frame.argtypes = [C.c_int, C.c_int, _i8p, C.c_int, _u8p, ip, ip]
         lib.orc_const_create.argtypes = [C.c_int, C.c_float, C.c_float]
         lib.orc_const_create.restype = C.c_void_p

@@ -194,7 +194,9 @@ def test_whole_stage_bit_exact(dec, short, rate, n):
     assert np.array_equal(bb, want_bb)
     assert np.array_equal(res["tag"], np.arange(n))
     flags = (want_it < 0) * 1 + (want_c < 0) * 2
-    assert np.array_equal(res["flags"], flags)
+    assert np.array_equal(res["flags"] & 3, flags)
+    crc_bad = np.array([orclib.oracle().orc_bbheader_crc8(np.ascontiguousarray(want_bb[i])) != 0 for i in range(n)])
+    assert np.array_equal((res["flags"] & 4) != 0, crc_bad)
     assert dec.last_launch_count() >= 2
 
 
@@ -262,3 +264,25 @@ def test_stage_objects_mirror_reference_interface():
     orclib.oracle().orc_descramble(1, 3, payload_copy := np.concatenate([payload, np.zeros(21, np.uint8)]))
     assert np.array_equal(packed[: 7032 // 8], payload_copy[: 7032 // 8])
     ldpc.dec.close()
+
+
+def test_bbheader_crc_flag(dec):
+    """flag bit 4 mirrors BBFrameTSParser's CRC-8 gate: clear for a well-formed BBHEADER, set otherwise"""
+    o = orclib.oracle()
+    dec.setDemodParams(4, True, False)
+    rng = np.random.default_rng(77)
+    n = 12
+    payload = rng.integers(0, 256, (n, dec.kbch // 8), dtype=np.uint8)
+    for i in range(0, n, 2):   # make every other header valid: choose the CRC byte that zeroes the check
+        for b in range(256):
+            payload[i, 9] = b
+            if o.orc_bbheader_crc8(np.ascontiguousarray(payload[i])) == 0:
+                break
+        else:
+            raise AssertionError("no CRC byte found")
+    llr = np.stack([np.where(pkg.encode_fecframe(4, True, payload[i]) > 0, -10, 10).astype(np.int8) for i in range(n)])
+    bb, res = dec.decode_batch(llr)
+    assert np.array_equal(bb, payload)
+    want = np.array([o.orc_bbheader_crc8(np.ascontiguousarray(payload[i])) != 0 for i in range(n)])
+    assert (~want[0::2]).all()
+    assert np.array_equal((res["flags"] & pkg.FLAG_BBHEADER_CRC_FAIL) != 0, want)

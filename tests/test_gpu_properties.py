@@ -75,7 +75,7 @@ def test_worst_case_all_frames_fail():
     dec.setDemodParams(4, False, False, 10)
     llr, _ = make_batch(4, False, 40, -1.0, 3)
     bb, res = dec.decode_batch(llr)
-    assert (res["ldpc_iters"] == -1).all() and (res["bch_corr"] == -1).all() and (res["flags"] == 3).all()
+    assert (res["ldpc_iters"] == -1).all() and (res["bch_corr"] == -1).all() and ((res["flags"] & 3) == 3).all()
     o = orclib.oracle()
     want = np.zeros(dec.kbch // 8, np.uint8)
     it, co = C.c_int(), C.c_int()

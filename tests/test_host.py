@@ -111,3 +111,21 @@ def test_bb_scrambler_sequence_start():
         bits.append(b)
         sr = [b] + sr[:-1]
     assert np.array_equal(np.unpackbits(z[:8]), np.array(bits, np.uint8))
+
+
+def test_bbheader_crc8_restatement_agrees_with_standard_encoder():
+    """EN 302 307 5.1.6: CRC-8 with g(x) = x^8+x^7+x^6+x^4+x^2+1 over the first 72 BBHEADER bits, appended MSB
+    first; the reference parser's check (bbframe_ts_parser.cpp:66-80), as restated in the oracle, must then be 0."""
+    o = orclib.oracle()
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        hdr = rng.integers(0, 256, 10, dtype=np.uint8)
+        reg = 0
+        for n in range(72):
+            bit = (int(hdr[n >> 3]) >> (7 - (n & 7))) & 1
+            fb = ((reg >> 7) & 1) ^ bit
+            reg = ((reg << 1) & 0xFF) ^ (0xD5 if fb else 0)
+        hdr[9] = reg
+        assert o.orc_bbheader_crc8(hdr) == 0
+        hdr[3] ^= 0x10
+        assert o.orc_bbheader_crc8(hdr) != 0
