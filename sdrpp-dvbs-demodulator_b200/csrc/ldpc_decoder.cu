@@ -2,7 +2,9 @@
 // (layered_decoder.hh:23-74,121-133; algorithms.hh:235-256,261-276; bbframe_ldpc.cpp:123-139).
 #include "ldpc_decoder.cuh"
 
+#include <algorithm>
 #include <cstdio>
+#include <vector>
 
 namespace s2 {
 namespace {
@@ -23,6 +25,7 @@ struct LdpcParams {
     const uint8_t* row_level;
     uint16_t layer_off[kMaxLayers + 1];
     uint8_t layer_nlev[kMaxLayers];
+    uint8_t layer_sync[kMaxLayers];   // 1: a CTA barrier must follow this layer (see ldpc_launch)
     uint32_t links[kMaxLinks];
 };
 static_assert(sizeof(LdpcParams) <= 4096, "kernel parameter block must stay within the 4 KB constant window");
@@ -365,7 +368,9 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
                         else
                             row_update<CNT, UNIFORM, false>(vbytes, voff, cnt, msg, pown, psec, has2, lf);
                     }
-                    __syncthreads();
+                    // barriers separate dependency levels, and layers only where a later layer touches a bit group
+                    // that a layer since the last barrier also touches (rows on disjoint bits commute)
+                    if (lvl + 1 < nlev || p.layer_sync[i]) __syncthreads();
                 }
                 // write the row's messages back; retire the parity LLR that just got its last update
                 if (active) {
@@ -488,6 +493,33 @@ int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
     if (nlinks > kMaxLinks) return (int)cudaErrorInvalidValue;
     for (int i = 0; i <= c.q; ++i) p.layer_off[i] = (uint16_t)c.layer_off[i];
     for (int i = 0; i < c.q; ++i) p.layer_nlev[i] = c.layer_nlev[i];
+    {   // Barrier elision.  The reference visits rows strictly in order, but two rows commute unless they touch a
+        // common bit.  Parity bits chain rows of the same thread only (kept in registers), except pty[q-1][j-1]
+        // (layer 0 of thread j, layer q-1 of thread j-1).  Data bits are shared between threads, group by group:
+        // a barrier is needed before a layer exactly when it touches a 360-bit group that some layer since the
+        // last barrier touched; level-scheduled layers are always fenced on both sides.
+        std::vector<char> seen(c.ngroups, 0);
+        bool any = false;
+        for (int i = 0; i < c.q; ++i) {
+            const bool multi = c.layer_nlev[i] > 1;
+            bool conflict = multi;
+            for (int k = c.layer_off[i]; k < c.layer_off[i + 1] && !conflict; ++k) conflict = seen[c.links[k] >> 16] != 0;
+            if (i > 0 && conflict) {
+                p.layer_sync[i - 1] = 1;
+                any = any || (i - 1 <= c.q - 3);
+                std::fill(seen.begin(), seen.end(), 0);
+            }
+            p.layer_sync[i] = 0;
+            for (int k = c.layer_off[i]; k < c.layer_off[i + 1]; ++k) seen[c.links[k] >> 16] = 1;
+            if (multi) {
+                p.layer_sync[i] = 1;
+                any = any || (i <= c.q - 3);
+                std::fill(seen.begin(), seen.end(), 0);
+            }
+        }
+        p.layer_sync[c.q - 1] = 1;            // end of the pass
+        if (!any) p.layer_sync[0] = 1;        // pty[q-1][j-1]: stored in layer 0, prefetched (by thread j-1) in layer q-2
+    }
     for (int i = 0; i < nlinks; ++i) p.links[i] = c.links[i];
     size_t smem = ldpc_smem_bytes(c);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
