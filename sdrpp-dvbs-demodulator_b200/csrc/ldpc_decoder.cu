@@ -459,6 +459,21 @@ KernelFn pick_fn(const LdpcDev& c) {
 
 }  // namespace
 
+// Opt every launch of `fn` in to the device's full dynamic shared memory.  The value is the same for every
+// code that shares a kernel instantiation, so handles configured for different MODCODs can launch concurrently
+// from different host threads without racing on the function attribute.
+static cudaError_t allow_max_smem(KernelFn fn) {
+    int dev = 0, optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, fn);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
 int ldpc_slot_groups(int max_cnt) {
     const Variant* v = pick(max_cnt);
     return v ? (v->cnt + 2 + 7) / 8 : 0;
@@ -468,7 +483,7 @@ int ldpc_max_ctas_per_sm(const LdpcDev& code) {
     KernelFn fn = pick_fn(code);
     if (!fn) return 0;
     size_t smem = ldpc_smem_bytes(code);
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (allow_max_smem(fn) != cudaSuccess) return 0;
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kLdpcThreads, smem);
     return n;
@@ -522,7 +537,7 @@ int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
     }
     for (int i = 0; i < nlinks; ++i) p.links[i] = c.links[i];
     size_t smem = ldpc_smem_bytes(c);
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_max_smem(fn);
     if (e != cudaSuccess) return (int)e;
     fn<<<grid, kLdpcThreads, smem, stream>>>(p);
     return (int)cudaGetLastError();

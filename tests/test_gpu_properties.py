@@ -220,3 +220,32 @@ def test_config5_mixed_modcod_transponders_in_submission_order():
         assert np.array_equal(res["tag"], 10 * t + np.arange(5))
         assert np.array_equal(bb, want[t])
         d.close()
+
+
+def test_concurrent_handles_on_host_threads():
+    """two transponders = two handles driven from two host threads at the same time, different codes that share a
+    kernel instantiation (n1/2 and s1/2 both use the 5-link kernel with different shared-memory sizes)"""
+    import threading
+    specs = [(4, False, 2.4, 48), (4, True, 2.8, 200), (6, False, 4.4, 32)]
+    out = {}
+
+    def work(k, modcod, short, esn0, n):
+        d = pkg.DVBS2Decoder(max_batch=64)
+        d.setDemodParams(modcod, short, False)
+        llr, payload = make_batch(modcod, short, n, esn0, 900 + k)
+        for _ in range(3):
+            bb, res = d.decode_batch(llr)
+        out[k] = (bb, res, payload)
+        d.close()
+
+    th = [threading.Thread(target=work, args=(k,) + s) for k, s in enumerate(specs)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert len(out) == len(specs)
+    for k in out:
+        bb, res, payload = out[k]
+        ok = res["bch_corr"] >= 0
+        assert ok.mean() > 0.9
+        assert np.array_equal(bb[ok], payload[ok])
