@@ -243,10 +243,41 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
             o.w = prmt(a.y, b.y, 0x7362) ^ 0x80808080u;
             reinterpret_cast<uint4*>(vdata)[x] = o;
         }
-        for (int x = tid; x < R; x += kLdpcThreads) {
-            uint32_t a = (uint8_t)__ldg(inA + K + x), b = (uint8_t)__ldg(inB + K + x);
-            int jj = x / q, ii = x - jj * q;
-            __stcg(&wpty[360 * ii + jj], (uint16_t)((a | (b << 8)) ^ 0x8080u));
+        // The parity part is a q x 360 transpose.  It goes through shared memory in tiles of 32 columns (the
+        // bit-plane area is free at this point): 64-bit coalesced reads of v[K + q j + i], byte scatter into the
+        // tile, then rows of 32 pairs (64 B) out to the workspace -- instead of 2R single-byte loads and R
+        // isolated 2-byte stores.
+        {
+            uint8_t* tile = reinterpret_cast<uint8_t*>(HD);           // [q][32] pairs of bytes
+            const uint2* srcA = reinterpret_cast<const uint2*>(inA + K);
+            const uint2* srcB = reinterpret_cast<const uint2*>(inB + K);
+            for (int jj0 = 0; jj0 < 360; jj0 += 32) {
+                const int ncol = min(32, 360 - jj0);
+                const int nvec = ncol * q / 8;                        // q * 32 and q * 8 are multiples of 8
+                for (int x = tid; x < nvec; x += kLdpcThreads) {
+                    const int base = (q * jj0) / 8 + x;
+                    uint2 a = __ldg(srcA + base), b = __ldg(srcB + base);
+                    int jr = (8 * x) / q, ii = 8 * x - jr * q;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        uint32_t va = ((k < 4 ? a.x : a.y) >> (8 * (k & 3))) & 0xFFu;
+                        uint32_t vb = ((k < 4 ? b.x : b.y) >> (8 * (k & 3))) & 0xFFu;
+                        *reinterpret_cast<uint16_t*>(tile + 2 * (ii * 32 + jr)) = (uint16_t)((va | (vb << 8)) ^ 0x8080u);
+                        if (++ii == q) {
+                            ii = 0;
+                            ++jr;
+                        }
+                    }
+                }
+                __syncthreads();
+                for (int x = tid; x < q * 32; x += kLdpcThreads) {
+                    const int ii = x >> 5, jr = x & 31;
+                    if (jr < ncol) __stcg(&wpty[360 * ii + jj0 + jr], *reinterpret_cast<const uint16_t*>(tile + 2 * x));
+                }
+                __syncthreads();
+            }
+            // the tile lived in the bit-plane area: restore the all-zero state the planes rely on
+            for (int x = tid; x < 2 * (p.ngroups + q) * kBitWords; x += kLdpcThreads) HD[x] = 0;
         }
         __syncthreads();
 
