@@ -5,6 +5,7 @@
 #include "../../include/dvbs2fec.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdarg>
@@ -45,6 +46,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(DVBS2FEC_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+constexpr int kStages = 4; // page-locked staging batches per handle (frame queue)
 constexpr int kSlots = 2;  // double buffering per device: copy of batch k+1 overlaps kernels of batch k
 
 template <typename T>
@@ -119,7 +121,7 @@ struct BchTabDev {
 struct DevCtx {
     int device = 0;
     int sms = 0;
-    Slot slot[kSlots];
+    Slot slot[2 * kSlots];  // [0,kSlots): synchronous entry points; [kSlots,2 kSlots): the frame queue's worker
     std::map<int, CodeDev> codes;
     std::map<int, BchTabDev> bch;           // key m*100+t
     DevBuf<uint16_t> gf_log[2], gf_exp[2];  // [0]: m=14, [1]: m=16
@@ -151,19 +153,31 @@ struct dvbs2fec_handle {
     std::vector<uint32_t> h_links;
     // ---- queue
     std::mutex mu;
+    std::mutex submit_mu;               // serialises producers (the reference has one per instance)
     std::condition_variable cv_work, cv_done;
     std::thread worker;
     bool stop = false, flush_req = false, busy = false;
-    std::vector<int8_t> q_llr;          // pending LLR frames
-    std::vector<float> q_sym;           // pending PLFRAMEs
-    std::vector<uint64_t> q_tags;
-    bool q_is_sym = false;
-    std::chrono::steady_clock::time_point q_first;
-    struct Done {
-        std::vector<uint8_t> bb;
-        dvbs2fec_result r;
+    // Frames wait in page-locked staging batches ("stages"): submit copies a frame straight into the stage being
+    // filled, the worker hands a full (or timed-out) stage to the GPUs with asynchronous copies in both
+    // directions, collect copies BBFRAMEs out of finished stages.  Stages cycle free -> fill -> ready -> inflight
+    // -> done -> free; at most kSlots are in flight, so the copy-in of one overlaps the kernels of the other.
+    struct Stage {
+        PinBuf<uint8_t> in, bb;
+        PinBuf<dvbs2fec_result> res;
+        std::vector<uint64_t> tags;
+        int n = 0, taken = 0, cap = 0;
+        bool is_sym = false;
+        int rc = 0;
+        size_t kb = 0, in_bytes = 0;
+        std::atomic<int> outstanding{0};   // device shares still running
+        std::chrono::steady_clock::time_point first;
     };
-    std::deque<Done> done;
+    struct ShareDone { dvbs2fec_handle* h; int stage; };
+    Stage stages[kStages];
+    ShareDone share_done[kStages];
+    std::deque<int> st_free, st_ready, st_inflight, st_done;
+    int st_fill = -1;
+    uint64_t launch_seq = 0;
 };
 
 namespace {
@@ -435,53 +449,93 @@ int decode_host(dvbs2fec_handle* h, const int8_t* llr, const float* sym, int n, 
     return 0;
 }
 
+// stream callback at the end of one device's share of a stage (no CUDA calls allowed in here)
+void CUDART_CB stage_share_done(void* arg) {
+    auto* a = static_cast<dvbs2fec_handle::ShareDone*>(arg);
+    if (a->h->stages[a->stage].outstanding.fetch_sub(1) == 1) {
+        std::lock_guard<std::mutex> lk(a->h->mu);
+        a->h->cv_work.notify_all();
+    }
+}
+
+// hand stage `st` to the GPUs: contiguous shares by frame, everything asynchronous on slot kSlots + which
+void launch_stage(dvbs2fec_handle* h, int st, int which) {
+    dvbs2fec_handle::Stage& S = h->stages[st];
+    const int nd = (int)h->devs.size();
+    const int per = (S.n + nd - 1) / nd;
+    int shares = 0;
+    for (int k = 0; k < nd; ++k) shares += std::min(S.n, k * per) < S.n;
+    S.outstanding.store(shares);
+    S.rc = 0;
+    h->last_launches = 0;
+    for (int k = 0; k < nd; ++k) {
+        const int f0 = std::min(S.n, k * per), f1 = std::min(S.n, f0 + per), m = f1 - f0;
+        if (m <= 0) continue;
+        DevCtx& d = *h->devs[k];
+        Slot& s = d.slot[kSlots + which];
+        auto body = [&]() -> int {
+            int rc = reserve_slot(h, d, s, std::max(m, h->cfg.max_batch), S.is_sym, false);
+            if (rc) return rc;
+            void* dst = S.is_sym ? (void*)s.sym.p : (void*)s.llr.p;
+            CU(cudaMemcpyAsync(dst, S.in.p + (size_t)f0 * S.in_bytes, (size_t)m * S.in_bytes, cudaMemcpyHostToDevice, s.stream));
+            rc = enqueue_chain(h, d, s, S.is_sym ? s.sym.p : nullptr, S.is_sym ? nullptr : s.llr.p, m, s.bb.p, s.res.p, s.stream,
+                               &h->last_launches, (uint64_t)f0);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(S.bb.p + (size_t)f0 * S.kb, s.bb.p, (size_t)m * S.kb, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(S.res.p + f0, s.res.p, (size_t)m * sizeof(dvbs2fec_result), cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaLaunchHostFunc(s.stream, stage_share_done, &h->share_done[st]));
+            return 0;
+        };
+        int rc = body();
+        if (rc) {   // this share never got its completion callback
+            S.rc = rc;
+            S.outstanding.fetch_sub(1);
+        }
+    }
+}
+
 void worker_main(dvbs2fec_handle* h) {
     std::unique_lock<std::mutex> lk(h->mu);
+    const auto latency = std::chrono::microseconds(h->cfg.max_latency_us);
     for (;;) {
-        const size_t batch = (size_t)h->cfg.max_batch * h->devs.size();
-        while (!h->stop) {
-            size_t pending = h->q_tags.size();
-            if (pending >= batch || (pending && h->flush_req)) break;
-            if (pending) {
-                auto deadline = h->q_first + std::chrono::microseconds(h->cfg.max_latency_us);
-                if (std::chrono::steady_clock::now() >= deadline) break;
-                h->cv_work.wait_until(lk, deadline);
-            } else {
-                h->flush_req = false;
-                h->cv_done.notify_all();
-                h->cv_work.wait(lk);
+        // publish finished stages in launch order
+        bool published = false;
+        while (!h->st_inflight.empty() && h->stages[h->st_inflight.front()].outstanding.load() == 0) {
+            h->st_done.push_back(h->st_inflight.front());
+            h->st_inflight.pop_front();
+            published = true;
+        }
+        if (published) h->cv_done.notify_all();
+        // next stage to launch: a full one, else the one being filled once it is old enough (or on flush)
+        int st = -1;
+        if ((int)h->st_inflight.size() < kSlots) {
+            if (!h->st_ready.empty()) {
+                st = h->st_ready.front();
+                h->st_ready.pop_front();
+            } else if (h->st_fill >= 0 && h->stages[h->st_fill].n > 0 &&
+                       (h->flush_req || std::chrono::steady_clock::now() >= h->stages[h->st_fill].first + latency)) {
+                st = h->st_fill;
+                h->st_fill = -1;
             }
+        }
+        if (st >= 0) {
+            h->st_inflight.push_back(st);
+            const int which = (int)(h->launch_seq++ % kSlots);
+            lk.unlock();
+            launch_stage(h, st, which);
+            lk.lock();
+            continue;
         }
         if (h->stop) return;
-        std::vector<int8_t> llr;
-        std::vector<float> sym;
-        std::vector<uint64_t> tags;
-        llr.swap(h->q_llr);
-        sym.swap(h->q_sym);
-        tags.swap(h->q_tags);
-        const bool is_sym = h->q_is_sym;
-        h->busy = true;
-        lk.unlock();
-        const int n = (int)tags.size();
-        const size_t kb = h->code->kbch / 8;
-        std::vector<uint8_t> bb((size_t)n * kb);
-        std::vector<dvbs2fec_result> res(n);
-        int rc = decode_host(h, is_sym ? nullptr : llr.data(), is_sym ? sym.data() : nullptr, n, bb.data(), res.data());
-        lk.lock();
-        for (int i = 0; i < n; ++i) {
-            dvbs2fec_handle::Done d;
-            d.bb.assign(bb.begin() + (size_t)i * kb, bb.begin() + (size_t)(i + 1) * kb);
-            d.r = res[i];
-            d.r.tag = tags[i];
-            if (rc) {
-                d.r.ldpc_iters = -1;
-                d.r.bch_corr = -1;
-                d.r.flags = DVBS2FEC_FLAG_LDPC_FAIL | DVBS2FEC_FLAG_BCH_FAIL;
-            }
-            h->done.push_back(std::move(d));
+        const bool filling = h->st_fill >= 0 && h->stages[h->st_fill].n > 0;
+        if (!filling && h->st_ready.empty() && h->st_inflight.empty()) {
+            h->flush_req = false;
+            h->cv_done.notify_all();
         }
-        h->busy = false;
-        h->cv_done.notify_all();
+        if (filling && (int)h->st_inflight.size() < kSlots)
+            h->cv_work.wait_until(lk, h->stages[h->st_fill].first + latency);
+        else
+            h->cv_work.wait(lk);
     }
 }
 
@@ -490,7 +544,9 @@ void drain_queue(dvbs2fec_handle* h) {
     if (!h->worker.joinable()) return;
     h->flush_req = true;
     h->cv_work.notify_all();
-    h->cv_done.wait(lk, [h] { return h->q_tags.empty() && !h->busy; });
+    h->cv_done.wait(lk, [h] {
+        return h->st_ready.empty() && h->st_inflight.empty() && (h->st_fill < 0 || h->stages[h->st_fill].n == 0);
+    });
     h->flush_req = false;
 }
 
@@ -531,11 +587,15 @@ int dvbs2fec_create(const dvbs2fec_config* cfg, dvbs2fec_handle** out) {
             return fail(DVBS2FEC_ENODEV, "device %d is sm_%d%d; this library carries sm_100a code only", id, prop.major,
                         prop.minor);
         d->sms = prop.multiProcessorCount;
-        for (int k = 0; k < kSlots; ++k) {
+        for (int k = 0; k < 2 * kSlots; ++k) {
             CU(cudaStreamCreateWithFlags(&d->slot[k].stream, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&d->slot[k].done, cudaEventDisableTiming));
         }
         h->devs.push_back(std::move(d));
+    }
+    for (int k = 0; k < kStages; ++k) {
+        h->share_done[k] = {h.get(), k};
+        h->st_free.push_back(k);
     }
     *out = h.release();
     return 0;
@@ -552,7 +612,7 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
     for (auto& dp : h->devs) {
         DevCtx& d = *dp;
         cudaSetDevice(d.device);
-        for (int k = 0; k < kSlots; ++k) {
+        for (int k = 0; k < 2 * kSlots; ++k) {
             Slot& s = d.slot[k];
             if (s.stream) cudaStreamSynchronize(s.stream);
             s.llr.release(); s.sym.release(); s.hard.release(); s.iters.release(); s.corr.release();
@@ -566,6 +626,11 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
         for (auto& kv : d.luts) kv.second.release();
         for (int i = 0; i < 2; ++i) { d.gf_log[i].release(); d.gf_exp[i].release(); }
         d.prbs.release();
+    }
+    for (auto& S : h->stages) {
+        S.in.release();
+        S.bb.release();
+        S.res.release();
     }
     delete h;
 }
@@ -740,23 +805,52 @@ int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n,
 
 static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym, uint64_t tag) {
     if (!h || !h->configured) return fail(DVBS2FEC_EINVAL, "set_modcod has not been called");
+    std::lock_guard<std::mutex> producer(h->submit_mu);
     std::unique_lock<std::mutex> lk(h->mu);
     if (!h->worker.joinable()) h->worker = std::thread(worker_main, h);
     const bool is_sym = sym != nullptr;
-    if (!h->q_tags.empty() && h->q_is_sym != is_sym) {  // mixed kinds: push the pending ones through first
-        lk.unlock();
-        drain_queue(h);
-        lk.lock();
+    if (h->st_fill >= 0 && h->stages[h->st_fill].n > 0 && h->stages[h->st_fill].is_sym != is_sym) {
+        h->st_ready.push_back(h->st_fill);   // a batch holds one kind of input: close the pending one
+        h->st_fill = -1;
+        h->cv_work.notify_all();
     }
-    if (h->q_tags.size() >= (size_t)h->cfg.max_batch * h->devs.size() * 4) return fail(DVBS2FEC_EAGAIN, "queue full");
-    if (h->q_tags.empty()) h->q_first = std::chrono::steady_clock::now();
-    h->q_is_sym = is_sym;
-    if (is_sym)
-        h->q_sym.insert(h->q_sym.end(), sym, sym + (size_t)h->plsyms * 2);
-    else
-        h->q_llr.insert(h->q_llr.end(), llr, llr + h->code->N);
-    h->q_tags.push_back(tag);
-    h->cv_work.notify_all();
+    if (h->st_fill < 0) {
+        if (h->st_free.empty()) return fail(DVBS2FEC_EAGAIN, "queue full");
+        const int idx = h->st_free.front();
+        h->st_free.pop_front();
+        dvbs2fec_handle::Stage& S = h->stages[idx];
+        S.cap = h->cfg.max_batch * (int)h->devs.size();
+        S.kb = h->code->kbch / 8;
+        S.in_bytes = is_sym ? (size_t)h->plsyms * 8 : (size_t)h->code->N;
+        S.is_sym = is_sym;
+        S.n = S.taken = 0;
+        S.tags.clear();
+        // page-locked allocation may synchronise with the device, and stream callbacks take h->mu: allocate unlocked
+        // (submit_mu keeps other producers out, and a stage that is on no list is invisible to worker and collect)
+        lk.unlock();
+        cudaError_t e = cudaSetDevice(h->devs[0]->device);
+        if (e == cudaSuccess) e = S.in.reserve((size_t)S.cap * S.in_bytes);
+        if (e == cudaSuccess) e = S.bb.reserve((size_t)S.cap * S.kb);
+        if (e == cudaSuccess) e = S.res.reserve(S.cap);
+        lk.lock();
+        if (e != cudaSuccess) {
+            h->st_free.push_back(idx);
+            return fail(DVBS2FEC_ECUDA, "page-locked staging: %s", cudaGetErrorString(e));
+        }
+        h->st_fill = idx;
+    }
+    dvbs2fec_handle::Stage& S = h->stages[h->st_fill];
+    memcpy(S.in.p + (size_t)S.n * S.in_bytes, is_sym ? (const void*)sym : (const void*)llr, S.in_bytes);
+    S.tags.push_back(tag);
+    if (++S.n == 1) {
+        S.first = std::chrono::steady_clock::now();
+        h->cv_work.notify_all();   // arms the latency deadline
+    }
+    if (S.n == S.cap) {
+        h->st_ready.push_back(h->st_fill);
+        h->st_fill = -1;
+        h->cv_work.notify_all();
+    }
     return 0;
 }
 
@@ -773,8 +867,8 @@ int dvbs2fec_submit_plframe(dvbs2fec_handle* h, const float* plframe, int nsym, 
 int dvbs2fec_collect(dvbs2fec_handle* h, uint8_t* bb_out, dvbs2fec_result* results, int max, int timeout_us) {
     if (!h || !h->configured || max < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
     std::unique_lock<std::mutex> lk(h->mu);
-    if (h->done.empty() && timeout_us != 0) {
-        auto ready = [h] { return !h->done.empty(); };
+    if (h->st_done.empty() && timeout_us != 0) {
+        auto ready = [h] { return !h->st_done.empty(); };
         if (timeout_us < 0)
             h->cv_done.wait(lk, ready);
         else
@@ -782,12 +876,32 @@ int dvbs2fec_collect(dvbs2fec_handle* h, uint8_t* bb_out, dvbs2fec_result* resul
     }
     int n = 0;
     const size_t kb = h->code->kbch / 8;
-    while (n < max && !h->done.empty()) {
-        auto& d = h->done.front();
-        if (bb_out) memcpy(bb_out + (size_t)n * kb, d.bb.data(), std::min(kb, d.bb.size()));
-        if (results) results[n] = d.r;
-        h->done.pop_front();
-        ++n;
+    while (n < max && !h->st_done.empty()) {
+        dvbs2fec_handle::Stage& S = h->stages[h->st_done.front()];
+        const int k = std::min(max - n, S.n - S.taken);
+        if (bb_out) {
+            if (S.kb == kb)
+                memcpy(bb_out + (size_t)n * kb, S.bb.p + (size_t)S.taken * kb, (size_t)k * kb);
+            else   // frames of the MODCOD before a set_modcod call: as many bytes as fit the current frame size
+                for (int i = 0; i < k; ++i) memcpy(bb_out + (size_t)(n + i) * kb, S.bb.p + (size_t)(S.taken + i) * S.kb, std::min(kb, S.kb));
+        }
+        if (results)
+            for (int i = 0; i < k; ++i) {
+                dvbs2fec_result r = S.res.p[S.taken + i];
+                r.tag = S.tags[S.taken + i];
+                if (S.rc) {
+                    r.ldpc_iters = -1;
+                    r.bch_corr = -1;
+                    r.flags = DVBS2FEC_FLAG_LDPC_FAIL | DVBS2FEC_FLAG_BCH_FAIL;
+                }
+                results[n + i] = r;
+            }
+        S.taken += k;
+        n += k;
+        if (S.taken == S.n) {
+            h->st_free.push_back(h->st_done.front());
+            h->st_done.pop_front();
+        }
     }
     return n;
 }

@@ -232,6 +232,81 @@ def test_queue_returns_frames_in_submission_order(dec):
     assert np.array_equal(res["bch_corr"], want_c)
 
 
+def test_queue_many_small_batches_partial_collects_and_backpressure():
+    """max_batch 4: 37 frames pass through ten staging batches; collect takes odd-sized bites; a producer that
+    never collects eventually gets EAGAIN ("queue full") and loses nothing once it does collect"""
+    short, rate = 1, 3
+    d = pkg.DVBS2Decoder(max_batch=4, max_latency_us=500, max_trials=25)
+    try:
+        d.setDemodParams(4, True, False)
+        llr = make_llrs(short, rate, 37, 4321)
+        want_bb, want_it, want_c = oracle_chain(short, rate, llr, 25)
+        got_bb, got_res = [], []
+        refused = 0
+        for i in range(len(llr)):
+            while True:
+                rc = pkg.lib().dvbs2fec_submit_llr(d._h, llr[i].ctypes.data_as(C.c_void_p), i)
+                if rc != pkg.EAGAIN:
+                    break
+                refused += 1   # all four staging batches hold uncollected frames: take a bite and retry
+                bb, res = d.collect(3, timeout_us=100_000)
+                got_bb.append(bb.copy()); got_res.append(res.copy())
+            assert rc == 0
+            if i % 5 == 4:
+                bb, res = d.collect(3, timeout_us=0)
+                got_bb.append(bb.copy()); got_res.append(res.copy())
+        assert refused > 0
+        d.flush()
+        while sum(len(r) for r in got_res) < len(llr):
+            bb, res = d.collect(7, timeout_us=2_000_000)
+            assert len(res) > 0
+            got_bb.append(bb.copy()); got_res.append(res.copy())
+        bb, res = np.concatenate(got_bb), np.concatenate(got_res)
+        assert np.array_equal(res["tag"], np.arange(len(llr)))
+        assert np.array_equal(bb, want_bb)
+        assert np.array_equal(res["ldpc_iters"], want_it)
+        assert np.array_equal(res["bch_corr"], want_c)
+        # back-pressure: 4 staging batches of up to 4 frames (a batch may close early on its latency deadline)
+        accepted = 0
+        for i in range(40):
+            rc = pkg.lib().dvbs2fec_submit_llr(d._h, llr[i % len(llr)].ctypes.data_as(C.c_void_p), 100 + i)
+            if rc == pkg.EAGAIN:
+                break
+            assert rc == 0
+            accepted += 1
+        assert 4 <= accepted <= 16
+        d.flush()
+        tags = []
+        while len(tags) < accepted:
+            _, res = d.collect(64, timeout_us=2_000_000)
+            assert len(res) > 0
+            tags += list(res["tag"])
+        assert tags == list(range(100, 100 + accepted))
+    finally:
+        d.close()
+
+
+def test_queue_mixed_llr_and_plframe_inputs_keep_order(dec):
+    """LLR frames and PLFRAMEs submitted alternately in runs: each run becomes its own batch, order is kept"""
+    modcod, short = 4, True
+    dec.setDemodParams(modcod, short, False)
+    rng = np.random.default_rng(77)
+    n = 9
+    payload = rng.integers(0, 256, (n, dec.kbch // 8), dtype=np.uint8)
+    codes = [pkg.encode_fecframe(modcod, short, payload[i]) for i in range(n)]
+    for i in range(n):
+        if (i // 3) % 2 == 0:
+            dec.submit_llr(np.where(codes[i] > 0, -40, 40).astype(np.int8), i)
+        else:
+            pl = pkg.modulate(modcod, short, False, codes[i]).view(np.float32)
+            dec.submit_plframe(pl + rng.normal(0, 0.05, pl.shape).astype(np.float32), i)
+    dec.flush()
+    bb, res = dec.collect(64, timeout_us=2_000_000)
+    assert list(res["tag"]) == list(range(n))
+    assert (res["bch_corr"] >= 0).all()
+    assert np.array_equal(bb, payload)
+
+
 def test_modcod_switch_and_errors(dec):
     with pytest.raises(pkg.DVBS2FecError):
         dec.setDemodParams(0)
