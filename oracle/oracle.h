@@ -40,9 +40,21 @@ int orc_bch_decode(int shortframe, int rate, uint8_t* frame);
 int orc_bch_encode(int shortframe, int rate, uint8_t* frame);
 /* BBFrameDescrambler::work (bbframe_descramble.cpp:122-143) */
 int orc_descramble(int shortframe, int rate, uint8_t* frame);
-/* BBFrameTSParser::check_crc8(bbf, 80) (dvbs2/bbframe_ts_parser.cpp:66-80): 0 = BBHEADER valid.  Restated only:
- * the parser needs SDR++ core headers and is not part of the oracle/_ref build (parity unpinned by execution). */
+/* BBFrameTSParser::check_crc8(bbf, 80) (dvbs2/bbframe_ts_parser.cpp:66-80): 0 = BBHEADER valid */
 unsigned orc_bbheader_crc8(const uint8_t* bbframe);
+/* ---- downstream row 8(f)-1: BBFrameTSParser (dvbs2/bbframe_ts_parser.cpp:31-43,100-392), see oracle_ts.c ---- */
+typedef struct orc_ts_parser orc_ts_parser;
+orc_ts_parser* orc_ts_create(int kbch_bits);                     /* setFrameSize */
+void orc_ts_destroy(orc_ts_parser* p);
+/* work(): cnt BBFRAMEs of kbch/8 bytes -> TS packets (or GRE-wrapped GSE PDUs); returns bytes written */
+int orc_ts_work(orc_ts_parser* p, const uint8_t* bbframes, int cnt, uint8_t* out, int out_cap);
+/* last_header as the 10 raw BBHEADER bytes (have_header = 0 until one frame was accepted), last_bb_cnt,
+ * last_bb_proc, last_gse_crc_err, plus the private sync flag and the size of the pending partial unit */
+void orc_ts_stats(const orc_ts_parser* p, uint8_t last_header[10], int* have_header, int* last_bb_cnt, int* last_bb_proc,
+                  int* last_gse_crc_err, int* synched, int* pending);
+/* transmit-side helpers for tests (EN 302 307 5.1.4, 5.1.6) */
+void orc_bbheader_seal(uint8_t* hdr10);
+uint8_t orc_up_crc8(const uint8_t* payload187);
 /* whole A3..A10 chain for one frame: llr[N] in (modified), bb[kbch/8] out */
 int orc_decode_frame(int shortframe, int rate, int8_t* llr, int max_trials, uint8_t* bb, int* ldpc_iters, int* bch_corr);
 

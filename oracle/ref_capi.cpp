@@ -20,6 +20,7 @@
 #include "dvbs2/codings/s2_deinterleaver.h"
 #include "dvbs2/codings/xdsopl-ldpc-pabr/dvb_s2_tables.hh"
 #include "common/dsp/demod/constellation.h"
+#include "dvbs2/bbframe_ts_parser.h"
 
 using namespace dsp::dvbs2;
 
@@ -229,6 +230,27 @@ void ref_mod(int type, float g1, float g2, const uint8_t* symbols, int nsym, flo
         out[2 * i] = v.re;
         out[2 * i + 1] = v.im;
     }
+}
+
+// ---- BBFrameTSParser (dvbs2/bbframe_ts_parser.h:67-108), one long-lived object per handle ----
+void* ref_ts_create(int kbch_bits) {
+    auto* p = new dsp::dvbs2::BBFrameTSParser();
+    p->setFrameSize(kbch_bits);
+    return p;
+}
+void ref_ts_destroy(void* h) { delete static_cast<dsp::dvbs2::BBFrameTSParser*>(h); }
+int ref_ts_work(void* h, uint8_t* bbframes, int cnt, uint8_t* out, int out_cap) {
+    return static_cast<dsp::dvbs2::BBFrameTSParser*>(h)->work(bbframes, cnt, out, out_cap);
+}
+// public members after work(): fields[0..10] = ts_gs, sis_mis, ccm_acm, issyi, npd, ro, isi, upl, dfl, sync, syncd
+void ref_ts_stats(void* h, int* fields, int* last_bb_cnt, int* last_bb_proc, int* last_gse_crc_err) {
+    auto* p = static_cast<dsp::dvbs2::BBFrameTSParser*>(h);
+    const dsp::dvbs2::BBHeader& b = p->last_header;
+    int v[11] = {b.ts_gs, b.sis_mis, b.ccm_acm, b.issyi, b.npd, b.ro, b.isi, b.upl, b.dfl, b.sync, b.syncd};
+    for (int i = 0; i < 11; ++i) fields[i] = v[i];
+    *last_bb_cnt = p->last_bb_cnt;
+    *last_bb_proc = p->last_bb_proc;
+    *last_gse_crc_err = p->last_gse_crc_err;
 }
 
 } // extern "C"

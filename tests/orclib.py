@@ -25,7 +25,7 @@ _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 
 def _build_oracle():
     so = os.path.join(ORACLE_DIR, "libdvbs2_oracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_ldpc.c", "oracle_bch.c", "oracle_demap.c", "oracle.h")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_ldpc.c", "oracle_bch.c", "oracle_demap.c", "oracle_ts.c", "oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
     return so
@@ -63,6 +63,14 @@ def oracle():
         lib.orc_mod.argtypes = [C.c_void_p, C.c_int, _f32p]
         lib.orc_deinterleave.argtypes = [C.c_int, C.c_int, C.c_int, _i8p, _i8p]
         lib.orc_bb_to_soft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p, _i8p]
+        lib.orc_ts_create.argtypes = [C.c_int]
+        lib.orc_ts_create.restype = C.c_void_p
+        lib.orc_ts_destroy.argtypes = [C.c_void_p]
+        lib.orc_ts_work.argtypes = [C.c_void_p, _u8p, C.c_int, _u8p, C.c_int]
+        lib.orc_ts_stats.argtypes = [C.c_void_p, _u8p, ip, ip, ip, ip, ip, ip]
+        lib.orc_bbheader_seal.argtypes = [_u8p]
+        lib.orc_up_crc8.argtypes = [_u8p]
+        lib.orc_up_crc8.restype = C.c_uint8
         _oracle = lib
     return _oracle
 
@@ -91,6 +99,12 @@ def ref():
         lib.ref_demap.argtypes = [C.c_int, C.c_float, C.c_float, _f32p, C.c_int, _i8p]
         lib.ref_demap_calc.argtypes = [C.c_int, C.c_float, C.c_float, _f32p, C.c_int, _i8p]
         lib.ref_mod.argtypes = [C.c_int, C.c_float, C.c_float, _u8p, C.c_int, _f32p]
+        if hasattr(lib, "ref_ts_create"):
+            lib.ref_ts_create.argtypes = [C.c_int]
+            lib.ref_ts_create.restype = C.c_void_p
+            lib.ref_ts_destroy.argtypes = [C.c_void_p]
+            lib.ref_ts_work.argtypes = [C.c_void_p, _u8p, C.c_int, _u8p, C.c_int]
+            lib.ref_ts_stats.argtypes = [C.c_void_p, _i32p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _ref = lib
     return _ref
 

@@ -24,7 +24,7 @@ def sha_rows(a):
 
 
 def test_fixtures_present():
-    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 12
+    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 15
 
 
 @pytest.mark.parametrize("name", ["chain_s1_2", "chain_s8_9", "chain_s1_4", "chain_n1_2"])
@@ -42,6 +42,37 @@ def test_oracle_reproduces_reference_chain(name):
         assert np.array_equal(bb, g["bb"][i])
     assert np.array_equal(sha_rows(post), g["post_sha"])
     assert len(set(g["iters"].tolist())) >= 2
+
+
+TS_FIXTURES = ["tsparse_ts_n12", "tsparse_odd_s14", "tsparse_gse_n12"]
+
+
+def _ts_header_fields(h):
+    h = [int(x) for x in h]
+    sis = (h[0] >> 5) & 1
+    return [h[0] >> 6, sis, (h[0] >> 4) & 1, (h[0] >> 3) & 1, (h[0] >> 2) & 1, h[0] & 3, h[1] if sis == 0 else 0,
+            (h[2] << 8) | h[3], (h[4] << 8) | h[5], h[6], (h[7] << 8) | h[8]]
+
+
+@pytest.mark.parametrize("name", TS_FIXTURES)
+def test_oracle_reproduces_reference_ts_parser(name):
+    g = load(name)
+    o = orclib.oracle()
+    h = o.orc_ts_create(int(g["kbch"]))
+    at = 0
+    for k, (a, b) in enumerate(zip(g["cuts"][:-1], g["cuts"][1:])):
+        out = np.zeros(65536 * 10 + 4096, np.uint8)
+        n = o.orc_ts_work(h, np.ascontiguousarray(g["frames"][a:b]), int(b - a), out, 65536 * 10)
+        assert n == g["out_len"][k]
+        assert np.array_equal(out[:n], g["out"][at:at + n])
+        at += n
+        hdr = np.zeros(10, np.uint8)
+        v = [C.c_int() for _ in range(6)]
+        o.orc_ts_stats(h, hdr, *[C.byref(x) for x in v])
+        assert [v[1].value, v[2].value, v[3].value] == [int(x) for x in g["stats"][k][11:14]]
+        if v[0].value:
+            assert _ts_header_fields(hdr) == [int(x) for x in g["stats"][k][:11]]
+    o.orc_ts_destroy(h)
 
 
 @pytest.mark.parametrize("name", ["bch_n12", "bch_n10", "bch_n8", "bch_s12"])

@@ -18,6 +18,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import orclib  # noqa: E402
+import bbstream  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 SNR = {0: -2.0, 1: -1.0, 2: 0.0, 3: 1.3, 4: 2.6, 5: 3.4, 6: 4.3, 7: 5.0, 8: 5.5, 10: 6.5, 11: 6.7}
@@ -86,6 +87,36 @@ def demap_fixture(ctype, const, short, rate, g1, g2, seed):
     return dict(ctype=ctype, const=const, short=short, rate=rate, g1=g1, g2=g2, plframe=pl, llr=out)
 
 
+def ts_parser_fixture(kind, kbch, seed):
+    """BBFrameTSParser::work over a stream cut into three calls; outputs concatenated, lengths + stats per call"""
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+    if kind == "ts_odd":
+        frames = bbstream.odd_ts_scenario(rng, kbch)
+        cuts = [0, 60, 61, len(frames)]
+    elif kind == "ts":
+        pk = bbstream.ts_packets(260, rng)
+        frames, _ = bbstream.ts_bbframes(kbch, pk, first_byte=101)
+        cuts = [0, 3, 4, len(frames)]
+    else:
+        frames = bbstream.gse_bbframes(kbch, bbstream.gse_scenario(rng))
+        cuts = [0, 2, 3, len(frames)]
+    r = orclib.ref()
+    h = r.ref_ts_create(kbch)
+    outs, lens, stats = [], [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        out = np.zeros(65536 * 10 + 4096, np.uint8)
+        n = r.ref_ts_work(h, np.ascontiguousarray(frames[a:b]).copy(), b - a, out, 65536 * 10)
+        f = np.zeros(11, np.int32)
+        x, y, z = C.c_int(), C.c_int(), C.c_int()
+        r.ref_ts_stats(h, f, C.byref(x), C.byref(y), C.byref(z))
+        outs.append(out[:n].copy())
+        lens.append(n)
+        stats.append(list(f) + [x.value, y.value, z.value])
+    return dict(kbch=kbch, frames=frames, cuts=np.array(cuts), out=np.concatenate(outs), out_len=np.array(lens),
+                stats=np.array(stats, np.int32))
+
+
 def main():
     if not orclib.have_ref():
         raise SystemExit("oracle/_ref/libdvbs2_ref.so is missing: run `make -C oracle ref` in the build container")
@@ -101,6 +132,9 @@ def main():
     np.savez_compressed(os.path.join(OUT, "demap_8psk35.npz"), **demap_fixture(3, 1, 1, 4, 0.0, 0.0, 6))
     np.savez_compressed(os.path.join(OUT, "demap_16apsk.npz"), **demap_fixture(4, 2, 1, 5, 3.15, 0.0, 7))
     np.savez_compressed(os.path.join(OUT, "demap_32apsk.npz"), **demap_fixture(5, 3, 1, 6, 2.84, 5.27, 8))
+    np.savez_compressed(os.path.join(OUT, "tsparse_ts_n12.npz"), **ts_parser_fixture("ts", 32208, 11))
+    np.savez_compressed(os.path.join(OUT, "tsparse_odd_s14.npz"), **ts_parser_fixture("ts_odd", 3072, 5))
+    np.savez_compressed(os.path.join(OUT, "tsparse_gse_n12.npz"), **ts_parser_fixture("gse", 32208, 8))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

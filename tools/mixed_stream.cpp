@@ -171,12 +171,12 @@ int main(int argc, char** argv) {
                 return 2;
             }
         }
-        const long total = std::max<long>({64L, 5L * batch, (long)std::min(frames_per_stream, batch * 64)});
+        const long total = std::max<long>({64L, 5L * batch * gpus, (long)std::min(frames_per_stream, batch * 64)});
         const int window = std::max(2 * batch, 8);
         for (int pass = 0; pass < 2; ++pass) {   // pass 0 warms up (lazy allocations, first launches)
             std::atomic<int> go{0};
             std::vector<std::thread> th;
-            const long n = pass == 0 ? std::max(5 * batch, 32) : total;   // warm-up touches every staging batch and both slots
+            const long n = pass == 0 ? std::max(5 * batch * gpus, 32) : total;   // warm-up touches every staging batch and both slots
             for (auto& s : streams) th.emplace_back(run_stream, std::ref(s), n, window, std::ref(go));
             auto t0 = Clock::now();
             go.store(1);
