@@ -115,6 +115,31 @@ int dvbs2fec_flush(dvbs2fec_handle* h);
 void* dvbs2fec_alloc_pinned(size_t bytes);
 void dvbs2fec_free_pinned(void* p);
 
+/* ---- downstream of the decode stage: BBFRAME -> MPEG-TS packets ----
+ * Mirrors BBFrameTSParser (dvbs2/bbframe_ts_parser.h:67-108) as main.cpp:538 uses it.  The parser is its own
+ * object, like the reference's; its state (sync, unfinished packet) lives on the device between calls. */
+typedef struct dvbs2fec_ts_parser dvbs2fec_ts_parser;
+typedef struct dvbs2fec_bbheader { /* BBHeader (bbframe_ts_parser.h:37-65) */
+    uint8_t ts_gs, sis_mis, ccm_acm, issyi, npd, ro, isi, sync;
+    uint16_t upl, dfl, syncd, reserved;
+} dvbs2fec_bbheader;
+int dvbs2fec_ts_create(int device, dvbs2fec_ts_parser** out);
+void dvbs2fec_ts_destroy(dvbs2fec_ts_parser* p);
+/* BBFrameTSParser::setFrameSize (bbframe_ts_parser.cpp:31-43): kbch in bits; resets the parser state */
+int dvbs2fec_ts_set_frame_size(dvbs2fec_ts_parser* p, int kbch_bits);
+/* BBFrameTSParser::work (bbframe_ts_parser.cpp:100-392), TS frames: cnt BBFRAMEs of kbch/8 bytes in, 188-byte
+ * packets out; returns the number of bytes written (a multiple of 188) or a negative error.  Host buffers.
+ * Frames carrying GSE (ts_gs = 01) are accepted and counted but their PDUs are not extracted here. */
+int dvbs2fec_ts_work(dvbs2fec_ts_parser* p, const uint8_t* bbframes, int cnt, uint8_t* tsframes, int buffer_outsize);
+/* same on device buffers (e.g. straight from dvbs2fec_decode_batch_device), asynchronous on `stream`;
+ * d_produced (optional, device int) receives the byte count */
+int dvbs2fec_ts_work_device(dvbs2fec_ts_parser* p, const uint8_t* d_bbframes, int cnt, uint8_t* d_tsframes,
+                            int buffer_outsize, int* d_produced, void* stream);
+/* public members after work() (bbframe_ts_parser.h:72-76): last_header (returns 0 if no frame was accepted
+ * yet, 1 otherwise), last_bb_cnt, last_bb_proc; gse_frames = accepted GSE frames in the last call */
+int dvbs2fec_ts_stats(dvbs2fec_ts_parser* p, dvbs2fec_bbheader* last_header, int* last_bb_cnt, int* last_bb_proc,
+                      int* gse_frames);
+
 /* ---- in-tree transmitter for synthetic input (not part of the reference's decode path) ---- */
 /* bbframe: kbch/8 bytes -> code_bits: N bytes of 0/1 (BB scramble, BCH, LDPC; EN 302 307 5.2-5.3) */
 int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits);

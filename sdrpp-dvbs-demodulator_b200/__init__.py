@@ -41,6 +41,12 @@ class Config(C.Structure):
                 ("max_latency_us", C.c_int32), ("max_trials", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
+class BBHeader(C.Structure):
+    """dvbs2fec_bbheader == BBHeader (dvbs2/bbframe_ts_parser.h:37-65)"""
+    _fields_ = [(n, C.c_uint8) for n in ("ts_gs", "sis_mis", "ccm_acm", "issyi", "npd", "ro", "isi", "sync")] + \
+               [(n, C.c_uint16) for n in ("upl", "dfl", "syncd", "reserved")]
+
+
 class Result(C.Structure):
     _fields_ = [("tag", C.c_uint64), ("ldpc_iters", C.c_int16), ("bch_corr", C.c_int16), ("flags", C.c_uint32)]
 
@@ -93,6 +99,13 @@ def lib():
     L.dvbs2fec_encode_fecframe.argtypes = [C.c_int, C.c_int, vp, vp]
     L.dvbs2fec_modulate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     L.dvbs2fec_modcod_info.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip, ip]
+    L.dvbs2fec_ts_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.dvbs2fec_ts_destroy.argtypes = [vp]
+    L.dvbs2fec_ts_destroy.restype = None
+    L.dvbs2fec_ts_set_frame_size.argtypes = [vp, C.c_int]
+    L.dvbs2fec_ts_work.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.dvbs2fec_ts_work_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]
+    L.dvbs2fec_ts_stats.argtypes = [vp, C.POINTER(BBHeader), ip, ip, ip]
     _lib = L
     return L
 
@@ -311,3 +324,48 @@ class S2BBToSoft:
 
     def process(self, plframe):
         return self.dec.bb_to_soft(plframe)[0]
+
+
+class BBFrameTSParser:
+    """dvbs2/bbframe_ts_parser.h:67-108 on the device: BBFRAMEs in, 188-byte TS packets out (GSE frames are
+    accepted and counted, not unpacked).  Parser state persists between work() calls like the reference's."""
+
+    def __init__(self, device=0):
+        self._p = C.c_void_p()
+        _check(lib().dvbs2fec_ts_create(device, C.byref(self._p)))
+        self.last_header = BBHeader()
+        self.last_bb_cnt = self.last_bb_proc = self.gse_frames = 0
+        self.have_header = False
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().dvbs2fec_ts_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setFrameSize(self, bbframe_size):
+        _check(lib().dvbs2fec_ts_set_frame_size(self._p, bbframe_size))
+        self.kbch = bbframe_size
+
+    def _stats(self):
+        a, b, g = C.c_int(), C.c_int(), C.c_int()
+        self.have_header = bool(_check(lib().dvbs2fec_ts_stats(self._p, C.byref(self.last_header), C.byref(a), C.byref(b), C.byref(g))))
+        self.last_bb_cnt, self.last_bb_proc, self.gse_frames = a.value, b.value, g.value
+
+    def work(self, bbframes, cnt=None, buffer_outsize=65536 * 10):
+        """returns the TS bytes produced (uint8 array), like work()'s tsframes[:return value]"""
+        x = np.ascontiguousarray(bbframes, np.uint8)
+        if cnt is None:
+            cnt = x.size // (self.kbch // 8)
+        out = np.zeros(max(buffer_outsize, 1), np.uint8)
+        n = _check(lib().dvbs2fec_ts_work(self._p, _ptr(x), cnt, _ptr(out), buffer_outsize))
+        self._stats()
+        return out[:n]
+
+    def work_device(self, d_bb_ptr, cnt, d_out_ptr, buffer_outsize, d_produced_ptr=0, stream_ptr=0):
+        _check(lib().dvbs2fec_ts_work_device(self._p, d_bb_ptr, cnt, d_out_ptr, buffer_outsize, d_produced_ptr, stream_ptr))

@@ -26,6 +26,7 @@
 #include "host_tables.h"
 #include "ldpc_decoder.cuh"
 #include "s2_codes.h"
+#include "ts_parser.cuh"
 
 using namespace s2;
 
@@ -920,6 +921,132 @@ void* dvbs2fec_alloc_pinned(size_t bytes) {
 void dvbs2fec_free_pinned(void* p) {
     if (p) cudaFreeHost(p);
 }
+
+// ---------------------------------------------------------------- BBFRAME -> TS (row 8(f)-1)
+struct dvbs2fec_ts_parser {
+    int device = 0;
+    int kb = 0, max_dfl = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf<TsState> state;
+    DevBuf<TsPlan> plan;
+    DevBuf<uint8_t> bb, out;
+    PinBuf<int> h_produced;
+};
+
+int dvbs2fec_ts_create(int device, dvbs2fec_ts_parser** out) {
+    if (!out) return fail(DVBS2FEC_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(DVBS2FEC_ENODEV, "no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    if (device < 0 || device >= ndev) return fail(DVBS2FEC_EINVAL, "device %d out of range (%d present)", device, ndev);
+    std::unique_ptr<dvbs2fec_ts_parser> p(new dvbs2fec_ts_parser());
+    p->device = device;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CU(p->state.reserve(1));
+    CU(p->h_produced.reserve(1));
+    CU(cudaMemset(p->state.p, 0, sizeof(TsState)));
+    *out = p.release();
+    return 0;
+}
+
+void dvbs2fec_ts_destroy(dvbs2fec_ts_parser* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) {
+        cudaStreamSynchronize(p->stream);
+        cudaStreamDestroy(p->stream);
+    }
+    p->state.release();
+    p->plan.release();
+    p->bb.release();
+    p->out.release();
+    p->h_produced.release();
+    delete p;
+}
+
+int dvbs2fec_ts_set_frame_size(dvbs2fec_ts_parser* p, int kbch_bits) {
+    if (!p || kbch_bits < 88 || kbch_bits > 65535 || kbch_bits % 8) return fail(DVBS2FEC_EINVAL, "bad frame size");
+    CU(cudaSetDevice(p->device));
+    p->kb = kbch_bits / 8;
+    p->max_dfl = kbch_bits - 80;
+    CU(cudaMemsetAsync(p->state.p, 0, sizeof(TsState), p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int dvbs2fec_ts_work_device(dvbs2fec_ts_parser* p, const uint8_t* d_bbframes, int cnt, uint8_t* d_tsframes,
+                            int buffer_outsize, int* d_produced, void* stream) {
+    if (!p || !p->kb) return fail(DVBS2FEC_EINVAL, "set_frame_size has not been called");
+    if (cnt < 0 || (cnt && !d_bbframes) || !d_tsframes || buffer_outsize < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    CU(cudaSetDevice(p->device));
+    CU(p->plan.reserve(std::max(cnt, 1)));
+    TsArgs a{};
+    a.bb = d_bbframes;
+    a.cnt = cnt;
+    a.kb = p->kb;
+    a.max_dfl = p->max_dfl;
+    a.out = d_tsframes;
+    a.out_cap = buffer_outsize;
+    a.state = p->state.p;
+    a.plan = p->plan.p;
+    a.produced_out = d_produced;
+    int e = ts_launch(a, (cudaStream_t)stream);
+    if (e) return fail(DVBS2FEC_ECUDA, "ts launch: %s", cudaGetErrorString((cudaError_t)e));
+    return 0;
+}
+
+int dvbs2fec_ts_work(dvbs2fec_ts_parser* p, const uint8_t* bbframes, int cnt, uint8_t* tsframes, int buffer_outsize) {
+    if (!p || !p->kb) return fail(DVBS2FEC_EINVAL, "set_frame_size has not been called");
+    if (cnt < 0 || (cnt && !bbframes) || !tsframes || buffer_outsize < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    CU(cudaSetDevice(p->device));
+    const size_t in_bytes = (size_t)cnt * p->kb;
+    // every frame yields fewer output bytes than it has input bytes, plus one carried unit
+    const size_t out_need = std::min((size_t)buffer_outsize, in_bytes + 188);
+    CU(p->bb.reserve(std::max<size_t>(in_bytes, 1)));
+    CU(p->out.reserve(std::max<size_t>(out_need, 1)));
+    if (in_bytes) CU(cudaMemcpyAsync(p->bb.p, bbframes, in_bytes, cudaMemcpyHostToDevice, p->stream));
+    int rc = dvbs2fec_ts_work_device(p, p->bb.p, cnt, p->out.p, buffer_outsize, nullptr, p->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(p->h_produced.p, &p->state.p->produced, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    const int produced = *p->h_produced.p;
+    if (produced > 0) {
+        CU(cudaMemcpyAsync(tsframes, p->out.p, (size_t)produced, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+    }
+    return produced;
+}
+
+int dvbs2fec_ts_stats(dvbs2fec_ts_parser* p, dvbs2fec_bbheader* last_header, int* last_bb_cnt, int* last_bb_proc,
+                      int* gse_frames) {
+    if (!p) return fail(DVBS2FEC_EINVAL, "parser is NULL");
+    CU(cudaSetDevice(p->device));
+    TsState s;
+    CU(cudaMemcpy(&s, p->state.p, sizeof s, cudaMemcpyDeviceToHost));
+    if (last_header) {
+        const uint8_t* b = s.last_header;   // BBHeader(uint8_t*) (bbframe_ts_parser.h:52-64)
+        dvbs2fec_bbheader h{};
+        h.ts_gs = b[0] >> 6;
+        h.sis_mis = (b[0] >> 5) & 1;
+        h.ccm_acm = (b[0] >> 4) & 1;
+        h.issyi = (b[0] >> 3) & 1;
+        h.npd = (b[0] >> 2) & 1;
+        h.ro = b[0] & 3;
+        h.isi = h.sis_mis == 0 ? b[1] : 0;
+        h.upl = (uint16_t)((b[2] << 8) | b[3]);
+        h.dfl = (uint16_t)((b[4] << 8) | b[5]);
+        h.sync = b[6];
+        h.syncd = (uint16_t)((b[7] << 8) | b[8]);
+        *last_header = h;
+    }
+    if (last_bb_cnt) *last_bb_cnt = s.last_bb_cnt;
+    if (last_bb_proc) *last_bb_proc = s.last_bb_proc;
+    if (gse_frames) *gse_frames = s.gse_frames;
+    return s.have_header;
+}
+
 
 int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits) {
     ModcodCfg mc;

@@ -1,0 +1,134 @@
+"""Row 8(f)-1 on the GPU: dvbs2fec_ts_work (BBFRAME -> TS packets) against the CPU oracle of
+BBFrameTSParser::work, against golden outputs of the reference parser, and through properties at full size."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import bbstream
+import orclib
+from fec import pkg
+from test_ts_parser_oracle import OrcParser, header_fields, KBCH
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gpu_header_fields(h):
+    return [h.ts_gs, h.sis_mis, h.ccm_acm, h.issyi, h.npd, h.ro, h.isi, h.upl, h.dfl, h.sync, h.syncd]
+
+
+def compare(kbch, batches, cap=65536 * 10):
+    o = OrcParser(kbch)
+    g = pkg.BBFrameTSParser()
+    g.setFrameSize(kbch)
+    for frames in batches:
+        want = o.work(frames, cap)
+        got = g.work(frames, len(frames), cap)
+        assert np.array_equal(got, want)
+        st = o.stats()
+        assert (g.last_bb_cnt, g.last_bb_proc) == (st["cnt"], st["proc"])
+        assert g.have_header == bool(st["have"])
+        if st["have"]:
+            assert gpu_header_fields(g.last_header) == header_fields(st["hdr"])
+    o.close()
+    g.close()
+
+
+@pytest.mark.parametrize("name", list(KBCH))
+def test_ts_matches_oracle(name):
+    kbch = KBCH[name]
+    rng = np.random.default_rng(len(name) + kbch)
+    pk = bbstream.ts_packets(max(300, 40 * kbch // 1504), rng)
+    frames, _ = bbstream.ts_bbframes(kbch, pk, first_byte=int(rng.integers(0, 188)))
+    cuts = sorted(set(int(x) for x in rng.integers(1, len(frames), 5)))
+    compare(kbch, [frames[a:b] for a, b in zip([0] + cuts, cuts + [len(frames)])])
+
+
+def test_ts_odd_streams_match_oracle():
+    kbch = KBCH["s1/4"]
+    f = bbstream.odd_ts_scenario(np.random.default_rng(5), kbch)
+    compare(kbch, [f[:60], f[60:61], f[61:]])
+    compare(kbch, [f[i:i + 1] for i in range(len(f))])          # one frame per call: all state crosses calls
+    compare(kbch, [f[:0], f])                                   # empty call first
+
+
+def test_ts_output_room_rule_matches_oracle():
+    rng = np.random.default_rng(6)
+    kbch = KBCH["n1/2"]
+    frames, _ = bbstream.ts_bbframes(kbch, bbstream.ts_packets(200, rng))
+    for cap in (0, 188, 189, 190, 188 * 7 + 5, 188 * 21, 188 * 21 + 1, 188 * 22, 188 * 43):
+        compare(kbch, [frames[:3]], cap=cap)
+
+
+def test_gse_frames_are_counted_not_unpacked():
+    rng = np.random.default_rng(8)
+    kbch = KBCH["n1/2"]
+    frames = bbstream.gse_bbframes(kbch, bbstream.gse_scenario(rng))
+    g = pkg.BBFrameTSParser()
+    g.setFrameSize(kbch)
+    out = g.work(frames)
+    assert len(out) == 0 and g.last_bb_proc == len(frames) and g.gse_frames == len(frames)
+    assert g.last_header.ts_gs == 1
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["tsparse_ts_n12", "tsparse_odd_s14"])
+def test_cuda_reproduces_reference_ts_parser(name):
+    gold = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    g = pkg.BBFrameTSParser()
+    g.setFrameSize(int(gold["kbch"]))
+    at = 0
+    for k, (a, b) in enumerate(zip(gold["cuts"][:-1], gold["cuts"][1:])):
+        out = g.work(gold["frames"][a:b], int(b - a))
+        n = int(gold["out_len"][k])
+        assert len(out) == n and np.array_equal(out, gold["out"][at:at + n])
+        at += n
+        assert [g.last_bb_cnt, g.last_bb_proc] == [int(x) for x in gold["stats"][k][11:13]]
+        if g.have_header:
+            assert gpu_header_fields(g.last_header) == [int(x) for x in gold["stats"][k][:11]]
+    g.close()
+
+
+def test_full_size_stream_round_trip_on_device_buffers():
+    """4096 normal-frame BBFRAMEs (16 MB) through the device-pointer entry point, fed in uneven calls: every
+    TS packet after the first sync point comes back exactly once, in order, with 0x47 restored"""
+    import torch
+    rng = np.random.default_rng(9)
+    kbch = KBCH["n1/2"]
+    kb = kbch // 8
+    nframes = 4096
+    npk = nframes * (kb - 10) // 188 + 2
+    pk = bbstream.ts_packets(npk, rng)
+    stream = pk.copy()
+    stream[:, 0] = 0xEE                                       # stands in for the CRC-8 slot (never checked)
+    stream = stream.reshape(-1)
+    df = kb - 10
+    frames = np.zeros((nframes, kb), np.uint8)
+    hdrs = {}
+    for f in range(nframes):
+        pos = f * df
+        syncd = ((-pos) % 188) * 8
+        if syncd not in hdrs:
+            hdrs[syncd] = bbstream.bbheader(0xF0, 1504, df * 8, 0x47, syncd)
+        frames[f, :10] = hdrs[syncd]
+        frames[f, 10:] = stream[pos:pos + df]
+    dev = torch.device("cuda", 0)
+    d_bb = torch.from_numpy(frames).to(dev)
+    d_out = torch.zeros(nframes * kb + 188, dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    g = pkg.BBFrameTSParser()
+    g.setFrameSize(kbch)
+    st = torch.cuda.current_stream()
+    got, at = [], 0
+    for n in (1, 2, 1000, 3, 3090):
+        g.work_device(d_bb[at:at + n].data_ptr(), n, d_out.data_ptr(), d_out.numel(), d_n.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        got.append(d_out[:int(d_n.item())].cpu().numpy().copy())
+        at += n
+    assert at == nframes
+    out = np.concatenate(got).reshape(-1, 188)
+    assert len(out) == (nframes * df - 1) // 188
+    assert np.array_equal(out, pk[:len(out)])
+    g.close()
