@@ -929,6 +929,7 @@ struct dvbs2fec_ts_parser {
     cudaStream_t stream = nullptr;
     DevBuf<TsState> state;
     DevBuf<TsPlan> plan;
+    DevBuf<uint32_t> meta;
     DevBuf<uint8_t> bb, out;
     PinBuf<int> h_produced;
 };
@@ -960,6 +961,7 @@ void dvbs2fec_ts_destroy(dvbs2fec_ts_parser* p) {
     }
     p->state.release();
     p->plan.release();
+    p->meta.release();
     p->bb.release();
     p->out.release();
     p->h_produced.release();
@@ -982,6 +984,7 @@ int dvbs2fec_ts_work_device(dvbs2fec_ts_parser* p, const uint8_t* d_bbframes, in
     if (cnt < 0 || (cnt && !d_bbframes) || !d_tsframes || buffer_outsize < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
     CU(cudaSetDevice(p->device));
     CU(p->plan.reserve(std::max(cnt, 1)));
+    CU(p->meta.reserve(std::max(cnt, 1)));
     TsArgs a{};
     a.bb = d_bbframes;
     a.cnt = cnt;
@@ -991,6 +994,7 @@ int dvbs2fec_ts_work_device(dvbs2fec_ts_parser* p, const uint8_t* d_bbframes, in
     a.out_cap = buffer_outsize;
     a.state = p->state.p;
     a.plan = p->plan.p;
+    a.meta = p->meta.p;
     a.produced_out = d_produced;
     int e = ts_launch(a, (cudaStream_t)stream);
     if (e) return fail(DVBS2FEC_ECUDA, "ts launch: %s", cudaGetErrorString((cudaError_t)e));

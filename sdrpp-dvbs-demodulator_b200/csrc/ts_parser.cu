@@ -1,9 +1,9 @@
 // K6: BBFRAME -> MPEG-TS packets.  See ts_parser.cuh.
 //
-// Two kernels.  ts_plan_kernel (one CTA): all threads check BBHEADERs in parallel, 256 frames at a time; one
-// thread then walks the 256 verdicts in order, because what a frame contributes depends on the parser state the
-// frames before it left behind (in sync or not, bytes of an unfinished unit, room left in the output) -- a few
-// register operations per frame.  ts_copy_kernel (one CTA per frame, a warp per packet) moves the bytes.
+// Two kernels.  ts_plan_kernel (one CTA) checks all BBHEADERs in parallel and then works out what every frame
+// contributes; that depends on the parser state the frames before it left behind (in sync or not, bytes of an
+// unfinished unit), which a three-phase scan over composable state maps delivers without walking the frames
+// one by one.  ts_copy_kernel (one CTA per frame, a warp per packet) moves the bytes.
 // HBM-bound: every BBFRAME byte is read once and every TS byte written once.
 #include "ts_parser.cuh"
 
@@ -26,113 +26,250 @@ __device__ inline unsigned bbheader_crc8(const uint8_t* h) {
 
 enum { kInvalid = 0, kTs = 1, kGse = 2, kOther = 3 };
 
+// One frame's verdict in a word: kind | data-field bytes << 2 | resync skip (SYNCD/8 + 1) << 15
+__device__ inline uint32_t pack_meta(int kind, int dfl, int syncd) { return (uint32_t)kind | ((uint32_t)(dfl >> 3) << 2) | ((uint32_t)((syncd >> 3) + 1) << 15); }
+
+// Parser state seen from outside a frame: -1 = out of sync, else in sync with `st` bytes of an unfinished unit.
+// (The byte count of an out-of-sync parser is never read again: resynchronising zeroes it, :163.)
+struct Step {
+    int next;       // state after the frame
+    int npk;        // packets it emits
+    int off;        // offset in the frame where its bytes start being consumed
+    int tail_off;   // where its own unfinished unit starts, -1 if it leaves none of its own
+};
+__device__ inline Step ts_step(uint32_t m, int st) {
+    const int kind = m & 3;
+    Step r{-1, 0, 10, -1};
+    if (kind == kInvalid) return r;
+    int left = (m >> 2) & 0x1FFF, count = st;
+    if (st < 0) {   // enter just past the first sync byte (:157-168)
+        const int skip = (int)(m >> 15);
+        r.off += skip;
+        left -= skip;
+        count = 0;
+    }
+    r.next = count;
+    if (kind != kTs) return r;
+    if (left >= 188) {   // (:176-201) the carried bytes are completed first, then whole units
+        const int total = left + count;
+        r.npk = total / 188;
+        r.next = total - 188 * r.npk;
+        if (r.next > 0) r.tail_off = r.off + 188 * r.npk - count;
+    } else if (left > 0) {   // (:203-207) too short to complete anything: the carry is replaced
+        r.next = left;
+        r.tail_off = r.off;
+    }
+    return r;
+}
+
+// Exact sequential walk, used when the output may run out of room (:176,208-211): one thread, in frame order.
+__device__ void ts_plan_serial(const TsArgs& a, const uint32_t* meta, int st, int& o_out, int& processed_out, int& gse_out,
+                               int& last_valid_out, int& st_out, int& car_src_out, int& car_off_out) {
+    int o = 0, processed = 0, gse = 0, last_valid = -1, car_src = -1, car_off = 0;
+    bool stop = false;
+    for (int f = 0; f < a.cnt; ++f) {
+        TsPlan p{o, 0, -1, 0, 0, 0};
+        const uint32_t m = meta[f];
+        const int kind = m & 3;
+        if (!stop) {
+            if (kind == kInvalid) {
+                st = -1;
+            } else {
+                int left = (m >> 2) & 0x1FFF, off = 10, count = st;
+                if (st < 0) {
+                    const int skip = (int)(m >> 15);
+                    off += skip;
+                    left -= skip;
+                    count = 0;
+                }
+                last_valid = f;
+                ++processed;
+                gse += kind == kGse;
+                if (kind == kTs) {
+                    const int room = a.out_cap - o;
+                    int consumed = 0;
+                    p.src_off = off;
+                    if (left >= 188 && room > 188) {
+                        int fit = (room - 189) / 188 + 1;
+                        if (count > 0) {
+                            p.head = (short)count;
+                            p.head_src = car_src;
+                            p.head_src_off = car_off;
+                            consumed = 188 - count;
+                            left -= consumed;
+                            count = 0;
+                            p.npk = 1;
+                            --fit;
+                        }
+                        const int whole = min(left / 188, fit);
+                        p.npk = (short)(p.npk + whole);
+                        left -= 188 * whole;
+                        consumed += 188 * whole;
+                    }
+                    o += 188 * p.npk;
+                    if (left > 0) {
+                        count = left;
+                        car_src = f;
+                        car_off = off + consumed;
+                    }
+                    if (a.out_cap - o <= 188) stop = true;
+                }
+                st = count;
+            }
+        }
+        a.plan[f] = p;
+    }
+    o_out = o; processed_out = processed; gse_out = gse; last_valid_out = last_valid; st_out = st;
+    car_src_out = car_src; car_off_out = car_off;
+}
+
+// What a run of frames does to the parser state is one of a small family of maps -- out of sync -> `from_unsync`;
+// in sync with c bytes -> out of sync (`kill`) or (a c + b) mod 188 with a in {0,1} -- so runs compose, and the
+// state in front of every frame follows from a three-phase scan: every thread summarises its run of frames (by
+// probing it with three entry states), one thread chains the summaries, every thread replays its run.
+struct RunMap {
+    short from_unsync, b;
+    uint8_t a, kill;
+    __device__ int operator()(int st) const { return st < 0 ? from_unsync : kill ? -1 : (a * st + b) % 188; }
+};
+
 __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
-    __shared__ uint16_t s_dfl[kPlanThreads], s_syncd[kPlanThreads];
-    __shared__ uint8_t s_kind[kPlanThreads];
-    __shared__ int s_carry[3];   // frame, offset, bytes of the carry this call ends with
+    __shared__ RunMap s_map[kPlanThreads];
+    __shared__ int s_entry[kPlanThreads];                        // state in front of each thread's run
+    __shared__ int s_npk[kPlanThreads], s_valid[kPlanThreads], s_gse[kPlanThreads], s_lastv[kPlanThreads];
+    __shared__ int s_wsrc[kPlanThreads], s_woff[kPlanThreads];   // last frame of the run that left a carry
+    __shared__ int s_fin[8];
     const int tid = threadIdx.x;
     TsState* S = a.state;
-    // parser state, live in thread 0 only
-    unsigned count = 0;
-    int synched = 0, car_src = -1, car_off = 0, o = 0, processed = 0, gse = 0, last_valid = -1;
-    bool stop = false;
-    if (tid == 0) {
-        count = S->count;
-        synched = S->synched;
-        S->entry_buf = S->cur;
-    }
-    for (int base = 0; base < a.cnt; base += kPlanThreads) {
-        const int f = base + tid;
-        if (f < a.cnt) {
-            const uint8_t* h = a.bb + (size_t)f * a.kb;
-            const int dfl = (h[4] << 8) | h[5], syncd = (h[7] << 8) | h[8];
-            int kind = kInvalid;
-            // (:122-150) CRC-8, DFL <= kbch-80, SYNCD < DFL-8 as signed ints, DFL a whole number of bytes
-            if (bbheader_crc8(h) == 0 && dfl <= a.max_dfl && syncd < dfl - 8 && (dfl & 7) == 0) {
-                const int ts_gs = h[0] >> 6;
-                kind = ts_gs == 3 ? kTs : ts_gs == 1 ? kGse : kOther;
-            }
-            s_kind[tid] = (uint8_t)kind;
-            s_dfl[tid] = (uint16_t)dfl;
-            s_syncd[tid] = (uint16_t)syncd;
+    // (0) BBHEADER checks, all frames in parallel (:122-150): CRC-8, DFL <= kbch-80, SYNCD < DFL-8 as signed
+    //     ints, DFL a whole number of bytes
+    for (int f = tid; f < a.cnt; f += kPlanThreads) {
+        const uint8_t* h = a.bb + (size_t)f * a.kb;
+        const int dfl = (h[4] << 8) | h[5], syncd = (h[7] << 8) | h[8];
+        int kind = kInvalid;
+        if (bbheader_crc8(h) == 0 && dfl <= a.max_dfl && syncd < dfl - 8 && (dfl & 7) == 0) {
+            const int ts_gs = h[0] >> 6;
+            kind = ts_gs == 3 ? kTs : ts_gs == 1 ? kGse : kOther;
         }
-        __syncthreads();
-        if (tid == 0) {
-            const int m = min(kPlanThreads, a.cnt - base);
-            for (int k = 0; k < m; ++k) {
-                TsPlan p{o, 0, -1, 0, 0, 0};
-                const int kind = s_kind[k];
-                if (!stop) {
-                    if (kind == kInvalid) {
-                        synched = 0;
-                    } else {
-                        int left = s_dfl[k] >> 3, off = 10;
-                        if (!synched) {   // enter just past the first sync byte (:157-168)
-                            const int skip = (s_syncd[k] >> 3) + 1;
-                            off += skip;
-                            left -= skip;
-                            count = 0;
-                            synched = 1;
-                        }
-                        last_valid = base + k;
-                        ++processed;
-                        gse += kind == kGse;
-                        if (kind == kTs) {   // (:173-212)
-                            const int room = a.out_cap - o;
-                            int consumed = 0;
-                            p.src_off = off;
-                            if (left >= 188 && room > 188) {
-                                int fit = (room - 189) / 188 + 1;
-                                if (count > 0) {
-                                    p.head = (short)count;
-                                    p.head_src = car_src;
-                                    p.head_src_off = car_off;
-                                    consumed = 188 - (int)count;
-                                    left -= consumed;
-                                    count = 0;
-                                    p.npk = 1;
-                                    --fit;
-                                }
-                                const int whole = min(left / 188, fit);
-                                p.npk = (short)(p.npk + whole);
-                                left -= 188 * whole;
-                                consumed += 188 * whole;
-                            }
-                            o += 188 * p.npk;
-                            if (left > 0) {
-                                count = (unsigned)left;
-                                car_src = base + k;
-                                car_off = off + consumed;
-                            }
-                            if (a.out_cap - o <= 188) stop = true;
-                        }
-                    }
-                }
-                a.plan[base + k] = p;
-            }
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        S->count = count;
-        S->synched = synched;
-        S->last_bb_cnt = a.cnt;
-        S->last_bb_proc = processed;
-        S->gse_frames = gse;
-        S->produced = o;
-        if (a.produced_out) *a.produced_out = o;
-        if (last_valid >= 0) {
-            S->have_header = 1;
-            for (int i = 0; i < 10; ++i) S->last_header[i] = a.bb[(size_t)last_valid * a.kb + i];
-        }
-        s_carry[0] = car_src;
-        s_carry[1] = car_off;
-        s_carry[2] = (int)min(count, 188u);
-        if (car_src >= 0) S->cur ^= 1;
+        a.meta[f] = pack_meta(kind, dfl, syncd);
     }
     __syncthreads();
-    if (s_carry[0] >= 0 && tid < s_carry[2])
-        S->unit[S->entry_buf ^ 1][tid] = a.bb[(size_t)s_carry[0] * a.kb + s_carry[1] + tid];
+    const int per = (a.cnt + kPlanThreads - 1) / kPlanThreads;
+    const int f0 = min(a.cnt, tid * per), f1 = min(a.cnt, f0 + per);
+    // (1) summarise the run
+    {
+        int su = -1, s0 = 0, s1 = 1;
+        for (int f = f0; f < f1; ++f) {
+            const uint32_t m = a.meta[f];
+            su = ts_step(m, su).next;
+            s0 = ts_step(m, s0).next;
+            s1 = ts_step(m, s1).next;
+        }
+        RunMap r;
+        r.from_unsync = (short)su;
+        r.kill = s0 < 0;
+        r.b = (short)max(s0, 0);
+        r.a = (uint8_t)(s0 >= 0 && s1 != s0);
+        s_map[tid] = r;
+    }
+    __syncthreads();
+    // (2) chain the summaries
+    if (tid == 0) {
+        int st = S->synched ? (int)S->count : -1;
+        for (int t = 0; t < kPlanThreads; ++t) {
+            s_entry[t] = st;
+            st = s_map[t](st);
+        }
+        s_fin[0] = st;
+        S->entry_buf = S->cur;
+    }
+    __syncthreads();
+    // (3) replay for the run's totals
+    {
+        int st = s_entry[tid], npk = 0, valid = 0, gse = 0, lastv = -1, wsrc = -1, woff = 0;
+        for (int f = f0; f < f1; ++f) {
+            const uint32_t m = a.meta[f];
+            const Step r = ts_step(m, st);
+            if ((m & 3) != kInvalid) {
+                ++valid;
+                lastv = f;
+                gse += (m & 3) == kGse;
+            }
+            npk += r.npk;
+            if (r.tail_off >= 0) {
+                wsrc = f;
+                woff = r.tail_off;
+            }
+            st = r.next;
+        }
+        s_npk[tid] = npk; s_valid[tid] = valid; s_gse[tid] = gse; s_lastv[tid] = lastv; s_wsrc[tid] = wsrc; s_woff[tid] = woff;
+    }
+    __syncthreads();
+    // (4) exclusive prefixes over the runs
+    if (tid == 0) {
+        int o = 0, valid = 0, gse = 0, lastv = -1, wsrc = -1, woff = 0;
+        for (int t = 0; t < kPlanThreads; ++t) {
+            const int n = s_npk[t], ws = s_wsrc[t], wo = s_woff[t];
+            s_npk[t] = o;
+            s_wsrc[t] = wsrc;
+            s_woff[t] = woff;
+            o += n;
+            valid += s_valid[t];
+            gse += s_gse[t];
+            lastv = max(lastv, s_lastv[t]);
+            if (ws >= 0) {
+                wsrc = ws;
+                woff = wo;
+            }
+        }
+        s_fin[1] = 188 * o; s_fin[2] = valid; s_fin[3] = gse; s_fin[4] = lastv; s_fin[5] = wsrc; s_fin[6] = woff;
+        // enough room for everything (no test of :176/:208 can fail)?  Otherwise redo it the sequential way.
+        s_fin[7] = a.out_cap - 188 * o > 188;
+        if (!s_fin[7]) {
+            const int st = S->synched ? (int)S->count : -1;
+            ts_plan_serial(a, a.meta, st, s_fin[1], s_fin[2], s_fin[3], s_fin[4], s_fin[0], s_fin[5], s_fin[6]);
+        }
+    }
+    __syncthreads();
+    // (5) replay once more, now writing what every frame contributes
+    if (s_fin[7]) {
+        int st = s_entry[tid], o = s_npk[tid], wsrc = s_wsrc[tid], woff = s_woff[tid];
+        for (int f = f0; f < f1; ++f) {
+            const Step r = ts_step(a.meta[f], st);
+            TsPlan p{188 * o, r.off, -1, 0, (short)r.npk, 0};
+            if (r.npk > 0 && st > 0) {   // first unit starts with the carried bytes (st <= 0: entered clean or resynced)
+                p.head = (short)st;
+                p.head_src = wsrc;
+                p.head_src_off = woff;
+            }
+            a.plan[f] = p;
+            o += r.npk;
+            if (r.tail_off >= 0) {
+                wsrc = f;
+                woff = r.tail_off;
+            }
+            st = r.next;
+        }
+    }
+    // (6) commit the state the call ends with
+    if (tid == 0) {
+        const int st = s_fin[0];
+        S->synched = st >= 0;
+        if (st >= 0) S->count = (unsigned)st;   // out of sync: the stale count is dead (zeroed on resync)
+        S->last_bb_cnt = a.cnt;
+        S->last_bb_proc = s_fin[2];
+        S->gse_frames = s_fin[3];
+        S->produced = s_fin[1];
+        if (a.produced_out) *a.produced_out = s_fin[1];
+        if (s_fin[4] >= 0) {
+            S->have_header = 1;
+            for (int i = 0; i < 10; ++i) S->last_header[i] = a.bb[(size_t)s_fin[4] * a.kb + i];
+        }
+        if (s_fin[5] >= 0) S->cur ^= 1;
+    }
+    __syncthreads();
+    if (s_fin[5] >= 0 && tid < min(max(s_fin[0], 0), 188))
+        S->unit[S->entry_buf ^ 1][tid] = a.bb[(size_t)s_fin[5] * a.kb + s_fin[6] + tid];
 }
 
 __global__ void __launch_bounds__(kCopyThreads) ts_copy_kernel(const TsArgs a) {
@@ -144,16 +281,30 @@ __global__ void __launch_bounds__(kCopyThreads) ts_copy_kernel(const TsArgs a) {
     if (p.head) carry = p.head_src < 0 ? a.state->unit[a.state->entry_buf] : a.bb + (size_t)p.head_src * a.kb + p.head_src_off;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool words = ((uintptr_t)a.out & 3) == 0;
+    const uint8_t* bb_end = a.bb + (size_t)a.cnt * a.kb;
     for (int u = warp; u < p.npk; u += kCopyThreads / 32) {
         uint8_t* dst = a.out + p.out_off + 188 * u;
         // frame offset of the unit's byte 0; the first `head` bytes of unit 0 lie in the carry instead
         const int ustart = p.src_off + 188 * u - p.head;
         const int head = u == 0 ? p.head : 0;
+        // output byte k is unit byte k-1 (k = 0: the sync byte); the unit's 188th byte, the next CRC slot, is dropped
+        const uintptr_t s0 = (uintptr_t)(fr + ustart - 1);
+        if (words && head == 0 && reinterpret_cast<const uint8_t*>((s0 & ~(uintptr_t)3) + 192) <= bb_end) {
+            // aligned 32-bit loads, realigned with a funnel shift
+            const uint32_t* al = reinterpret_cast<const uint32_t*>(s0 & ~(uintptr_t)3);
+            const int sh = 8 * (int)(s0 & 3);
+            for (int w = lane; w < 47; w += 32) {
+                uint32_t v = __funnelshift_r(__ldg(al + w), __ldg(al + w + 1), sh);
+                if (w == 0) v = (v & 0xFFFFFF00u) | 0x47u;
+                reinterpret_cast<uint32_t*>(dst)[w] = v;
+            }
+            continue;
+        }
         for (int w = lane; w < 47; w += 32) {
             uint32_t v = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int i = 4 * w + k - 1;   // unit byte behind output byte 4w+k; the unit's 188th byte is dropped
+                const int i = 4 * w + k - 1;
                 const uint32_t byte = i < 0 ? 0x47u : (i < head ? carry[i] : fr[ustart + i]);
                 v |= byte << (8 * k);
             }

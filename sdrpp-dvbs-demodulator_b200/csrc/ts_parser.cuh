@@ -44,6 +44,7 @@ struct TsArgs {
     int out_cap;
     TsState* state;
     TsPlan* plan;        // cnt entries of scratch
+    uint32_t* meta;      // cnt words of scratch
     int* produced_out;   // optional device int
 };
 
