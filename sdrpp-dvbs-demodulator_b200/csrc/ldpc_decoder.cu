@@ -22,6 +22,7 @@ struct LdpcParams {
     uint8_t* workspace;
     unsigned long long ws_stride;
     unsigned int* work_counter;
+    const unsigned int* arrived;      // frames resident so far (streamed input), or nullptr
     const uint8_t* row_level;
     uint16_t layer_off[kMaxLayers + 1];
     uint8_t layer_nlev[kMaxLayers];
@@ -196,7 +197,20 @@ __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const i
     }
 }
 
-template <int CNT, bool UNIFORM>
+// Streamed input: block until the copy engine has delivered `need` frames.  Kept out of line so that the decoder
+// around the call site compiles to the same code as without it.
+__device__ __noinline__ void wait_arrived(const unsigned int* arrived_ptr, unsigned need) {
+    const volatile unsigned* arrived = arrived_ptr;
+    const long long t0 = clock64();
+    while (*arrived < need) {
+        __nanosleep(500);
+        if (clock64() - t0 > (10ll << 30)) __trap();   // ~5 s: the host never sent the data
+    }
+}
+
+// STREAMED: the input copy is still running when the kernel starts (LdpcArgs::arrived); a separate instantiation,
+// because the waiting code in the pair hand-out measurably perturbs the scheduling of the resident-input kernel.
+template <int CNT, bool UNIFORM, bool STREAMED>
 __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kernel(const __grid_constant__ LdpcParams p) {
     constexpr int SLOTS = CNT + 2;
     constexpr int MW = (SLOTS + 1) / 2;     // message words per row in registers
@@ -222,7 +236,17 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_pair = atomicAdd(p.work_counter, 1u);
+        if (tid == 0) {
+            const unsigned np = atomicAdd(p.work_counter, 1u);
+            s_pair = np;
+            if (STREAMED && np < (unsigned)npairs) {
+                // streamed input: the copy engine raises *arrived behind every piece of frames it has delivered
+                // (same stream, so the data is in memory before the count); pairs are handed out in frame order,
+                // so every waiter is waiting for a copy that is already queued
+                wait_arrived(p.arrived, min(2u * np + 2u, (unsigned)p.nframes));
+                __threadfence();
+            }
+        }
         __syncthreads();
         const unsigned pair = s_pair;
         if (pair >= (unsigned)npairs) break;
@@ -234,8 +258,9 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
         // ---- load: systematic LLRs -> shared (A in even bytes, B in odd), parity LLRs -> workspace,
         //      permuted to layered order pty[360 i + j] = v[K + q j + i] (layered_decoder.hh:124-126)
         for (int x = tid; x < K / 8; x += kLdpcThreads) {
-            uint2 a = __ldg(reinterpret_cast<const uint2*>(inA) + x);
-            uint2 b = __ldg(reinterpret_cast<const uint2*>(inB) + x);
+            // streamed: the copy engine is still writing other frames of this buffer -> L2-coherent loads
+            uint2 a = STREAMED ? __ldcg(reinterpret_cast<const uint2*>(inA) + x) : __ldg(reinterpret_cast<const uint2*>(inA) + x);
+            uint2 b = STREAMED ? __ldcg(reinterpret_cast<const uint2*>(inB) + x) : __ldg(reinterpret_cast<const uint2*>(inB) + x);
             uint4 o;
             o.x = prmt(a.x, b.x, 0x5140) ^ 0x80808080u;   // interleave A/B bytes, to offset binary
             o.y = prmt(a.x, b.x, 0x7362) ^ 0x80808080u;
@@ -256,7 +281,7 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
                 const int nvec = ncol * q / 8;                        // q * 32 and q * 8 are multiples of 8
                 for (int x = tid; x < nvec; x += kLdpcThreads) {
                     const int base = (q * jj0) / 8 + x;
-                    uint2 a = __ldg(srcA + base), b = __ldg(srcB + base);
+                    uint2 a = STREAMED ? __ldcg(srcA + base) : __ldg(srcA + base), b = STREAMED ? __ldcg(srcB + base) : __ldg(srcB + base);
                     int jr = (8 * x) / q, ii = 8 * x - jr * q;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
@@ -463,12 +488,12 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
 using KernelFn = void (*)(const LdpcParams);
 struct Variant {
     int cnt;
-    KernelFn uniform;   // every layer has exactly cnt data links per row (all normal codes, 5 short ones)
-    KernelFn ragged;    // layers with fewer links exist (short 1/4, 1/2, 3/4, 4/5, 5/6)
+    KernelFn uniform[2];   // every layer has exactly cnt data links per row (all normal codes, 5 short ones)
+    KernelFn ragged[2];    // layers with fewer links exist (short 1/4, 1/2, 3/4, 4/5, 5/6); [1] = streamed input
 };
-#define VU(c) {c, ldpc_pair_kernel<c, true>, nullptr}
-#define VB(c) {c, ldpc_pair_kernel<c, true>, ldpc_pair_kernel<c, false>}
-#define VR(c) {c, nullptr, ldpc_pair_kernel<c, false>}
+#define VU(c) {c, {ldpc_pair_kernel<c, true, false>, ldpc_pair_kernel<c, true, true>}, {nullptr, nullptr}}
+#define VB(c) {c, {ldpc_pair_kernel<c, true, false>, ldpc_pair_kernel<c, true, true>}, {ldpc_pair_kernel<c, false, false>, ldpc_pair_kernel<c, false, true>}}
+#define VR(c) {c, {nullptr, nullptr}, {ldpc_pair_kernel<c, false, false>, ldpc_pair_kernel<c, false, true>}}
 // one instantiation per distinct "max data links per row" among the 21 codes
 const Variant kVariants[] = {VB(2), VU(3), VU(4), VB(5), VU(8), VU(9), VR(11), VU(12), VU(16), VR(17), VU(20), VU(25), VU(28)};
 #undef VU
@@ -480,12 +505,12 @@ const Variant* pick(int max_cnt) {
         if (v.cnt >= max_cnt) return &v;
     return nullptr;
 }
-KernelFn pick_fn(const LdpcDev& c) {
+KernelFn pick_fn(const LdpcDev& c, bool streamed = false) {
     const Variant* v = pick(c.max_cnt);
     if (!v) return nullptr;
     bool uniform = v->cnt == c.max_cnt;
     for (int i = 0; i < c.q && uniform; ++i) uniform = (c.layer_off[i + 1] - c.layer_off[i]) == v->cnt;
-    return (uniform && v->uniform) ? v->uniform : v->ragged;
+    return (uniform && v->uniform[0]) ? v->uniform[streamed] : v->ragged[streamed];
 }
 
 }  // namespace
@@ -523,7 +548,7 @@ int ldpc_max_ctas_per_sm(const LdpcDev& code) {
 int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
     const LdpcDev& c = a.code;
     const Variant* v = pick(c.max_cnt);
-    KernelFn fn = pick_fn(c);
+    KernelFn fn = pick_fn(c, a.arrived != nullptr);
     if (!v || !fn || c.q > kMaxLayers) return (int)cudaErrorInvalidValue;
     LdpcParams p;
     p.N = c.N; p.K = c.K; p.R = c.R; p.q = c.q; p.ngroups = c.ngroups;
@@ -534,6 +559,7 @@ int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
     p.workspace = a.workspace;
     p.ws_stride = ldpc_workspace_bytes(c);
     p.work_counter = a.work_counter;
+    p.arrived = a.arrived;
     p.row_level = c.row_level;
     const int nlinks = c.layer_off[c.q];
     if (nlinks > kMaxLinks) return (int)cudaErrorInvalidValue;

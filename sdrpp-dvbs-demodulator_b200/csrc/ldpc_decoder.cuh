@@ -55,6 +55,7 @@ struct LdpcArgs {
     int8_t* llr_out;        // [nframes][N] or nullptr: posterior LLRs (what the reference leaves in place)
     uint8_t* workspace;     // gridDim.x * ldpc_workspace_bytes(code)
     unsigned int* work_counter;  // zeroed before launch
+    const unsigned int* arrived; // nullptr, or a device word the input copy raises: frames of llr_in delivered so far
 };
 
 inline size_t ldpc_workspace_bytes(const LdpcDev& c) {
