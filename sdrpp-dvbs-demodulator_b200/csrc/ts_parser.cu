@@ -1,7 +1,7 @@
 // K6: BBFRAME -> MPEG-TS packets.  See ts_parser.cuh.
 //
-// Two kernels.  ts_plan_kernel (one CTA) checks all BBHEADERs in parallel and then works out what every frame
-// contributes; that depends on the parser state the frames before it left behind (in sync or not, bytes of an
+// Three kernels.  ts_header_kernel checks the BBHEADERs, a thread per frame.  ts_plan_kernel (one CTA) works out
+// what every frame contributes; that depends on the parser state the frames before it left behind (in sync or not, bytes of an
 // unfinished unit), which a three-phase scan over composable state maps delivers without walking the frames
 // one by one.  ts_copy_kernel (one CTA per frame, a warp per packet) moves the bytes.
 // HBM-bound: every BBFRAME byte is read once and every TS byte written once.
@@ -10,6 +10,7 @@
 namespace s2 {
 namespace {
 
+constexpr int kHeaderThreads = 128;
 constexpr int kPlanThreads = 256;
 constexpr int kCopyThreads = 128;
 
@@ -123,72 +124,118 @@ __device__ void ts_plan_serial(const TsArgs& a, const uint32_t* meta, int st, in
     car_src_out = car_src; car_off_out = car_off;
 }
 
-// What a run of frames does to the parser state is one of a small family of maps -- out of sync -> `from_unsync`;
-// in sync with c bytes -> out of sync (`kill`) or (a c + b) mod 188 with a in {0,1} -- so runs compose, and the
-// state in front of every frame follows from a three-phase scan: every thread summarises its run of frames (by
-// probing it with three entry states), one thread chains the summaries, every thread replays its run.
-struct RunMap {
-    short from_unsync, b;
-    uint8_t a, kill;
-    __device__ int operator()(int st) const { return st < 0 ? from_unsync : kill ? -1 : (a * st + b) % 188; }
-};
+// What a run of frames does to the parser state is one of a small family of maps -- out of sync -> a constant;
+// in sync with c bytes -> out of sync ("kill") or (a c + b) mod 188 with a in {0,1} -- which is closed under
+// composition.  So the state in front of every frame follows from a scan: every thread summarises its run of
+// frames (by probing it with three entry states), a block-wide scan composes the summaries, every thread
+// replays its run.  A map is packed as (image of "out of sync") + 1 | b << 9 | a << 17 | kill << 18.
+__device__ inline uint32_t map_pack(int from_unsync, int a, int b, int kill) {
+    return (uint32_t)(from_unsync + 1) | (uint32_t)b << 9 | (uint32_t)a << 17 | (uint32_t)kill << 18;
+}
+__device__ inline int map_apply(uint32_t m, int st) {
+    if (st < 0) return (int)(m & 0x1FF) - 1;
+    if ((m >> 18) & 1) return -1;
+    return (int)(((m >> 17) & 1) * st + ((m >> 9) & 0xFF)) % 188;
+}
+__device__ inline uint32_t map_compose(uint32_t f, uint32_t g) {   // f first, then g
+    const int from_unsync = map_apply(g, (int)(f & 0x1FF) - 1);
+    if ((f >> 18) & 1) {   // in sync -> out of sync -> wherever g sends "out of sync"
+        const int gu = (int)(g & 0x1FF) - 1;
+        return gu < 0 ? map_pack(from_unsync, 0, 0, 1) : map_pack(from_unsync, 0, gu, 0);
+    }
+    if ((g >> 18) & 1) return map_pack(from_unsync, 0, 0, 1);
+    const int fa = (f >> 17) & 1, fb = (f >> 9) & 0xFF, ga = (g >> 17) & 1, gb = (g >> 9) & 0xFF;
+    return map_pack(from_unsync, ga & fa, (ga * fb + gb) % 188, 0);
+}
+constexpr uint32_t kMapIdentity = 0u | 0u << 9 | 1u << 17;   // out of sync stays out of sync, c -> c
+
+// block-wide scans over the kPlanThreads per-thread values: exclusive prefix in the return value, total in `total`
+template <typename T, typename Op>
+__device__ inline T block_scan_exclusive(T v, T identity, Op op, T* s_warp, T& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kPlanThreads / 32;
+    T incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const T o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl = op(o, incl);
+    }
+    __syncthreads();   // s_warp may still be read from a previous scan
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    T wpre = identity;
+    T run = identity;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {   // 8 warp totals: every thread folds them itself
+        if (w == warp) wpre = run;
+        run = op(run, s_warp[w]);
+    }
+    total = run;
+    T excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+    if (lane == 0) excl = identity;
+    return op(wpre, excl);
+}
+
+// (0) BBHEADER checks, one thread per frame (:122-150): CRC-8, DFL <= kbch-80, SYNCD < DFL-8 as signed ints,
+//     DFL a whole number of bytes
+__global__ void __launch_bounds__(kHeaderThreads) ts_header_kernel(const TsArgs a) {
+    const int f = blockIdx.x * kHeaderThreads + threadIdx.x;
+    if (f >= a.cnt) return;
+    const uint8_t* h = a.bb + (size_t)f * a.kb;
+    uint8_t b[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) b[i] = h[i];
+    const int dfl = (b[4] << 8) | b[5], syncd = (b[7] << 8) | b[8];
+    int kind = kInvalid;
+    if (bbheader_crc8(b) == 0 && dfl <= a.max_dfl && syncd < dfl - 8 && (dfl & 7) == 0) {
+        const int ts_gs = b[0] >> 6;
+        kind = ts_gs == 3 ? kTs : ts_gs == 1 ? kGse : kOther;
+    }
+    a.meta[f] = pack_meta(kind, dfl, syncd);
+}
+
+constexpr int kMetaShared = 8192;   // frames whose verdict words are staged in shared memory
 
 __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
-    __shared__ RunMap s_map[kPlanThreads];
-    __shared__ int s_entry[kPlanThreads];                        // state in front of each thread's run
-    __shared__ int s_npk[kPlanThreads], s_valid[kPlanThreads], s_gse[kPlanThreads], s_lastv[kPlanThreads];
-    __shared__ int s_wsrc[kPlanThreads], s_woff[kPlanThreads];   // last frame of the run that left a carry
+    __shared__ uint32_t s_meta[kMetaShared];
+    __shared__ uint32_t s_w32[kPlanThreads / 32];
+    __shared__ unsigned long long s_w64[kPlanThreads / 32];
     __shared__ int s_fin[8];
     const int tid = threadIdx.x;
     TsState* S = a.state;
-    // (0) BBHEADER checks, all frames in parallel (:122-150): CRC-8, DFL <= kbch-80, SYNCD < DFL-8 as signed
-    //     ints, DFL a whole number of bytes
-    for (int f = tid; f < a.cnt; f += kPlanThreads) {
-        const uint8_t* h = a.bb + (size_t)f * a.kb;
-        const int dfl = (h[4] << 8) | h[5], syncd = (h[7] << 8) | h[8];
-        int kind = kInvalid;
-        if (bbheader_crc8(h) == 0 && dfl <= a.max_dfl && syncd < dfl - 8 && (dfl & 7) == 0) {
-            const int ts_gs = h[0] >> 6;
-            kind = ts_gs == 3 ? kTs : ts_gs == 1 ? kGse : kOther;
-        }
-        a.meta[f] = pack_meta(kind, dfl, syncd);
+    const uint32_t* M = a.meta;
+    if (a.cnt <= kMetaShared) {
+        for (int f = tid; f < a.cnt; f += kPlanThreads) s_meta[f] = a.meta[f];
+        M = s_meta;
+        __syncthreads();
     }
-    __syncthreads();
+    const int st0 = S->synched ? (int)S->count : -1;
     const int per = (a.cnt + kPlanThreads - 1) / kPlanThreads;
     const int f0 = min(a.cnt, tid * per), f1 = min(a.cnt, f0 + per);
     // (1) summarise the run
+    uint32_t mymap;
     {
         int su = -1, s0 = 0, s1 = 1;
         for (int f = f0; f < f1; ++f) {
-            const uint32_t m = a.meta[f];
+            const uint32_t m = M[f];
             su = ts_step(m, su).next;
             s0 = ts_step(m, s0).next;
             s1 = ts_step(m, s1).next;
         }
-        RunMap r;
-        r.from_unsync = (short)su;
-        r.kill = s0 < 0;
-        r.b = (short)max(s0, 0);
-        r.a = (uint8_t)(s0 >= 0 && s1 != s0);
-        s_map[tid] = r;
+        mymap = map_pack(su, s0 >= 0 && s1 != s0, max(s0, 0), s0 < 0);
     }
-    __syncthreads();
-    // (2) chain the summaries
-    if (tid == 0) {
-        int st = S->synched ? (int)S->count : -1;
-        for (int t = 0; t < kPlanThreads; ++t) {
-            s_entry[t] = st;
-            st = s_map[t](st);
-        }
-        s_fin[0] = st;
-        S->entry_buf = S->cur;
-    }
-    __syncthreads();
+    // (2) compose the summaries: state in front of each run, and after the last one
+    uint32_t total_map;
+    const uint32_t pre_map = block_scan_exclusive(mymap, kMapIdentity, map_compose, s_w32, total_map);
+    const int entry = map_apply(pre_map, st0);
+    const int final_state = map_apply(total_map, st0);
     // (3) replay for the run's totals
+    int npk = 0, valid = 0, gse = 0, lastv = -1;
+    unsigned long long writer = 0;   // (frame + 1) << 32 | offset of the carry it leaves; 0: none
     {
-        int st = s_entry[tid], npk = 0, valid = 0, gse = 0, lastv = -1, wsrc = -1, woff = 0;
+        int st = entry;
         for (int f = f0; f < f1; ++f) {
-            const uint32_t m = a.meta[f];
+            const uint32_t m = M[f];
             const Step r = ts_step(m, st);
             if ((m & 3) != kInvalid) {
                 ++valid;
@@ -196,46 +243,40 @@ __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
                 gse += (m & 3) == kGse;
             }
             npk += r.npk;
-            if (r.tail_off >= 0) {
-                wsrc = f;
-                woff = r.tail_off;
-            }
+            if (r.tail_off >= 0) writer = ((unsigned long long)(f + 1) << 32) | (unsigned)r.tail_off;
             st = r.next;
         }
-        s_npk[tid] = npk; s_valid[tid] = valid; s_gse[tid] = gse; s_lastv[tid] = lastv; s_wsrc[tid] = wsrc; s_woff[tid] = woff;
     }
-    __syncthreads();
-    // (4) exclusive prefixes over the runs
+    // (4) prefixes over the runs: packets before a run, last frame before it that left a carry; totals
+    auto add = [](uint32_t x, uint32_t y) { return x + y; };
+    auto umax = [](uint32_t x, uint32_t y) { return x > y ? x : y; };
+    auto later = [](unsigned long long x, unsigned long long y) { return y ? y : x; };   // y is the later run
+    uint32_t npk_total, valid_total, gse_total, lastv_total;
+    unsigned long long writer_total;
+    const uint32_t npk_before = block_scan_exclusive((uint32_t)npk, 0u, add, s_w32, npk_total);
+    block_scan_exclusive((uint32_t)valid, 0u, add, s_w32, valid_total);
+    block_scan_exclusive((uint32_t)gse, 0u, add, s_w32, gse_total);
+    block_scan_exclusive((uint32_t)(lastv + 1), 0u, umax, s_w32, lastv_total);
+    const unsigned long long writer_before = block_scan_exclusive(writer, 0ull, later, s_w64, writer_total);
+    // enough room for everything (no test of :176/:208 can fail)?  Otherwise one thread redoes it in frame order.
+    const bool roomy = a.out_cap - 188 * (int)npk_total > 188;
     if (tid == 0) {
-        int o = 0, valid = 0, gse = 0, lastv = -1, wsrc = -1, woff = 0;
-        for (int t = 0; t < kPlanThreads; ++t) {
-            const int n = s_npk[t], ws = s_wsrc[t], wo = s_woff[t];
-            s_npk[t] = o;
-            s_wsrc[t] = wsrc;
-            s_woff[t] = woff;
-            o += n;
-            valid += s_valid[t];
-            gse += s_gse[t];
-            lastv = max(lastv, s_lastv[t]);
-            if (ws >= 0) {
-                wsrc = ws;
-                woff = wo;
-            }
-        }
-        s_fin[1] = 188 * o; s_fin[2] = valid; s_fin[3] = gse; s_fin[4] = lastv; s_fin[5] = wsrc; s_fin[6] = woff;
-        // enough room for everything (no test of :176/:208 can fail)?  Otherwise redo it the sequential way.
-        s_fin[7] = a.out_cap - 188 * o > 188;
-        if (!s_fin[7]) {
-            const int st = S->synched ? (int)S->count : -1;
-            ts_plan_serial(a, a.meta, st, s_fin[1], s_fin[2], s_fin[3], s_fin[4], s_fin[0], s_fin[5], s_fin[6]);
-        }
+        S->entry_buf = S->cur;
+        s_fin[0] = final_state;
+        s_fin[1] = 188 * (int)npk_total;
+        s_fin[2] = (int)valid_total;
+        s_fin[3] = (int)gse_total;
+        s_fin[4] = (int)lastv_total - 1;
+        s_fin[5] = (int)(writer_total >> 32) - 1;
+        s_fin[6] = (int)(writer_total & 0xFFFFFFFFu);
+        if (!roomy) ts_plan_serial(a, M, st0, s_fin[1], s_fin[2], s_fin[3], s_fin[4], s_fin[0], s_fin[5], s_fin[6]);
     }
-    __syncthreads();
     // (5) replay once more, now writing what every frame contributes
-    if (s_fin[7]) {
-        int st = s_entry[tid], o = s_npk[tid], wsrc = s_wsrc[tid], woff = s_woff[tid];
+    if (roomy) {
+        int st = entry, o = (int)npk_before;
+        int wsrc = (int)(writer_before >> 32) - 1, woff = (int)(writer_before & 0xFFFFFFFFu);
         for (int f = f0; f < f1; ++f) {
-            const Step r = ts_step(a.meta[f], st);
+            const Step r = ts_step(M[f], st);
             TsPlan p{188 * o, r.off, -1, 0, (short)r.npk, 0};
             if (r.npk > 0 && st > 0) {   // first unit starts with the carried bytes (st <= 0: entered clean or resynced)
                 p.head = (short)st;
@@ -251,6 +292,7 @@ __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
             st = r.next;
         }
     }
+    __syncthreads();
     // (6) commit the state the call ends with
     if (tid == 0) {
         const int st = s_fin[0];
@@ -321,6 +363,7 @@ __global__ void __launch_bounds__(kCopyThreads) ts_copy_kernel(const TsArgs a) {
 }  // namespace
 
 int ts_launch(const TsArgs& a, cudaStream_t stream) {
+    if (a.cnt > 0) ts_header_kernel<<<(a.cnt + kHeaderThreads - 1) / kHeaderThreads, kHeaderThreads, 0, stream>>>(a);
     ts_plan_kernel<<<1, kPlanThreads, 0, stream>>>(a);   // also for cnt == 0: the counters are per call
     if (a.cnt > 0) ts_copy_kernel<<<a.cnt, kCopyThreads, 0, stream>>>(a);
     return (int)cudaGetLastError();

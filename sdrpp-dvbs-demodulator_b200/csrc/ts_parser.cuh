@@ -48,6 +48,6 @@ struct TsArgs {
     int* produced_out;   // optional device int
 };
 
-int ts_launch(const TsArgs& a, cudaStream_t stream);  // two launches; returns a cudaError_t value
+int ts_launch(const TsArgs& a, cudaStream_t stream);  // three launches; returns a cudaError_t value
 
 }  // namespace s2
