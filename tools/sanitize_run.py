@@ -31,3 +31,31 @@ for modcod, short, esn0 in ((4, True, 1.6), (5, True, 3.2), (4, False, 1.6)):
     bb, res = dec.decode_batch(llr)
     print(modcod, short, res["ldpc_iters"].tolist(), res["bch_corr"].tolist())
 dec.close()
+# frame queue: small batches through the staging ring, partial collects
+dec = pkg.DVBS2Decoder(max_batch=2, max_latency_us=300, max_trials=6)
+dec.setDemodParams(4, True, False, 6)
+codes = [pkg.encode_fecframe(4, True, rng.integers(0, 256, dec.kbch // 8, dtype=np.uint8)) for _ in range(7)]
+got = 0
+for i, c in enumerate(codes):
+    dec.submit_llr(np.where(c > 0, -20, 20).astype(np.int8), i)
+    got += len(dec.collect(1)[1])
+dec.flush()
+while got < len(codes):
+    got += len(dec.collect(3, timeout_us=2_000_000)[1])
+print("queue", got)
+dec.close()
+# BBFRAME -> TS: header faults, resyncs, carried units, tiny output room, calls of every size
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bbstream  # noqa: E402
+ts = pkg.BBFrameTSParser()
+ts.setFrameSize(3072)
+f = bbstream.odd_ts_scenario(np.random.default_rng(5), 3072)
+tot = 0
+for a, b, cap in ((0, 60, 655360), (60, 61, 655360), (61, 90, 189), (90, 120, 655360)):
+    tot += len(ts.work(f[a:b], b - a, cap))
+ts.setFrameSize(32208)
+pk = bbstream.ts_packets(300, np.random.default_rng(6))
+fr, _ = bbstream.ts_bbframes(32208, pk, first_byte=50)
+tot += len(ts.work(fr))
+print("ts bytes", tot)
+ts.close()
