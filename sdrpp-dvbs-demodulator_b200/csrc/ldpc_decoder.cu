@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace s2 {
@@ -27,6 +28,7 @@ struct LdpcParams {
     uint16_t layer_off[kMaxLayers + 1];
     uint8_t layer_nlev[kMaxLayers];
     uint8_t layer_sync[kMaxLayers];   // 1: a CTA barrier must follow this layer (see ldpc_launch)
+    uint16_t layer_chain[kMaxLayers]; // 0, or 0x8000 | d << 6 | orientation << 5 | first link of the pair (see ldpc_launch)
     uint32_t links[kMaxLinks];
 };
 static_assert(sizeof(LdpcParams) <= 4096, "kernel parameter block must stay within the 4 KB constant window");
@@ -117,10 +119,13 @@ __device__ __forceinline__ uint32_t sat_add_u8x2(uint32_t u, uint32_t d) { retur
 //              of a, so the two smallest are found on a itself and the "-1, >= 0, <= 32" is applied after)
 //   ex_k = min of a over the other links        (prefix/suffix minima; == "a_k == min0 ? min1 : min0")
 //   mag_k = clamp(ex_k - 1, 0, 32);  msg_k' = sign * mag_k limited to [-32, 31];  link' = sat8(t + msg_k')
-template <int CNT, bool EXACT, bool BOTH>
+// MID  : second pass of a "middle" row of a chained layer (see chain_walk): link `xlink` takes its t from `xsaved`
+//        (computed by row_pre from the LLR as it was before the layer) and its LLR is not written back, because
+//        the row that shares the bit comes later in row order and writes the final value.
+template <int CNT, bool EXACT, bool BOTH, bool MID = false>
 __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const int (&voff)[CNT], int cnt,
                                            uint32_t (&msg)[(CNT + 3) / 2], uint32_t& pown, uint32_t& psec,
-                                           bool has2, int lf) {
+                                           bool has2, int lf, int xlink = -1, uint32_t xsaved = 0) {
     constexpr int D = CNT + 2;
     constexpr uint32_t kNeutralT = 0x00FF00FFu;   // t = +127: never the minimum that matters, sign +
     uint32_t tu[D], a[D], mo_keep[D];
@@ -144,6 +149,7 @@ __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const i
         uint32_t m = (c & 1) ? unpack23(mw) : unpack01(mw);
         uint32_t x = sat_add_u8x2(u, __vsub2(0u, m));        // t = sat8(link - msg), offset binary
         if (!(EXACT && c < CNT) && c != CNT) x = present ? x : kNeutralT;
+        if (MID && c < CNT && c == xlink) x = xsaved;
         tu[c] = x;
         a[c] = __vabsdiffu4(x, 0x00800080u);                 // |t| in [0, 128]
         sx ^= x;
@@ -172,7 +178,9 @@ __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const i
         uint32_t mo = __viaddmin_s16x2(om ^ neg, neg & 0x00010001u, kP31);  // +-om, limited to [-32, 31]
         uint32_t pk = pack1(sat_add_u8x2(x, mo));                    // link' = sat8(t + msg')
         if (c < CNT) {
-            if (BOTH)
+            if (MID && c == xlink) {
+                // not written: the bit's final value comes from the later row that shares it
+            } else if (BOTH)
                 *reinterpret_cast<uint16_t*>(vbytes + voff[c]) = (uint16_t)pk;
             else
                 vbytes[voff[c] + lf] = (uint8_t)(pk >> (8 * lf));
@@ -197,6 +205,81 @@ __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const i
     }
 }
 
+// ---- chained layers ---------------------------------------------------------------------------
+// A layer in which exactly two links X, Y fall into the same 360-bit group makes row j and row j+d share one bit
+// (row j's X bit is row j+d's Y bit, d = (shift_Y - shift_X) mod 360 taken <= 180).  The reference visits rows in
+// order, so row j+d must see that bit as row j left it.  Instead of one CTA barrier per dependency level (up to
+// 360/d of them, with one warp working and eleven waiting), such a layer runs in three phases:
+//   P  rows j < d ("sources", nobody before them) are updated normally; rows with a successor (j >= d, j+d < 360:
+//      "middle") reduce everything that does not depend on the late Y input to four words (row_pre);
+//   C  thread c < d walks its chain c+d, c+2d, ...: from the predecessor's X output it gets the row's Y input
+//      and from that, in ten instructions, the row's X output, which it leaves in the LLR array;
+//   F  every row j >= d is updated normally -- its Y bit now holds what the row before it in the chain produced
+//      -- except that a middle row takes the t of its X link from phase P and leaves the X bit alone (MID).
+// Rows j+d >= 360 ("sinks") have two late inputs (Y from the chain, X from source j+d-360) and no successor.
+template <int CNT, bool EXACT>
+__device__ __forceinline__ uint32_t row_pre(const uint8_t* __restrict__ vbytes, const int (&voff)[CNT], int cnt,
+                                            const uint32_t (&msg)[(CNT + 3) / 2], uint32_t pown, uint32_t psec, bool has2,
+                                            int X, int Y, uint4* slot) {
+    constexpr int D = CNT + 2;
+    constexpr uint32_t kNeutralT = 0x00FF00FFu;
+    uint32_t sx = ((D + 1) & 1) ? 0x00800080u : 0u;   // as in row_update, without the t of X and Y
+    uint32_t rmin = 0x00FF00FFu;                       // min |t| over the links other than X and Y
+    uint32_t tux = 0, my = 0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const uint32_t mw = msg[c >> 1];
+        const uint32_t m = (c & 1) ? unpack23(mw) : unpack01(mw);
+        if (c < CNT && c == Y) {
+            my = m;
+            continue;
+        }
+        uint32_t u;
+        bool present = true;
+        if (c < CNT) {
+            present = EXACT || c < cnt;
+            u = present ? unpack_u01(*reinterpret_cast<const uint16_t*>(vbytes + voff[c])) : 0u;
+        } else if (c == CNT) {
+            u = unpack_u01(pown);
+        } else {
+            present = has2;
+            u = unpack_u01(psec);
+        }
+        uint32_t x = sat_add_u8x2(u, __vsub2(0u, m));
+        if (!(EXACT && c < CNT) && c != CNT) x = present ? x : kNeutralT;
+        if (c < CNT && c == X) {
+            tux = x;
+            continue;
+        }
+        sx ^= x;
+        rmin = __vminu2(rmin, __vabsdiffu4(x, 0x00800080u));
+    }
+    *slot = make_uint4(rmin, sx, tux, my);
+    return tux;
+}
+
+// phase C for the chain that starts at source row c0; lkx = link word of X ((group << 16) | shift)
+__device__ __forceinline__ void chain_walk(uint8_t* __restrict__ vbytes, const uint4* __restrict__ scratch, uint32_t lkx,
+                                           int c0, int d) {
+    uint8_t* grp = vbytes + 2 * 360 * (int)(lkx >> 16);
+    int m = c0 - (int)(lkx & 0xFFFFu);                 // X bit of row c0 inside the group
+    m += (m < 0) ? 360 : 0;
+    uint32_t u = unpack_u01(*reinterpret_cast<const uint16_t*>(grp + 2 * m));   // what the source left there
+    for (int r = c0 + d; r + d < 360; r += d) {
+        m += d;                                        // X bit of row r
+        m -= (m >= 360) ? 360 : 0;
+        const uint4 sc = scratch[r];                   // rmin, sx, t_X, old message of Y
+        const uint32_t ty = sat_add_u8x2(u, __vsub2(0u, sc.w));
+        const uint32_t ex = __vminu2(sc.x, __vabsdiffu4(ty, 0x00800080u));       // min |t| over all links but X
+        const uint32_t om = __viaddmin_s16x2_relu(ex, kM1, kP32);
+        const uint32_t neg = prmt(sc.y ^ ty, 0, 0xAA88);                         // sign over all links but X
+        const uint32_t mo = __viaddmin_s16x2(om ^ neg, neg & 0x00010001u, kP31);
+        const uint32_t pk = pack1(sat_add_u8x2(sc.z, mo));
+        *reinterpret_cast<uint16_t*>(grp + 2 * m) = (uint16_t)pk;
+        u = unpack_u01(pk);
+    }
+}
+
 // Streamed input: block until the copy engine has delivered `need` frames.  Kept out of line so that the decoder
 // around the call site compiles to the same code as without it.
 __device__ __noinline__ void wait_arrived(const unsigned int* arrived_ptr, unsigned need) {
@@ -210,7 +293,9 @@ __device__ __noinline__ void wait_arrived(const unsigned int* arrived_ptr, unsig
 
 // STREAMED: the input copy is still running when the kernel starts (LdpcArgs::arrived); a separate instantiation,
 // because the waiting code in the pair hand-out measurably perturbs the scheduling of the resident-input kernel.
-template <int CNT, bool UNIFORM, bool STREAMED>
+// CHAINS: chained layers run in three phases (see chain_walk) instead of level by level; again its own
+// instantiation, chosen per code where it measurably pays (ldpc_chains_pay_off).
+template <int CNT, bool UNIFORM, bool STREAMED, bool CHAINS>
 __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kernel(const __grid_constant__ LdpcParams p) {
     constexpr int SLOTS = CNT + 2;
     constexpr int MW = (SLOTS + 1) / 2;     // message words per row in registers
@@ -230,6 +315,8 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
     uint16_t* wpty = reinterpret_cast<uint16_t*>(p.workspace + (size_t)blockIdx.x * p.ws_stride +
                                                  (size_t)q * SG * 360 * 16);
     const int npairs = (p.nframes + 1) >> 1;
+    // four words per row handed from phase P to phase C of a chained layer, behind the bit planes
+    uint4* chain_scratch = reinterpret_cast<uint4*>(smem_raw + ((((size_t)K * 2 + (size_t)2 * (p.ngroups + q) * kBitWords * 4) + 15) & ~(size_t)15));
 
     // zero the bit planes once: bytes 45..51 of every 360-bit group are never written and must read as 0
     for (int x = tid; x < 2 * (p.ngroups + q) * kBitWords; x += kLdpcThreads) HD[x] = 0;
@@ -417,6 +504,29 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
                 }
                 uint8_t* vbytes = reinterpret_cast<uint8_t*>(vdata);
                 const int lf = (live == 2) ? 1 : 0;
+                const int chain = CHAINS ? p.layer_chain[i] : 0;
+                if (CHAINS && chain && live == 3) {   // chained layer, both frames iterating: phases P, C, F (see chain_walk)
+                    const int d = (chain >> 6) & 0x1FF, first = chain & 31;
+                    const int X = first + ((chain >> 5) & 1), Y = first + 1 - ((chain >> 5) & 1);
+                    const bool source = j < d, middle = !source && j + d < 360;
+                    uint32_t xsaved = 0;
+                    if (active) {
+                        if (source)
+                            row_update<CNT, UNIFORM, true>(vbytes, voff, cnt, msg, pown, psec, has2, 0);
+                        else if (middle)
+                            xsaved = row_pre<CNT, UNIFORM>(vbytes, voff, cnt, msg, pown, psec, has2, X, Y, &chain_scratch[j]);
+                    }
+                    __syncthreads();
+                    if (source) chain_walk(vbytes, chain_scratch, p.links[loff + X], j, d);
+                    __syncthreads();
+                    if (active && !source) {
+                        if (middle)
+                            row_update<CNT, UNIFORM, true, true>(vbytes, voff, cnt, msg, pown, psec, has2, 0, X, xsaved);
+                        else
+                            row_update<CNT, UNIFORM, true>(vbytes, voff, cnt, msg, pown, psec, has2, 0);
+                    }
+                    __syncthreads();
+                } else
                 for (int lvl = 0; lvl < nlev; ++lvl) {
                     if (active && mylev == lvl) {
                         if (live == 3)
@@ -488,17 +598,22 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
 using KernelFn = void (*)(const LdpcParams);
 struct Variant {
     int cnt;
-    KernelFn uniform[2];   // every layer has exactly cnt data links per row (all normal codes, 5 short ones)
-    KernelFn ragged[2];    // layers with fewer links exist (short 1/4, 1/2, 3/4, 4/5, 5/6); [1] = streamed input
+    // [streamed input][chained layers]
+    KernelFn uniform[2][2];   // every layer has exactly cnt data links per row (all normal codes, 5 short ones)
+    KernelFn ragged[2][2];    // layers with fewer links exist (short 1/4, 1/2, 3/4, 4/5, 5/6)
 };
-#define VU(c) {c, {ldpc_pair_kernel<c, true, false>, ldpc_pair_kernel<c, true, true>}, {nullptr, nullptr}}
-#define VB(c) {c, {ldpc_pair_kernel<c, true, false>, ldpc_pair_kernel<c, true, true>}, {ldpc_pair_kernel<c, false, false>, ldpc_pair_kernel<c, false, true>}}
-#define VR(c) {c, {nullptr, nullptr}, {ldpc_pair_kernel<c, false, false>, ldpc_pair_kernel<c, false, true>}}
+#define K4(c, u) {{ldpc_pair_kernel<c, u, false, false>, ldpc_pair_kernel<c, u, false, true>}, {ldpc_pair_kernel<c, u, true, false>, ldpc_pair_kernel<c, u, true, true>}}
+#define N4 {{nullptr, nullptr}, {nullptr, nullptr}}
+#define VU(c) {c, K4(c, true), N4}
+#define VB(c) {c, K4(c, true), K4(c, false)}
+#define VR(c) {c, N4, K4(c, false)}
 // one instantiation per distinct "max data links per row" among the 21 codes
 const Variant kVariants[] = {VB(2), VU(3), VU(4), VB(5), VU(8), VU(9), VR(11), VU(12), VU(16), VR(17), VU(20), VU(25), VU(28)};
 #undef VU
 #undef VB
 #undef VR
+#undef K4
+#undef N4
 
 const Variant* pick(int max_cnt) {
     for (const Variant& v : kVariants)
@@ -506,11 +621,12 @@ const Variant* pick(int max_cnt) {
     return nullptr;
 }
 KernelFn pick_fn(const LdpcDev& c, bool streamed = false) {
+    const int ch = c.chains ? 1 : 0;
     const Variant* v = pick(c.max_cnt);
     if (!v) return nullptr;
     bool uniform = v->cnt == c.max_cnt;
     for (int i = 0; i < c.q && uniform; ++i) uniform = (c.layer_off[i + 1] - c.layer_off[i]) == v->cnt;
-    return (uniform && v->uniform[0]) ? v->uniform[streamed] : v->ragged[streamed];
+    return (uniform && v->uniform[0][0]) ? v->uniform[streamed][ch] : v->ragged[streamed][ch];
 }
 
 }  // namespace
@@ -528,6 +644,19 @@ static cudaError_t allow_max_smem(KernelFn fn) {
     e = cudaFuncGetAttributes(&fa, fn);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
+// Codes for which the three-phase treatment of chained layers beats the level-by-level one.  Measured with
+// tools/modcod_sweep.py (2048 normal / 8192 short frames, fixed noise) against the same kernel without it:
+// n1/3 -9 %, n2/3 -6 %, n3/4 -12 %, n8/9 -18 %, s2/5 -12 %, s2/3 -8 %, s3/4 -9 % time; within +-2 % or slower
+// for the others (few chained layers, or their other conflicted layers dominate; for n1/2 the co-resident CTA
+// already hides the level steps at full load).  Index = code table order B1..B11, C1..C10.
+bool ldpc_chains_pay_off(int code_index) {
+    static const bool table[21] = {false, true,  false, false, false, true,  true,  false, false, true,  false,
+                                   false, false, true,  false, false, true,  true,  false, false, false};
+    static const int force = [] { const char* e = getenv("DVBS2FEC_LDPC_CHAINS"); return e ? atoi(e) : -1; }();
+    if (force >= 0) return force != 0;
+    return code_index >= 0 && code_index < 21 && table[code_index];
 }
 
 int ldpc_slot_groups(int max_cnt) {
@@ -593,6 +722,32 @@ int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
         if (!any) p.layer_sync[0] = 1;        // pty[q-1][j-1]: stored in layer 0, prefetched (by thread j-1) in layer q-2
     }
     for (int i = 0; i < nlinks; ++i) p.links[i] = c.links[i];
+    {   // Chained layers: exactly one 360-bit group is hit by exactly two links of the layer (they are adjacent,
+        // links are sorted by group).  X is the one whose bit the EARLIER row of a pair owns: row j's X bit is row
+        // j+d's Y bit with d = (shift_Y - shift_X) mod 360 <= 180.
+        const bool enabled = true;
+        for (int i = 0; i < c.q; ++i) {
+            p.layer_chain[i] = 0;
+            if (!enabled || !c.chains || c.layer_nlev[i] <= 1) continue;
+            int pairs = 0, first = -1;
+            bool simple = true;
+            for (int k = c.layer_off[i]; k + 1 < c.layer_off[i + 1]; ++k) {
+                if ((c.links[k] >> 16) != (c.links[k + 1] >> 16)) continue;
+                if (k + 2 < c.layer_off[i + 1] && (c.links[k + 2] >> 16) == (c.links[k] >> 16)) simple = false;   // three in a group
+                ++pairs;
+                first = k - c.layer_off[i];
+            }
+            if (!simple || pairs != 1 || first > 30) continue;
+            const int s0 = (int)(c.links[c.layer_off[i] + first] & 0xFFFFu), s1 = (int)(c.links[c.layer_off[i] + first + 1] & 0xFFFFu);
+            int d = ((s1 - s0) % 360 + 360) % 360, orient = 0;   // X = first, Y = first + 1
+            if (d > 180) {
+                d = 360 - d;
+                orient = 1;                                      // X = first + 1, Y = first
+            }
+            if (d == 0) continue;
+            p.layer_chain[i] = (uint16_t)(0x8000u | (unsigned)d << 6 | (unsigned)orient << 5 | (unsigned)first);
+        }
+    }
     size_t smem = ldpc_smem_bytes(c);
     cudaError_t e = allow_max_smem(fn);
     if (e != cudaSuccess) return (int)e;

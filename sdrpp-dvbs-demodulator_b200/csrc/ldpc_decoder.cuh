@@ -34,6 +34,7 @@ struct LdpcDev {
     int ngroups;   // K / 360
     int max_cnt;   // data links per row (max over layers)
     int sg;        // uint4 message slot-groups per row in the workspace: ldpc_slot_groups(max_cnt)
+    bool chains;   // run chained layers in three phases (ldpc_chains_pay_off(code index))
     // HOST pointers: copied into the kernel parameter block (constant bank) at every launch
     const uint32_t* links;       // per layer: (group << 16) | shift
     const int* layer_off;        // [q + 1]
@@ -43,6 +44,7 @@ struct LdpcDev {
 };
 // slot groups of the kernel instantiation that serves max_cnt data links (0 = unsupported)
 int ldpc_slot_groups(int max_cnt);
+bool ldpc_chains_pay_off(int code_index);   // measured per code, see ldpc_decoder.cu
 
 struct LdpcArgs {
     LdpcDev code;
@@ -62,7 +64,9 @@ inline size_t ldpc_workspace_bytes(const LdpcDev& c) {
     return (((size_t)c.q * c.sg * 360 * 16 + (size_t)c.R * 2) + 255) & ~(size_t)255;
 }
 inline size_t ldpc_smem_bytes(const LdpcDev& c) {
-    return (size_t)c.K * 2 + (size_t)2 * (c.ngroups + c.q) * kBitWords * 4 + 64;
+    // LLR pairs, bit planes, slack; with chained layers also their 360 x 16 B hand-over words
+    const size_t base = (size_t)c.K * 2 + (size_t)2 * (c.ngroups + c.q) * kBitWords * 4;
+    return c.chains ? ((base + 15) & ~(size_t)15) + 360 * 16 + 64 : base + 64;
 }
 
 // returns cudaError_t as int; picks the kernel instantiation for code.max_cnt

@@ -38,7 +38,9 @@ def main():
             a, sigma2 = 1 / np.sqrt(2.0), 1.0 / (2.0 * 10 ** (esn0 / 10.0))
             cw = torch.from_numpy(codes).to(dev)
             y = (1.0 - 2.0 * cw[torch.arange(n, device=dev) % 8].float()) * a
-            y += torch.randn(y.shape, device=dev) * float(np.sqrt(sigma2))
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(1000 + 100 * int(short) + rate)   # same noise every run: results are comparable
+            y += torch.randn(y.shape, device=dev, generator=gen) * float(np.sqrt(sigma2))
             llr = torch.clamp(torch.round(4.0 * 2.0 * a * y / sigma2), -127, 127).to(torch.int8)
             d_bb = torch.empty((n, info["kbch"] // 8), dtype=torch.uint8, device=dev)
             d_res = torch.empty((n, 16), dtype=torch.uint8, device=dev)
