@@ -378,7 +378,7 @@ def main():
         "latency_ms_per_batch": latency,
         "clocks": sampler.summary(),
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU reference is timed beside the N=1 run only
         codes_h = codes
         procs = os.cpu_count() or 1
         pool_host = make_pool_numpy(codes_h, 16 * min(procs, 64), args.esn0, 2)
