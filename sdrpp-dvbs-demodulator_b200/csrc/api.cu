@@ -156,6 +156,7 @@ struct dvbs2fec_handle {
     bool profiling = false;
     struct Span { int kind; cudaEvent_t a, b; };
     std::vector<Span> spans;
+    std::mutex span_mu;
     // host copies of the layer tables referenced by LdpcDev (host pointers)
     std::vector<uint32_t> h_links;
     // ---- queue
@@ -296,16 +297,19 @@ int enqueue_chain(dvbs2fec_handle* h, DevCtx& d, Slot& s, const float* d_sym, co
                   uint8_t* d_bb, dvbs2fec_result* d_res, cudaStream_t st, int* launches, uint64_t tag_base = 0,
                   const unsigned int* arrived = nullptr) {
     const int8_t* llr = d_llr;
+    // kernel-time spans for dvbs2fec_kernel_times; several threads (one per GPU, the queue worker) may add some
+    dvbs2fec_handle::Span cur{0, nullptr, nullptr};
     auto mark = [&](int kind, bool begin) {
         if (!h->profiling) return;
         if (begin) {
-            dvbs2fec_handle::Span sp{kind, nullptr, nullptr};
-            cudaEventCreate(&sp.a);
-            cudaEventCreate(&sp.b);
-            cudaEventRecord(sp.a, st);
-            h->spans.push_back(sp);
+            cur = dvbs2fec_handle::Span{kind, nullptr, nullptr};
+            cudaEventCreate(&cur.a);
+            cudaEventCreate(&cur.b);
+            cudaEventRecord(cur.a, st);
         } else {
-            cudaEventRecord(h->spans.back().b, st);
+            cudaEventRecord(cur.b, st);
+            std::lock_guard<std::mutex> lk(h->span_mu);
+            h->spans.push_back(cur);
         }
     };
     if (d_sym) {
@@ -682,6 +686,10 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
         for (int i = 0; i < 2; ++i) { d.gf_log[i].release(); d.gf_exp[i].release(); }
         d.prbs.release();
     }
+    for (auto& sp : h->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
     for (auto& S : h->stages) {
         S.in.release();
         S.bb.release();
@@ -730,7 +738,12 @@ int dvbs2fec_kernel_times(dvbs2fec_handle* h, float* demap_ms, float* ldpc_ms, f
     if (!h) return fail(DVBS2FEC_EINVAL, "handle is NULL");
     float acc[3] = {0, 0, 0};
     int n = 0;
-    for (auto& sp : h->spans) {
+    std::vector<dvbs2fec_handle::Span> spans;
+    {
+        std::lock_guard<std::mutex> lk(h->span_mu);
+        spans.swap(h->spans);
+    }
+    for (auto& sp : spans) {
         float ms = 0;
         CU(cudaEventSynchronize(sp.b));
         CU(cudaEventElapsedTime(&ms, sp.a, sp.b));
@@ -739,7 +752,6 @@ int dvbs2fec_kernel_times(dvbs2fec_handle* h, float* demap_ms, float* ldpc_ms, f
         cudaEventDestroy(sp.b);
         ++n;
     }
-    h->spans.clear();
     if (demap_ms) *demap_ms = acc[0];
     if (ldpc_ms) *ldpc_ms = acc[1];
     if (bch_ms) *bch_ms = acc[2];
