@@ -678,7 +678,7 @@ int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
     const LdpcDev& c = a.code;
     const Variant* v = pick(c.max_cnt);
     KernelFn fn = pick_fn(c, a.arrived != nullptr);
-    if (!v || !fn || c.q > kMaxLayers) return (int)cudaErrorInvalidValue;
+    if (!v || !fn || c.q < 1 || c.q > kMaxLayers) return (int)cudaErrorInvalidValue;
     LdpcParams p;
     p.N = c.N; p.K = c.K; p.R = c.R; p.q = c.q; p.ngroups = c.ngroups;
     p.sg = (v->cnt + 2 + 7) / 8;
@@ -718,7 +718,7 @@ int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
                 std::fill(seen.begin(), seen.end(), 0);
             }
         }
-        p.layer_sync[c.q - 1] = 1;            // end of the pass
+        if (c.q > 0) p.layer_sync[c.q - 1] = 1;   // end of the pass
         if (!any) p.layer_sync[0] = 1;        // pty[q-1][j-1]: stored in layer 0, prefetched (by thread j-1) in layer q-2
     }
     for (int i = 0; i < nlinks; ++i) p.links[i] = c.links[i];
