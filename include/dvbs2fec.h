@@ -61,6 +61,13 @@ const char* dvbs2fec_last_error(void);
  * decoded and kept for collect() first.  max_trials <= 0 keeps the configured default. */
 int dvbs2fec_set_modcod(dvbs2fec_handle* h, int modcod, int shortframes, int pilots, int max_trials);
 
+/* PL descrambling inside the demapper (S2Scrambling, dvbs2/codings/s2_scrambling.h:12-45; the reference runs it in
+ * S2PLLBlock::process, dvbs2_pll.cpp:37-44, on the phase-corrected symbol): codenum = Gold code number
+ * 0..262141 -> PLFRAME inputs are taken as still PL-scrambled and every symbol after the 90 header symbols
+ * (pilots count) is turned back by Rn * 90 degrees before demapping; codenum < 0 (default) -> inputs are already
+ * descrambled.  Survives dvbs2fec_set_modcod; frames already queued are decoded with the previous setting. */
+int dvbs2fec_set_pl_scrambling(dvbs2fec_handle* h, int codenum);
+
 /* getKBCH (module_dvbs2_demod.h:80), BBFrameLDPC::dataSize (codings/bbframe_ldpc.h:48), frame length. Bits. */
 int dvbs2fec_kbch(const dvbs2fec_handle* h);
 int dvbs2fec_kldpc(const dvbs2fec_handle* h);

@@ -42,6 +42,11 @@ int orc_bch_encode(int shortframe, int rate, uint8_t* frame);
 int orc_descramble(int shortframe, int rate, uint8_t* frame);
 /* BBFrameTSParser::check_crc8(bbf, 80) (dvbs2/bbframe_ts_parser.cpp:66-80): 0 = BBHEADER valid */
 unsigned orc_bbheader_crc8(const uint8_t* bbframe);
+/* ---- upstream row 8(f)-2: S2Scrambling (dvbs2/codings/s2_scrambling.cpp), see oracle_demap.c ---- */
+void orc_pl_rn(int codenum, uint8_t* rn /* 131072 */);
+void orc_pl_descramble(const uint8_t* rn, const float* in, int nsym, float* out);
+void orc_pl_scramble(const uint8_t* rn, const float* in, int nsym, float* out);
+
 /* ---- downstream row 8(f)-1: BBFrameTSParser (dvbs2/bbframe_ts_parser.cpp:31-43,100-392), see oracle_ts.c ---- */
 typedef struct orc_ts_parser orc_ts_parser;
 orc_ts_parser* orc_ts_create(int kbch_bits);                     /* setFrameSize */

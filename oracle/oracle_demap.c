@@ -233,3 +233,48 @@ int orc_bb_to_soft(const orc_constellation* c, int constellation, int shortframe
     free(soft);
     return n;
 }
+
+/* ---- PL descrambling (row 8(f)-2, the part without a loop state) ---------------------------------
+ * S2Scrambling (dvbs2/codings/s2_scrambling.cpp:9-28, s2_scrambling.h:16-25): Gold sequence n from two 18-bit
+ * LFSRs, x (taps 0,7; state 1 advanced n times) and y (taps 0,5,7,10; all ones); Rn[i] = z(i) + 2 z(i+131072),
+ * z = lsb(x) ^ lsb(y).  descramble (s2_scrambling.cpp:37-58) turns a symbol by -Rn * 90 degrees; S2PLLBlock
+ * restarts the sequence at every frame and advances it on every symbol after the 90 header symbols, pilots
+ * included (dvbs2_pll.cpp:37-44). */
+static uint32_t pl_step_x(uint32_t x) { return ((((x >> 7) ^ x) & 1u) << 18 | x) >> 1; }
+static uint32_t pl_step_y(uint32_t y) { return ((((y >> 10) ^ (y >> 7) ^ (y >> 5) ^ y) & 1u) << 18 | y) >> 1; }
+void orc_pl_rn(int codenum, uint8_t* rn /* 131072 */)
+{
+    uint32_t x = 1, y = 0x3FFFF;
+    for (int i = 0; i < codenum; ++i) x = pl_step_x(x);
+    for (int half = 0; half < 2; ++half)
+        for (int i = 0; i < 131072; ++i) {
+            unsigned z = (x ^ y) & 1u;
+            rn[i] = half ? (uint8_t)(rn[i] | (z << 1)) : (uint8_t)z;
+            x = pl_step_x(x);
+            y = pl_step_y(y);
+        }
+}
+void orc_pl_descramble(const uint8_t* rn, const float* in, int nsym, float* out)
+{
+    for (int i = 0; i < nsym; ++i) {
+        float re = in[2 * i], im = in[2 * i + 1];
+        switch (rn[i]) {
+        case 3: out[2 * i] = -im; out[2 * i + 1] = re; break;
+        case 2: out[2 * i] = -re; out[2 * i + 1] = -im; break;
+        case 1: out[2 * i] = im; out[2 * i + 1] = -re; break;
+        default: out[2 * i] = re; out[2 * i + 1] = im; break;
+        }
+    }
+}
+void orc_pl_scramble(const uint8_t* rn, const float* in, int nsym, float* out) /* s2_scrambling.cpp:60-81 */
+{
+    for (int i = 0; i < nsym; ++i) {
+        float re = in[2 * i], im = in[2 * i + 1];
+        switch (rn[i]) {
+        case 3: out[2 * i] = im; out[2 * i + 1] = -re; break;
+        case 2: out[2 * i] = -re; out[2 * i + 1] = -im; break;
+        case 1: out[2 * i] = -im; out[2 * i + 1] = re; break;
+        default: out[2 * i] = re; out[2 * i + 1] = im; break;
+        }
+    }
+}

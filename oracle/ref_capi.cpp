@@ -21,6 +21,7 @@
 #include "dvbs2/codings/xdsopl-ldpc-pabr/dvb_s2_tables.hh"
 #include "common/dsp/demod/constellation.h"
 #include "dvbs2/bbframe_ts_parser.h"
+#include "dvbs2/codings/s2_scrambling.h"
 
 using namespace dsp::dvbs2;
 
@@ -251,6 +252,22 @@ void ref_ts_stats(void* h, int* fields, int* last_bb_cnt, int* last_bb_proc, int
     *last_bb_cnt = p->last_bb_cnt;
     *last_bb_proc = p->last_bb_proc;
     *last_gse_crc_err = p->last_gse_crc_err;
+}
+
+// ---- S2Scrambling (dvbs2/codings/s2_scrambling.h:12-45): reset(), then one (de)scramble per symbol ----
+void ref_pl_descramble(int codenum, const float* in, int nsym, float* out, int scramble) {
+    static std::map<int, std::unique_ptr<dsp::dvbs2::S2Scrambling>> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    auto& sc = cache[codenum];
+    if (!sc) sc.reset(new dsp::dvbs2::S2Scrambling(codenum));
+    sc->reset();
+    for (int i = 0; i < nsym; ++i) {
+        dsp::complex_t v{in[2 * i], in[2 * i + 1]};
+        dsp::complex_t r = scramble ? sc->scramble(v) : sc->descramble(v);
+        out[2 * i] = r.re;
+        out[2 * i + 1] = r.im;
+    }
 }
 
 } // extern "C"

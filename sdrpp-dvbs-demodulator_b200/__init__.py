@@ -99,6 +99,7 @@ def lib():
     L.dvbs2fec_encode_fecframe.argtypes = [C.c_int, C.c_int, vp, vp]
     L.dvbs2fec_modulate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     L.dvbs2fec_modcod_info.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip, ip]
+    L.dvbs2fec_set_pl_scrambling.argtypes = [vp, C.c_int]
     L.dvbs2fec_ts_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.dvbs2fec_ts_destroy.argtypes = [vp]
     L.dvbs2fec_ts_destroy.restype = None
@@ -184,6 +185,10 @@ class DVBS2Decoder:
         return self
 
     set_modcod = setDemodParams
+
+    def set_pl_scrambling(self, codenum):
+        """S2Scrambling(codenum) inside the demapper; -1: PLFRAMEs arrive descrambled (default)"""
+        _check(lib().dvbs2fec_set_pl_scrambling(self._h, codenum))
 
     def getKBCH(self):
         return self.kbch

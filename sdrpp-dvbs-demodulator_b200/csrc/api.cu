@@ -133,6 +133,7 @@ struct DevCtx {
     std::map<int, BchTabDev> bch;           // key m*100+t
     DevBuf<uint16_t> gf_log[2], gf_exp[2];  // [0]: m=14, [1]: m=16
     DevBuf<uint8_t> prbs;
+    DevBuf<uint8_t> pl_rn;                  // PL scrambling sequence of the handle's Gold code (empty: off)
     std::map<int, DevBuf<uint32_t>> luts;   // key modcod constellation/gamma: modcod number
     // current configuration
     LdpcDev ldpc{};
@@ -152,6 +153,7 @@ struct dvbs2fec_handle {
     int hard_stride = 0;
     int plsyms = 0;
     int last_launches = 0;
+    int pl_codenum = -1;                // Gold code of the PL descrambler in K1, -1 = inputs are descrambled
     bool configured = false;
     bool profiling = false;
     struct Span { int kind; cudaEvent_t a, b; };
@@ -258,6 +260,7 @@ int setup_device_tables(dvbs2fec_handle* h, DevCtx& d) {
         D.pts[2 * i + 1] = i < ch.states ? ch.im[i] : 0.f;
     }
     D.lut = nullptr;
+    D.rn = h->pl_codenum >= 0 ? d.pl_rn.p : nullptr;
     if (mc.constellation != APSK32) {
         int key = (mc.constellation == APSK16) ? mc.modcod : (int)mc.constellation;  // 16APSK: one LUT per gamma
         DevBuf<uint32_t>& lut = d.luts[key];
@@ -685,6 +688,7 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
         for (auto& kv : d.luts) kv.second.release();
         for (int i = 0; i < 2; ++i) { d.gf_log[i].release(); d.gf_exp[i].release(); }
         d.prbs.release();
+        d.pl_rn.release();
     }
     for (auto& sp : h->spans) {
         cudaEventDestroy(sp.a);
@@ -720,6 +724,25 @@ int dvbs2fec_set_modcod(dvbs2fec_handle* h, int modcod, int shortframes, int pil
         if (rc) return rc;
     }
     h->configured = true;
+    return 0;
+}
+
+int dvbs2fec_set_pl_scrambling(dvbs2fec_handle* h, int codenum) {
+    if (!h) return fail(DVBS2FEC_EINVAL, "handle is NULL");
+    if (codenum > 262141) return fail(DVBS2FEC_EINVAL, "Gold code number %d outside 0..262141", codenum);
+    drain_queue(h);
+    h->pl_codenum = codenum < 0 ? -1 : codenum;
+    for (auto& dp : h->devs) {
+        DevCtx& d = *dp;
+        CU(cudaSetDevice(d.device));
+        if (codenum >= 0) {
+            // longest PLFRAME payload: 64800 / 2 symbols + 22 pilot blocks of 36
+            std::vector<uint8_t> rn = pl_scrambling_rn(codenum, 32400 + 36 * 22 + 8);
+            CU(d.pl_rn.reserve(rn.size()));
+            CU(cudaMemcpy(d.pl_rn.p, rn.data(), rn.size(), cudaMemcpyHostToDevice));
+        }
+        d.demap.rn = codenum >= 0 ? d.pl_rn.p : nullptr;
+    }
     return 0;
 }
 

@@ -29,7 +29,14 @@ __global__ void __launch_bounds__(256) demap_kernel(const __grid_constant__ Dema
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= d.nsym) return;
     const int raw = 90 + s + (d.pilots ? 36 * (s / 1440) : 0);
-    const float2 v = __ldg(&in[(size_t)frame * d.plframe_syms + raw]);
+    float2 v = __ldg(&in[(size_t)frame * d.plframe_syms + raw]);
+    if (d.rn) {   // exact: quarter turns only swap and negate
+        const int r = __ldg(&d.rn[raw - 90]);
+        const float2 u = v;
+        if (r == 1) v = make_float2(u.y, -u.x);
+        else if (r == 2) v = make_float2(-u.x, -u.y);
+        else if (r == 3) v = make_float2(-u.y, u.x);
+    }
     int8_t* o = out + (size_t)frame * d.N;
     int8_t b[5];
     if (d.constellation != 3) {

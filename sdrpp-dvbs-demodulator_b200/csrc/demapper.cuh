@@ -9,6 +9,8 @@
 //     formula with CUDA's libm, so LLRs may differ by an LSB from glibc's (tolerance in the tests);
 //   * pilots: the intended rule (skip 36 symbols after every 16 slots); the reference's own loop
 //     mis-handles pilots-on (SURVEY.md note N2), so exact parity is defined for pilots off.
+//   * optional PL descrambling (S2Scrambling::descramble, dvbs2/codings/s2_scrambling.cpp:37-58, as driven by
+//     S2PLLBlock::process, dvbs2_pll.cpp:37-44): the symbol is turned by -Rn[position] * 90 degrees first;
 // One thread per payload symbol; LLR bytes land directly at their deinterleaved position.
 #pragma once
 #include <cstdint>
@@ -25,6 +27,7 @@ struct DemapDev {
     int pilots;
     int plframe_syms;      // stride of one PLFRAME in complex samples (header + payload + pilots)
     const uint32_t* lut;   // [256*256] packed soft bits (null for 32APSK)
+    const uint8_t* rn;     // PL scrambling sequence per position after the header (incl. pilots), or null: input is descrambled
     float amp, prescale, sca;
     float pts[64];         // 32APSK points (re, im), demapper scale
 };

@@ -103,6 +103,29 @@ void bch_encode(const BchHost& code, uint8_t* frame, int kbch) {
         if (reg[np - 1 - i]) par[i >> 3] |= 0x80 >> (i & 7);
 }
 
+std::vector<uint8_t> pl_scrambling_rn(int codenum, int count) {
+    // x: 1 + x^7 + x^18 from state 0...01, advanced by the code number; y: 1 + y^5 + y^7 + y^10 + y^18 from all
+    // ones; z(i) = x(i) ^ y(i); Rn(i) = z(i) + 2 z(i + 2^17).  Two copies of the generator 2^17 steps apart.
+    auto step_x = [](uint32_t v) { return ((((v >> 7) ^ v) & 1u) << 18 | v) >> 1; };
+    auto step_y = [](uint32_t v) { return ((((v >> 10) ^ (v >> 7) ^ (v >> 5) ^ v) & 1u) << 18 | v) >> 1; };
+    uint32_t x0 = 1, y0 = 0x3FFFF;
+    for (int i = 0; i < codenum; ++i) x0 = step_x(x0);
+    uint32_t x1 = x0, y1 = y0;
+    for (int i = 0; i < 131072; ++i) {
+        x1 = step_x(x1);
+        y1 = step_y(y1);
+    }
+    std::vector<uint8_t> rn((size_t)count);
+    for (int i = 0; i < count; ++i) {
+        rn[i] = (uint8_t)(((x0 ^ y0) & 1u) | (((x1 ^ y1) & 1u) << 1));
+        x0 = step_x(x0);
+        y0 = step_y(y0);
+        x1 = step_x(x1);
+        y1 = step_y(y1);
+    }
+    return rn;
+}
+
 const std::vector<uint8_t>& bb_prbs() {
     static std::vector<uint8_t> seq;
     static std::once_flag once;

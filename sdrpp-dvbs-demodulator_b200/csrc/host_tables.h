@@ -37,6 +37,10 @@ void bch_encode(const BchHost& code, uint8_t* frame, int kbch);
 // reference: bbframe_descramble.cpp:122-136), MSB first, 64800 bits.
 const std::vector<uint8_t>& bb_prbs();
 
+// PL scrambling sequence Rn (EN 302 307 5.5.4; reference: S2Scrambling, dvbs2/codings/s2_scrambling.cpp:9-28) for
+// Gold code `codenum`: 2 bits per symbol position after the PLHEADER, `count` positions.
+std::vector<uint8_t> pl_scrambling_rn(int codenum, int count);
+
 // LDPC systematic encode (EN 302 307 5.3.2): data_bits[K] 0/1 -> code_bits[N] 0/1
 void ldpc_encode_bits(int code, const uint8_t* data_bits, uint8_t* code_bits);
 

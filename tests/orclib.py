@@ -63,6 +63,9 @@ def oracle():
         lib.orc_mod.argtypes = [C.c_void_p, C.c_int, _f32p]
         lib.orc_deinterleave.argtypes = [C.c_int, C.c_int, C.c_int, _i8p, _i8p]
         lib.orc_bb_to_soft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p, _i8p]
+        lib.orc_pl_rn.argtypes = [C.c_int, _u8p]
+        lib.orc_pl_descramble.argtypes = [_u8p, _f32p, C.c_int, _f32p]
+        lib.orc_pl_scramble.argtypes = [_u8p, _f32p, C.c_int, _f32p]
         lib.orc_ts_create.argtypes = [C.c_int]
         lib.orc_ts_create.restype = C.c_void_p
         lib.orc_ts_destroy.argtypes = [C.c_void_p]
@@ -99,6 +102,8 @@ def ref():
         lib.ref_demap.argtypes = [C.c_int, C.c_float, C.c_float, _f32p, C.c_int, _i8p]
         lib.ref_demap_calc.argtypes = [C.c_int, C.c_float, C.c_float, _f32p, C.c_int, _i8p]
         lib.ref_mod.argtypes = [C.c_int, C.c_float, C.c_float, _u8p, C.c_int, _f32p]
+        if hasattr(lib, "ref_pl_descramble"):
+            lib.ref_pl_descramble.argtypes = [C.c_int, _f32p, C.c_int, _f32p, C.c_int]
         if hasattr(lib, "ref_ts_create"):
             lib.ref_ts_create.argtypes = [C.c_int]
             lib.ref_ts_create.restype = C.c_void_p

@@ -361,3 +361,39 @@ def test_bbheader_crc_flag(dec):
     want = np.array([o.orc_bbheader_crc8(np.ascontiguousarray(payload[i])) != 0 for i in range(n)])
     assert (~want[0::2]).all()
     assert np.array_equal((res["flags"] & pkg.FLAG_BBHEADER_CRC_FAIL) != 0, want)
+
+
+@pytest.mark.parametrize("modcod,short,pilots,codenum", [(4, True, False, 0), (13, True, True, 5), (18, True, False, 262141),
+                                                         (4, False, True, 1)])
+def test_pl_descrambling_inside_the_demapper(dec, modcod, short, pilots, codenum):
+    """PL-scrambled symbols (S2Scrambling::scramble restated by the oracle) with dvbs2fec_set_pl_scrambling(codenum)
+    give exactly the LLRs -- and BBFRAMEs -- of the descrambled symbols with the descrambler off"""
+    o = orclib.oracle()
+    try:
+        dec.set_pl_scrambling(-1)
+        dec.setDemodParams(modcod, short, pilots)
+        rng = np.random.default_rng(modcod + codenum % 97)
+        n = 3
+        payload = rng.integers(0, 256, (n, dec.kbch // 8), dtype=np.uint8)
+        pl = np.stack([pkg.modulate(modcod, short, pilots, pkg.encode_fecframe(modcod, short, payload[i])) for i in range(n)])
+        clean = pl.view(np.float32).reshape(n, -1) + rng.normal(0, 0.05, (n, dec.plframe_symbols * 2)).astype(np.float32)
+        rn = np.zeros(131072, np.uint8)
+        o.orc_pl_rn(codenum, rn)
+        scr = clean.copy()
+        nsym = dec.plframe_symbols - 90
+        for i in range(n):
+            out = np.zeros(2 * nsym, np.float32)
+            o.orc_pl_scramble(rn, np.ascontiguousarray(clean[i, 180:]), nsym, out)
+            scr[i, 180:] = out
+        want_llr = dec.bb_to_soft(clean)
+        want_bb, want_res = dec.decode_plframes(clean)
+        dec.set_pl_scrambling(codenum)
+        assert np.array_equal(dec.bb_to_soft(scr), want_llr)
+        bb, res = dec.decode_plframes(scr)
+        assert np.array_equal(bb, want_bb) and np.array_equal(res["ldpc_iters"], want_res["ldpc_iters"])
+        assert np.array_equal(bb, payload)
+        assert not np.array_equal(dec.bb_to_soft(clean), want_llr)   # the descrambler really is on
+    finally:
+        dec.set_pl_scrambling(-1)
+    with pytest.raises(pkg.DVBS2FecError):
+        dec.set_pl_scrambling(262142)

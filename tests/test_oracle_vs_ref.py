@@ -205,3 +205,27 @@ def test_deinterleaver_matches_reference(const, short, rate):
     o.orc_deinterleave(const, short, rate, x, a)
     r.ref_deinterleave(const, short, rate, x.copy(), b)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("codenum", [0, 1, 2, 17, 4096, 131071, 262141])
+def test_pl_scrambling_matches_reference(codenum):
+    """S2Scrambling: Rn sequence (through descramble of probe symbols), descramble and scramble, 33282 symbols =
+    the longest PLFRAME payload with pilots"""
+    o, r = orclib.oracle(), orclib.ref()
+    if not hasattr(r, "ref_pl_descramble"):
+        pytest.skip("oracle/_ref was built without s2_scrambling.cpp")
+    rn = np.zeros(131072, np.uint8)
+    o.orc_pl_rn(codenum, rn)
+    n = 33282
+    x = np.random.default_rng(codenum).normal(0, 1, 2 * n).astype(np.float32)
+    a, b = np.zeros_like(x), np.zeros_like(x)
+    o.orc_pl_descramble(rn, x, n, a)
+    r.ref_pl_descramble(codenum, x, n, b, 0)
+    assert np.array_equal(a, b)
+    o.orc_pl_scramble(rn, x, n, a)
+    r.ref_pl_descramble(codenum, x, n, b, 1)
+    assert np.array_equal(a, b)
+    back = np.zeros_like(x)
+    o.orc_pl_descramble(rn, a, n, back)
+    assert np.array_equal(back, x)
+    assert set(np.unique(rn[:n]).tolist()) == {0, 1, 2, 3}
