@@ -50,7 +50,8 @@ def ncu_traffic_per_frame():
         try:
             d = json.load(open(f))
             if "dram_traffic_bytes_per_frame" in d:
-                best = (d["dram_traffic_bytes_per_frame"], os.path.basename(f))
+                best = (d["dram_traffic_bytes_per_frame"], os.path.basename(f),
+                        {k: d.get(k) for k in ("alu_pipe_pct", "issue_slots_busy_pct", "fma_pipe_pct", "lsu_pipe_pct", "dram_throughput_pct")})
         except Exception:
             pass
     return best
@@ -374,7 +375,8 @@ def main():
                      "traffic_unit": "GB per launch (ncu dram__bytes_read+write, %s)" % (tr[1] if tr else "n/a"), "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": HBM_BYTES_PER_FRAME,
                      "edge_updates_per_s": args.pool / (ldpc_avg_ms * 1e-3) * links * mean_it,
-                     "note": "the kernel is bound by integer issue and shared memory, not HBM (DESIGN.md); HBM fraction is reported as the contract asks"},
+                     "note": "the kernel is bound by integer issue and shared memory, not HBM (DESIGN.md); HBM fraction is reported as the contract asks",
+                     "on_chip_utilisation_pct_ncu": (tr[2] if tr else None)},
         "latency_ms_per_batch": latency,
         "clocks": sampler.summary(),
     }
