@@ -156,3 +156,32 @@ def gse_scenario(rng):
     f3 = [b[1], c[1], broken[0]]
     f4 = [c[2], b[2], broken[1], gse_complete(pdus[5], 0x0800, label=lab)]
     return [f0, f1, f2, f3, f4]
+
+
+def random_ts_scenario(rng, kbch, nframes=80):
+    """random mix: data-field sizes from tiny to full, occasional header faults, non-TS frames, a restart of the
+    packet stream at an arbitrary byte (as after a MODCOD change)"""
+    kb = kbch // 8
+    max_df = kb - 10
+    choices = [max_df, max_df, max_df, max_df - 1, max(8, max_df // 2), 188, 187, 189, 376, 100, 16]
+    choices = [c for c in choices if 8 <= c <= max_df]
+    dfl = [int(x) for x in rng.choice(choices, nframes)]
+    pk = ts_packets(sum(dfl) // 188 + 4, rng)
+    frames, _ = ts_bbframes(kbch, pk, dfl_bytes=dfl, first_byte=int(rng.integers(0, 188)), pad=int(rng.integers(0, 256)))
+    f = frames.copy()
+    for i in rng.choice(len(f), max(1, len(f) // 12), replace=False):
+        kind = int(rng.integers(0, 6))
+        if kind == 0:
+            f[i, int(rng.integers(0, 10))] ^= 1 << int(rng.integers(0, 8))          # CRC-8 failure
+        elif kind == 1:
+            f[i, :10] = bbheader(0xF0, 1504, kbch - 80 + 8 * int(rng.integers(1, 5)), 0x47, 0)   # DFL too long
+        elif kind == 2:
+            d = 8 * int(rng.integers(2, 40))
+            f[i, :10] = bbheader(0xF0, 1504, d, 0x47, d - 8 + 8 * int(rng.integers(0, 3)))       # SYNCD >= DFL-8
+        elif kind == 3:
+            f[i, :10] = bbheader(0xF0, 1504, 8 * int(rng.integers(2, 40)) + int(rng.integers(1, 8)), 0x47, 0)   # DFL % 8
+        elif kind == 4:
+            f[i, :10] = bbheader(int(rng.choice([0x30, 0xB0, 0x74])), 0, 8 * int(rng.integers(2, 40)), 0, 0)    # not TS
+        else:
+            f[i, :10] = bbheader(0xF0, 1504, 8 * int(rng.integers(1, 3)), 0x47, 0)     # DFL of 8 or 16 bits
+    return f

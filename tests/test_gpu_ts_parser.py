@@ -132,3 +132,15 @@ def test_full_size_stream_round_trip_on_device_buffers():
     assert len(out) == (nframes * df - 1) // 188
     assert np.array_equal(out, pk[:len(out)])
     g.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_ts_random_streams_match_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    kbch = [3072, 7032, 14232, 32208][seed % 4]
+    f = bbstream.random_ts_scenario(rng, kbch, nframes=80 if seed % 3 else 700)   # 700: several frames per plan thread
+    cuts = sorted(set(int(x) for x in rng.integers(0, len(f) + 1, 6)) | {0, len(f)})
+    compare(kbch, [f[a:b] for a, b in zip(cuts[:-1], cuts[1:])])
+    if seed % 4 == 0:   # output room that runs out somewhere in the middle: the sequential fallback
+        total = len(OrcParser(kbch).work(f))
+        compare(kbch, [f], cap=max(189, total // 2))

@@ -166,3 +166,13 @@ def test_gse_matches_reference_parser():
         frames = bbstream.gse_bbframes(kbch, bbstream.gse_scenario(rng))
         _compare(kbch, [frames[:2], frames[2:]])
         _compare(kbch, [frames])
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(12))
+def test_ts_random_streams_match_reference_parser(seed):
+    rng = np.random.default_rng(1000 + seed)
+    kbch = [3072, 7032, 14232, 32208][seed % 4]
+    f = bbstream.random_ts_scenario(rng, kbch)
+    cuts = sorted(set(int(x) for x in rng.integers(0, len(f) + 1, 6)) | {0, len(f)})
+    _compare(kbch, [f[a:b] for a, b in zip(cuts[:-1], cuts[1:])])
