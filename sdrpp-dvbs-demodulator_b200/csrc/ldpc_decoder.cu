@@ -648,12 +648,13 @@ static cudaError_t allow_max_smem(KernelFn fn) {
 
 // Codes for which the three-phase treatment of chained layers beats the level-by-level one.  Measured with
 // tools/modcod_sweep.py (2048 normal / 8192 short frames, fixed noise) against the same kernel without it:
-// n1/3 -9 %, n2/3 -6 %, n3/4 -12 %, n8/9 -18 %, s2/5 -12 %, s2/3 -8 %, s3/4 -9 % time; within +-2 % or slower
-// for the others (few chained layers, or their other conflicted layers dominate; for n1/2 the co-resident CTA
-// already hides the level steps at full load).  Index = code table order B1..B11, C1..C10.
+// n1/3 -9 %, n2/3 -3..-6 %, n3/4 -12 %, n8/9 -20 %, s2/5 -12 %, s1/2 -3 %, s2/3 -9 %, s3/4 -10 % time; within +-2 %
+// or slower for the others (few layers with many levels, or their other conflicted layers dominate; for n1/2
+// the co-resident CTA already hides the level steps at full load).  Only layers with at least eight levels are
+// chained: the three phases cost about two extra passes over the rows.  Index = code table order B1..B11, C1..C10.
 bool ldpc_chains_pay_off(int code_index) {
     static const bool table[21] = {false, true,  false, false, false, true,  true,  false, false, true,  false,
-                                   false, false, true,  false, false, true,  true,  false, false, false};
+                                   false, false, true,  true,  false, true,  true,  false, false, false};
     static const int force = [] { const char* e = getenv("DVBS2FEC_LDPC_CHAINS"); return e ? atoi(e) : -1; }();
     if (force >= 0) return force != 0;
     return code_index >= 0 && code_index < 21 && table[code_index];
@@ -726,9 +727,11 @@ int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
         // links are sorted by group).  X is the one whose bit the EARLIER row of a pair owns: row j's X bit is row
         // j+d's Y bit with d = (shift_Y - shift_X) mod 360 <= 180.
         const bool enabled = true;
+        // a chained layer costs about two extra passes over the rows; below this many levels the level loop is cheaper
+        static const int min_levels = [] { const char* e = getenv("DVBS2FEC_CHAIN_MINLEV"); return e ? atoi(e) : 8; }();
         for (int i = 0; i < c.q; ++i) {
             p.layer_chain[i] = 0;
-            if (!enabled || !c.chains || c.layer_nlev[i] <= 1) continue;
+            if (!enabled || !c.chains || (int)c.layer_nlev[i] < min_levels) continue;
             int pairs = 0, first = -1;
             bool simple = true;
             for (int k = c.layer_off[i]; k + 1 < c.layer_off[i + 1]; ++k) {

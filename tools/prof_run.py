@@ -18,7 +18,11 @@ def main():
     ap.add_argument("--pool", type=int, default=592)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--esn0", type=float, default=2.2)
+    ap.add_argument("--modcod", type=int, default=None, help="MODCOD instead of the bench workload's")
+    ap.add_argument("--short", action="store_true")
     args = ap.parse_args()
+    if args.modcod is not None:
+        bench.MODCOD, bench.SHORT = args.modcod, args.short
     import torch
     pkg = importlib.import_module("sdrpp-dvbs-demodulator_b200")
     dev = torch.device("cuda", 0)
