@@ -64,8 +64,51 @@ def main():
             print(row, flush=True)
             dec.close()
             del llr, y
-    json.dump({"note": "device-resident LLR input, QPSK MODCOD of each rate, Es/N0 = threshold estimate + margin", "rows": rows},
-              open(args.out, "w"), indent=1)
+    # symbols path: PLFRAME symbols in pinned host memory -> K1 demap + K2 + K3 ->
+    # BBFRAMEs in pinned host memory through dvbs2fec_decode_plframes; symbols at the mapper's amplitude with
+    # light noise (the reference's LUT scale only converges well above threshold, SURVEY note N7)
+    import ctypes as C
+    import time
+    L = pkg.lib()
+    sym_rows = []
+    for modcod, name in ((4, "QPSK 1/2"), (12, "8PSK 3/5"), (18, "16APSK 2/3"), (28, "32APSK 9/10")):
+        info = pkg.modcod_info(modcod, False)
+        n = 1024
+        dec = pkg.DVBS2Decoder(devices=[0], max_batch=512, max_trials=25)
+        dec.setDemodParams(modcod, False, False, 25)
+        base = np.stack([pkg.modulate(modcod, False, False, pkg.encode_fecframe(modcod, False, rng.integers(0, 256, info["kbch"] // 8, dtype=np.uint8)))
+                         for _ in range(4)]).view(np.float32).reshape(4, -1)
+        sym_bytes = base.shape[1] * 4
+        h_in, h_bb, h_res = L.dvbs2fec_alloc_pinned(n * sym_bytes), L.dvbs2fec_alloc_pinned(n * (info["kbch"] // 8)), L.dvbs2fec_alloc_pinned(n * 16)
+        buf = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_float)), shape=(n, base.shape[1]))
+        nrng = np.random.default_rng(modcod)
+        for i in range(n):
+            buf[i] = base[i % 4] + nrng.normal(0, 0.04, base.shape[1]).astype(np.float32)
+        dec.set_profiling(True)
+        for _ in range(2):
+            assert L.dvbs2fec_decode_plframes(dec._h, h_in, n, h_bb, h_res) == 0
+        dec.kernel_times()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            assert L.dvbs2fec_decode_plframes(dec._h, h_in, n, h_bb, h_res) == 0
+        dt = (time.perf_counter() - t0) / reps
+        demap_ms, ldpc_ms, bch_ms, _ = dec.kernel_times()
+        res = np.ctypeslib.as_array(C.cast(h_res, C.POINTER(C.c_uint8)), shape=(n * 16,)).view(pkg.RESULT_DTYPE).reshape(-1)
+        it = res["ldpc_iters"].astype(np.int32)
+        row = {"modcod": modcod, "name": name + " normal", "frames": n, "e2e_ms": round(dt * 1e3, 3),
+               "e2e_frames_per_s": round(n / dt), "e2e_gbit_s": round(n * info["kbch"] / dt / 1e9, 2),
+               "h2d_gb_s": round(n * sym_bytes / dt / 1e9, 1),
+               "demap_ms": round(demap_ms / reps, 3), "ldpc_ms": round(ldpc_ms / reps, 3), "bch_ms": round(bch_ms / reps, 3),
+               "mean_iters": round(float(np.where(it < 0, 25, it).mean()), 2), "fer": round(float((res["bch_corr"] < 0).mean()), 4)}
+        sym_rows.append(row)
+        print(row, flush=True)
+        dec.close()
+        for ptr in (h_in, h_bb, h_res):
+            L.dvbs2fec_free_pinned(ptr)
+    json.dump({"note": "rows: device-resident LLR input, QPSK MODCOD of each rate, Es/N0 = threshold estimate + margin, fixed noise; "
+                       "plframes: symbols in pinned host memory through dvbs2fec_decode_plframes (H2D of 8 B per symbol inside the time)",
+               "rows": rows, "plframes": sym_rows}, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":
