@@ -118,6 +118,18 @@ int dvbs2fec_collect(dvbs2fec_handle* h, uint8_t* bb_out, dvbs2fec_result* resul
 /* force the partial batch through (DVBS2Demod::reset / tempStop) */
 int dvbs2fec_flush(dvbs2fec_handle* h);
 
+/* Fused TS output (SURVEY 8(f) rank 1 behind the queue): with on != 0 the worker runs the BBFRAME -> TS kernels on
+ * the device right behind the BCH kernel -- BBFrameTSParser::work (dvbs2/bbframe_ts_parser.cpp:100-212) as
+ * main.cpp:538 applies it to the decoded frames, parser state running through all frames of the handle in
+ * submission order and starting over at dvbs2fec_set_modcod like setFrameSize.  Single-device handles only.
+ * Frames are then taken with dvbs2fec_collect_ts instead of dvbs2fec_collect. */
+int dvbs2fec_set_ts_output(dvbs2fec_handle* h, int on);
+/* TS packets of finished frames, in order: returns the bytes written (a multiple of 188, <= cap).  results
+ * (optional, room for max_results records) receives one record per frame, batch by batch, together with the last
+ * packets of the batch; *nresults the count. */
+int dvbs2fec_collect_ts(dvbs2fec_handle* h, uint8_t* ts_out, int cap, dvbs2fec_result* results, int max_results,
+                        int* nresults, int timeout_us);
+
 /* pinned host memory for zero-staging transfers (optional) */
 void* dvbs2fec_alloc_pinned(size_t bytes);
 void dvbs2fec_free_pinned(void* p);

@@ -100,6 +100,8 @@ def lib():
     L.dvbs2fec_modulate.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     L.dvbs2fec_modcod_info.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, ip, ip]
     L.dvbs2fec_set_pl_scrambling.argtypes = [vp, C.c_int]
+    L.dvbs2fec_set_ts_output.argtypes = [vp, C.c_int]
+    L.dvbs2fec_collect_ts.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip, C.c_int]
     L.dvbs2fec_ts_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.dvbs2fec_ts_destroy.argtypes = [vp]
     L.dvbs2fec_ts_destroy.restype = None
@@ -274,6 +276,17 @@ class DVBS2Decoder:
 
     def flush(self):
         _check(lib().dvbs2fec_flush(self._h))
+
+    def set_ts_output(self, on=True):
+        """queue delivers TS packets (BBFrameTSParser::work fused behind the decoder) instead of BBFRAMEs"""
+        _check(lib().dvbs2fec_set_ts_output(self._h, int(on)))
+
+    def collect_ts(self, cap=65536 * 10, max_results=4096, timeout_us=0):
+        ts = np.zeros(max(cap, 1), np.uint8)
+        res = np.zeros(max_results, RESULT_DTYPE)
+        nres = C.c_int()
+        n = _check(lib().dvbs2fec_collect_ts(self._h, _ptr(ts), cap, _ptr(res), max_results, C.byref(nres), timeout_us))
+        return ts[:n], res[:nres.value]
 
 
 class _StageObject:

@@ -97,6 +97,8 @@ struct Slot {
     cudaStream_t copy = nullptr;
     cudaEvent_t armed = nullptr;
     DevBuf<unsigned int> arrived;        // frames delivered so far (device word the kernel polls)
+    DevBuf<uint8_t> ts;                  // fused TS output of the batch (queue, TS mode)
+    DevBuf<int> ts_len;
     PinBuf<unsigned int> arrived_vals;   // the values the copy engine writes there, one per piece
     DevBuf<int8_t> llr;
     DevBuf<float> sym;
@@ -144,6 +146,18 @@ struct DevCtx {
 
 }  // namespace
 
+// BBFRAME -> TS parser object (row 8(f)-1); entry points further down
+struct dvbs2fec_ts_parser {
+    int device = 0;
+    int kb = 0, max_dfl = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf<TsState> state;
+    DevBuf<TsPlan> plan;
+    DevBuf<uint32_t> meta;
+    DevBuf<uint8_t> bb, out;
+    PinBuf<int> h_produced;
+};
+
 struct dvbs2fec_handle {
     dvbs2fec_config cfg{};
     std::vector<std::unique_ptr<DevCtx>> devs;
@@ -154,6 +168,10 @@ struct dvbs2fec_handle {
     int plsyms = 0;
     int last_launches = 0;
     int pl_codenum = -1;                // Gold code of the PL descrambler in K1, -1 = inputs are descrambled
+    // fused TS output of the queue (dvbs2fec_set_ts_output): K6 runs behind K3 on the device
+    bool ts_output = false;
+    dvbs2fec_ts_parser* ts = nullptr;
+    cudaEvent_t ts_done = nullptr;      // K6 of the previous batch has finished (its state carries over)
     bool configured = false;
     bool profiling = false;
     struct Span { int kind; cudaEvent_t a, b; };
@@ -172,8 +190,11 @@ struct dvbs2fec_handle {
     // directions, collect copies BBFRAMEs out of finished stages.  Stages cycle free -> fill -> ready -> inflight
     // -> done -> free; at most kSlots are in flight, so the copy-in of one overlaps the kernels of the other.
     struct Stage {
-        PinBuf<uint8_t> in, bb;
+        PinBuf<uint8_t> in, bb, ts;
         PinBuf<dvbs2fec_result> res;
+        PinBuf<int> ts_len;
+        int ts_taken = 0;
+        bool has_ts = false;
         std::vector<uint64_t> tags;
         int n = 0, taken = 0, cap = 0;
         bool is_sym = false;
@@ -539,6 +560,32 @@ void launch_stage(dvbs2fec_handle* h, int st, int which) {
             if (rc) return rc;
             CU(cudaMemcpyAsync(S.bb.p + (size_t)f0 * S.kb, s.bb.p, (size_t)m * S.kb, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaMemcpyAsync(S.res.p + f0, s.res.p, (size_t)m * sizeof(dvbs2fec_result), cudaMemcpyDeviceToHost, s.stream));
+            if (S.has_ts) {   // K6 behind K3, on the BBFRAMEs still in device memory; its state runs through all batches
+                dvbs2fec_ts_parser* tp = h->ts;
+                const int ts_cap = (int)((size_t)m * S.kb + 188);
+                CU(s.ts.reserve((size_t)h->cfg.max_batch * S.kb + 188));
+                CU(s.ts_len.reserve(1));
+                CU(tp->plan.reserve(std::max(m, h->cfg.max_batch)));
+                CU(tp->meta.reserve(std::max(m, h->cfg.max_batch)));
+                CU(cudaStreamWaitEvent(s.stream, h->ts_done, 0));
+                TsArgs ta{};
+                ta.bb = s.bb.p;
+                ta.cnt = m;
+                ta.kb = tp->kb;
+                ta.max_dfl = tp->max_dfl;
+                ta.out = s.ts.p;
+                ta.out_cap = ts_cap;
+                ta.state = tp->state.p;
+                ta.plan = tp->plan.p;
+                ta.meta = tp->meta.p;
+                ta.produced_out = s.ts_len.p;
+                int e = ts_launch(ta, s.stream);
+                if (e) return fail(DVBS2FEC_ECUDA, "ts launch: %s", cudaGetErrorString((cudaError_t)e));
+                h->last_launches += 3;
+                CU(cudaEventRecord(h->ts_done, s.stream));
+                CU(cudaMemcpyAsync(S.ts.p, s.ts.p, (size_t)ts_cap, cudaMemcpyDeviceToHost, s.stream));
+                CU(cudaMemcpyAsync(S.ts_len.p, s.ts_len.p, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            }
             CU(cudaLaunchHostFunc(s.stream, stage_share_done, &h->share_done[st]));
             return 0;
         };
@@ -678,6 +725,7 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
             s.bb.release(); s.res.release(); s.workspace.release(); s.counter.release();
             s.h_in.release(); s.h_bb.release(); s.h_res.release();
             s.arrived.release(); s.arrived_vals.release();
+            s.ts.release(); s.ts_len.release();
             if (s.done) cudaEventDestroy(s.done);
             if (s.armed) cudaEventDestroy(s.armed);
             if (s.copy) cudaStreamDestroy(s.copy);
@@ -690,6 +738,8 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
         d.prbs.release();
         d.pl_rn.release();
     }
+    if (h->ts) dvbs2fec_ts_destroy(h->ts);
+    if (h->ts_done) cudaEventDestroy(h->ts_done);
     for (auto& sp : h->spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
@@ -698,6 +748,8 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
         S.in.release();
         S.bb.release();
         S.res.release();
+        S.ts.release();
+        S.ts_len.release();
     }
     delete h;
 }
@@ -724,6 +776,10 @@ int dvbs2fec_set_modcod(dvbs2fec_handle* h, int modcod, int shortframes, int pil
         if (rc) return rc;
     }
     h->configured = true;
+    if (h->ts_output) {   // like setFrameSize on a MODCOD change: the parser starts over
+        int rc = dvbs2fec_ts_set_frame_size(h->ts, h->code->kbch);
+        if (rc) return rc;
+    }
     return 0;
 }
 
@@ -915,6 +971,8 @@ static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym
         S.in_bytes = is_sym ? (size_t)h->plsyms * 8 : (size_t)h->code->N;
         S.is_sym = is_sym;
         S.n = S.taken = 0;
+        S.ts_taken = 0;
+        S.has_ts = h->ts_output;
         S.tags.clear();
         // page-locked allocation may synchronise with the device, and stream callbacks take h->mu: allocate unlocked
         // (submit_mu keeps other producers out, and a stage that is on no list is invisible to worker and collect)
@@ -923,6 +981,8 @@ static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym
         if (e == cudaSuccess) e = S.in.reserve((size_t)S.cap * S.in_bytes);
         if (e == cudaSuccess) e = S.bb.reserve((size_t)S.cap * S.kb);
         if (e == cudaSuccess) e = S.res.reserve(S.cap);
+        if (e == cudaSuccess && S.has_ts) e = S.ts.reserve((size_t)S.cap * S.kb + 188);
+        if (e == cudaSuccess && S.has_ts) e = S.ts_len.reserve(1);
         lk.lock();
         if (e != cudaSuccess) {
             h->st_free.push_back(idx);
@@ -997,6 +1057,66 @@ int dvbs2fec_collect(dvbs2fec_handle* h, uint8_t* bb_out, dvbs2fec_result* resul
     return n;
 }
 
+int dvbs2fec_set_ts_output(dvbs2fec_handle* h, int on) {
+    if (!h) return fail(DVBS2FEC_EINVAL, "handle is NULL");
+    if (on && h->devs.size() != 1)
+        return fail(DVBS2FEC_EINVAL, "TS output needs a single-device handle (the parser state runs through the frames in order)");
+    drain_queue(h);
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (!h->st_done.empty()) return fail(DVBS2FEC_EAGAIN, "collect the finished frames before switching the output kind");
+    }
+    if (on && !h->ts) {
+        int rc = dvbs2fec_ts_create(h->devs[0]->device, &h->ts);
+        if (rc) return rc;
+        CU(cudaEventCreateWithFlags(&h->ts_done, cudaEventDisableTiming));
+    }
+    h->ts_output = on != 0;
+    if (on && h->configured) return dvbs2fec_ts_set_frame_size(h->ts, h->code->kbch);
+    return 0;
+}
+
+int dvbs2fec_collect_ts(dvbs2fec_handle* h, uint8_t* ts_out, int cap, dvbs2fec_result* results, int max_results,
+                        int* nresults, int timeout_us) {
+    if (nresults) *nresults = 0;
+    if (!h || !h->configured || !ts_out || cap < 0 || max_results < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    std::unique_lock<std::mutex> lk(h->mu);
+    if (h->st_done.empty() && timeout_us != 0) {
+        auto ready = [h] { return !h->st_done.empty(); };
+        if (timeout_us < 0)
+            h->cv_done.wait(lk, ready);
+        else
+            h->cv_done.wait_for(lk, std::chrono::microseconds(timeout_us), ready);
+    }
+    int bytes = 0, nres = 0;
+    while (!h->st_done.empty()) {
+        dvbs2fec_handle::Stage& S = h->stages[h->st_done.front()];
+        if (!S.has_ts) return fail(DVBS2FEC_EINVAL, "frames decoded before dvbs2fec_set_ts_output: use dvbs2fec_collect");
+        if (results && max_results - nres < S.n) break;   // a batch's results go out with the end of its packets
+        const int total = S.rc ? 0 : *S.ts_len.p;
+        const int take = std::min(total - S.ts_taken, (cap - bytes) / 188 * 188);
+        memcpy(ts_out + bytes, S.ts.p + S.ts_taken, (size_t)take);
+        S.ts_taken += take;
+        bytes += take;
+        if (S.ts_taken < total) break;   // no room for the rest: next call
+        if (results)
+            for (int i = 0; i < S.n; ++i) {
+                dvbs2fec_result r = S.res.p[i];
+                r.tag = S.tags[i];
+                if (S.rc) {
+                    r.ldpc_iters = -1;
+                    r.bch_corr = -1;
+                    r.flags = DVBS2FEC_FLAG_LDPC_FAIL | DVBS2FEC_FLAG_BCH_FAIL;
+                }
+                results[nres++] = r;
+            }
+        h->st_free.push_back(h->st_done.front());
+        h->st_done.pop_front();
+    }
+    if (nresults) *nresults = nres;
+    return bytes;
+}
+
 int dvbs2fec_flush(dvbs2fec_handle* h) {
     if (!h) return fail(DVBS2FEC_EINVAL, "handle is NULL");
     drain_queue(h);
@@ -1013,17 +1133,6 @@ void dvbs2fec_free_pinned(void* p) {
 }
 
 // ---------------------------------------------------------------- BBFRAME -> TS (row 8(f)-1)
-struct dvbs2fec_ts_parser {
-    int device = 0;
-    int kb = 0, max_dfl = 0;
-    cudaStream_t stream = nullptr;
-    DevBuf<TsState> state;
-    DevBuf<TsPlan> plan;
-    DevBuf<uint32_t> meta;
-    DevBuf<uint8_t> bb, out;
-    PinBuf<int> h_produced;
-};
-
 int dvbs2fec_ts_create(int device, dvbs2fec_ts_parser** out) {
     if (!out) return fail(DVBS2FEC_EINVAL, "out is NULL");
     *out = nullptr;

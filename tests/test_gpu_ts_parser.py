@@ -144,3 +144,53 @@ def test_ts_random_streams_match_oracle(seed):
     if seed % 4 == 0:   # output room that runs out somewhere in the middle: the sequential fallback
         total = len(OrcParser(kbch).work(f))
         compare(kbch, [f], cap=max(189, total // 2))
+
+
+def _llr_of_bbframes(modcod, short, frames):
+    """BBFRAME bytes (already carrying a BBHEADER) -> clean LLRs of their FECFRAMEs"""
+    return np.stack([np.where(pkg.encode_fecframe(modcod, short, f) > 0, -40, 40).astype(np.int8) for f in frames])
+
+
+@pytest.mark.parametrize("modcod,scenario", [(1, "odd"), (4, "plain")])
+def test_queue_delivers_ts_packets_fused_behind_the_decoder(modcod, scenario):
+    """dvbs2fec_set_ts_output: BBFRAMEs never leave the device; what collect_ts returns equals BBFrameTSParser::work
+    (oracle) over the same BBFRAMEs, across many small batches (parser state carried on the device)"""
+    short = True
+    info = pkg.modcod_info(modcod, short)
+    kbch = info["kbch"]
+    rng = np.random.default_rng(31 + modcod)
+    if scenario == "odd":
+        frames = bbstream.odd_ts_scenario(rng, kbch)
+    else:
+        frames, _ = bbstream.ts_bbframes(kbch, bbstream.ts_packets(300, rng), first_byte=33)
+    want = OrcParser(kbch).work(frames)
+    llr = _llr_of_bbframes(modcod, short, frames)
+    d = pkg.DVBS2Decoder(max_batch=8, max_latency_us=300, max_trials=10)
+    try:
+        d.set_ts_output(True)
+        d.setDemodParams(modcod, short, False)
+        got, tags = [], []
+        for i in range(len(llr)):
+            while True:
+                rc = pkg.lib().dvbs2fec_submit_llr(d._h, llr[i].ctypes.data_as(C.c_void_p), i)
+                if rc != pkg.EAGAIN:
+                    break
+                ts, res = d.collect_ts(cap=188 * 7, timeout_us=100_000)       # small bites: batches split over calls
+                got.append(ts.copy()); tags += list(res["tag"])
+            assert rc == 0
+        d.flush()
+        while len(tags) < len(llr):
+            ts, res = d.collect_ts(cap=188 * 11, timeout_us=2_000_000)
+            got.append(ts.copy()); tags += list(res["tag"])
+        out = np.concatenate(got)
+        assert tags == list(range(len(llr)))
+        assert len(out) == len(want) and np.array_equal(out, want)
+        # switching the MODCOD starts the parser over (setFrameSize): a fresh oracle parser gives the same
+        d.setDemodParams(modcod, short, False)
+        for i in range(6):
+            d.submit_llr(llr[i], 100 + i)
+        d.flush()
+        ts, res = d.collect_ts(timeout_us=2_000_000)
+        assert np.array_equal(ts, OrcParser(kbch).work(frames[:6])) and len(res) == 6
+    finally:
+        d.close()
