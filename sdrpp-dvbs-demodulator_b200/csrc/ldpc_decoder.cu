@@ -138,7 +138,8 @@ __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const i
         bool present = true;
         if (c < CNT) {
             present = EXACT || c < cnt;
-            u = present ? unpack_u01(*reinterpret_cast<const uint16_t*>(vbytes + voff[c])) : 0u;
+            // (MID: the bit behind xlink is being written by the row that shares it -- not read at all here)
+            u = (present && !(MID && c == xlink)) ? unpack_u01(*reinterpret_cast<const uint16_t*>(vbytes + voff[c])) : 0u;
         } else if (c == CNT) {
             u = unpack_u01(pown);
         } else {

@@ -59,3 +59,26 @@ fr, _ = bbstream.ts_bbframes(32208, pk, first_byte=50)
 tot += len(ts.work(fr))
 print("ts bytes", tot)
 ts.close()
+# fused TS output of the queue
+dec = pkg.DVBS2Decoder(max_batch=4, max_latency_us=300, max_trials=6)
+dec.set_ts_output(True)
+dec.setDemodParams(1, True, False, 6)
+frames = bbstream.odd_ts_scenario(np.random.default_rng(7), 3072)[:24]
+n_ts, n_res = 0, 0
+for i, f in enumerate(frames):
+    llr = np.where(pkg.encode_fecframe(1, True, f) > 0, -30, 30).astype(np.int8)
+    while True:
+        try:
+            dec.submit_llr(llr, i)
+            break
+        except pkg.DVBS2FecError as e:
+            if e.code != pkg.EAGAIN:
+                raise
+            ts, res = dec.collect_ts(cap=188 * 5, timeout_us=200_000)
+            n_ts += len(ts); n_res += len(res)
+dec.flush()
+while n_res < len(frames):
+    ts, res = dec.collect_ts(timeout_us=2_000_000)
+    n_ts += len(ts); n_res += len(res)
+print("fused ts bytes", n_ts, "frames", n_res)
+dec.close()
