@@ -228,6 +228,7 @@ int setup_device_tables(dvbs2fec_handle* h, DevCtx& d) {
     L.max_cnt = c.max_cnt;
     L.sg = ldpc_slot_groups(c.max_cnt);
     L.chains = ldpc_chains_pay_off(c.index);
+    L.occ3 = ldpc_ctas_wanted3(c.index);
     if (!L.sg) return fail(DVBS2FEC_EINVAL, "no LDPC kernel for %d links per row", c.max_cnt);
     L.links = h->h_links.data();
     L.layer_off = c.layer_off.data();

@@ -296,8 +296,10 @@ __device__ __noinline__ void wait_arrived(const unsigned int* arrived_ptr, unsig
 // because the waiting code in the pair hand-out measurably perturbs the scheduling of the resident-input kernel.
 // CHAINS: chained layers run in three phases (see chain_walk) instead of level by level; again its own
 // instantiation, chosen per code where it measurably pays (ldpc_chains_pay_off).
-template <int CNT, bool UNIFORM, bool STREAMED, bool CHAINS>
-__global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kernel(const __grid_constant__ LdpcParams p) {
+// OCC: resident CTAs per SM the register allocation aims at (3 = at most 56 registers; pays for the codes whose
+// shared memory lets a third CTA in, costs the others ~10 %: ldpc_ctas_wanted).
+template <int CNT, bool UNIFORM, bool STREAMED, bool CHAINS, int OCC = (CNT <= 9 ? 2 : 1)>
+__global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_pair_kernel(const __grid_constant__ LdpcParams p) {
     constexpr int SLOTS = CNT + 2;
     constexpr int MW = (SLOTS + 1) / 2;     // message words per row in registers
     constexpr int SG = (SLOTS + 7) / 8;     // uint4 groups per row in the workspace
@@ -599,22 +601,24 @@ __global__ void __launch_bounds__(kLdpcThreads, CNT <= 9 ? 2 : 1) ldpc_pair_kern
 using KernelFn = void (*)(const LdpcParams);
 struct Variant {
     int cnt;
-    // [streamed input][chained layers]
-    KernelFn uniform[2][2];   // every layer has exactly cnt data links per row (all normal codes, 5 short ones)
-    KernelFn ragged[2][2];    // layers with fewer links exist (short 1/4, 1/2, 3/4, 4/5, 5/6)
+    // [streamed input][chained layers][third CTA per SM]
+    KernelFn uniform[2][2][2];   // every layer has exactly cnt data links per row (all normal codes, 5 short ones)
+    KernelFn ragged[2][2][2];    // layers with fewer links exist (short 1/4, 1/2, 3/4, 4/5, 5/6)
 };
-#define K4(c, u) {{ldpc_pair_kernel<c, u, false, false>, ldpc_pair_kernel<c, u, false, true>}, {ldpc_pair_kernel<c, u, true, false>, ldpc_pair_kernel<c, u, true, true>}}
-#define N4 {{nullptr, nullptr}, {nullptr, nullptr}}
-#define VU(c) {c, K4(c, true), N4}
-#define VB(c) {c, K4(c, true), K4(c, false)}
-#define VR(c) {c, N4, K4(c, false)}
+#define K2(c, u, st, ch) {ldpc_pair_kernel<c, u, st, ch>, (c <= 9) ? ldpc_pair_kernel<c, u, st, ch, (c <= 9 ? 3 : 1)> : nullptr}
+#define K8(c, u) {{K2(c, u, false, false), K2(c, u, false, true)}, {K2(c, u, true, false), K2(c, u, true, true)}}
+#define N8 {{{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
+#define VU(c) {c, K8(c, true), N8}
+#define VB(c) {c, K8(c, true), K8(c, false)}
+#define VR(c) {c, N8, K8(c, false)}
 // one instantiation per distinct "max data links per row" among the 21 codes
 const Variant kVariants[] = {VB(2), VU(3), VU(4), VB(5), VU(8), VU(9), VR(11), VU(12), VU(16), VR(17), VU(20), VU(25), VU(28)};
 #undef VU
 #undef VB
 #undef VR
-#undef K4
-#undef N4
+#undef K8
+#undef K2
+#undef N8
 
 const Variant* pick(int max_cnt) {
     for (const Variant& v : kVariants)
@@ -627,7 +631,8 @@ KernelFn pick_fn(const LdpcDev& c, bool streamed = false) {
     if (!v) return nullptr;
     bool uniform = v->cnt == c.max_cnt;
     for (int i = 0; i < c.q && uniform; ++i) uniform = (c.layer_off[i + 1] - c.layer_off[i]) == v->cnt;
-    return (uniform && v->uniform[0][0]) ? v->uniform[streamed][ch] : v->ragged[streamed][ch];
+    const int oc = (c.occ3 && v->cnt <= 9) ? 1 : 0;
+    return (uniform && v->uniform[0][0][0]) ? v->uniform[streamed][ch][oc] : v->ragged[streamed][ch][oc];
 }
 
 }  // namespace
@@ -657,6 +662,18 @@ bool ldpc_chains_pay_off(int code_index) {
     static const bool table[21] = {false, true,  false, false, false, true,  true,  false, false, true,  false,
                                    false, false, true,  true,  false, true,  true,  false, false, false};
     static const int force = [] { const char* e = getenv("DVBS2FEC_LDPC_CHAINS"); return e ? atoi(e) : -1; }();
+    if (force >= 0) return force != 0;
+    return code_index >= 0 && code_index < 21 && table[code_index];
+}
+
+// Codes that run faster with the register allocation squeezed to 56 so that three CTAs share an SM (their shared
+// memory allows it): measured with tools/modcod_sweep.py, n1/4 -11 %, n1/3 -13 %, n2/5 -2 %, s1/4 -6 %, s1/3 -9 %,
+// s2/5 -10 %, s1/2 -5 %, s3/5 -7 %, s2/3 -10 % time; n1/2, n3/5, n2/3 cannot hold three (shared memory) and lose
+// 3-11 % to the tighter allocation.  Index = code table order B1..B11, C1..C10.
+bool ldpc_ctas_wanted3(int code_index) {
+    static const bool table[21] = {true,  true,  true,  false, false, false, false, false, false, false, false,
+                                   true,  true,  true,  true,  true,  true,  false, false, false, false};
+    static const int force = [] { const char* e = getenv("DVBS2FEC_LDPC_OCC3"); return e ? atoi(e) : -1; }();
     if (force >= 0) return force != 0;
     return code_index >= 0 && code_index < 21 && table[code_index];
 }

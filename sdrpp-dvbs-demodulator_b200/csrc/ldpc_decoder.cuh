@@ -35,6 +35,7 @@ struct LdpcDev {
     int max_cnt;   // data links per row (max over layers)
     int sg;        // uint4 message slot-groups per row in the workspace: ldpc_slot_groups(max_cnt)
     bool chains;   // run chained layers in three phases (ldpc_chains_pay_off(code index))
+    bool occ3;     // kernel variant compiled for three CTAs per SM (ldpc_ctas_wanted3(code index))
     // HOST pointers: copied into the kernel parameter block (constant bank) at every launch
     const uint32_t* links;       // per layer: (group << 16) | shift
     const int* layer_off;        // [q + 1]
@@ -45,6 +46,7 @@ struct LdpcDev {
 // slot groups of the kernel instantiation that serves max_cnt data links (0 = unsupported)
 int ldpc_slot_groups(int max_cnt);
 bool ldpc_chains_pay_off(int code_index);   // measured per code, see ldpc_decoder.cu
+bool ldpc_ctas_wanted3(int code_index);     // likewise
 
 struct LdpcArgs {
     LdpcDev code;
