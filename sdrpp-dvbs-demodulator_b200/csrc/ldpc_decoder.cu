@@ -296,8 +296,8 @@ __device__ __noinline__ void wait_arrived(const unsigned int* arrived_ptr, unsig
 // because the waiting code in the pair hand-out measurably perturbs the scheduling of the resident-input kernel.
 // CHAINS: chained layers run in three phases (see chain_walk) instead of level by level; again its own
 // instantiation, chosen per code where it measurably pays (ldpc_chains_pay_off).
-// OCC: resident CTAs per SM the register allocation aims at (3 = at most 56 registers; pays for the codes whose
-// shared memory lets a third CTA in, costs the others ~10 %: ldpc_ctas_wanted).
+// OCC: resident CTAs per SM the register allocation aims at (one more than the default pays for the codes whose
+// shared memory lets the extra CTA in, and costs the others: ldpc_ctas_wanted3).
 template <int CNT, bool UNIFORM, bool STREAMED, bool CHAINS, int OCC = (CNT <= 9 ? 2 : 1)>
 __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_pair_kernel(const __grid_constant__ LdpcParams p) {
     constexpr int SLOTS = CNT + 2;
@@ -605,7 +605,7 @@ struct Variant {
     KernelFn uniform[2][2][2];   // every layer has exactly cnt data links per row (all normal codes, 5 short ones)
     KernelFn ragged[2][2][2];    // layers with fewer links exist (short 1/4, 1/2, 3/4, 4/5, 5/6)
 };
-#define K2(c, u, st, ch) {ldpc_pair_kernel<c, u, st, ch>, (c <= 9) ? ldpc_pair_kernel<c, u, st, ch, (c <= 9 ? 3 : 1)> : nullptr}
+#define K2(c, u, st, ch) {ldpc_pair_kernel<c, u, st, ch>, ldpc_pair_kernel<c, u, st, ch, (c <= 9 ? 3 : 2)>}
 #define K8(c, u) {{K2(c, u, false, false), K2(c, u, false, true)}, {K2(c, u, true, false), K2(c, u, true, true)}}
 #define N8 {{{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}}
 #define VU(c) {c, K8(c, true), N8}
@@ -631,7 +631,7 @@ KernelFn pick_fn(const LdpcDev& c, bool streamed = false) {
     if (!v) return nullptr;
     bool uniform = v->cnt == c.max_cnt;
     for (int i = 0; i < c.q && uniform; ++i) uniform = (c.layer_off[i + 1] - c.layer_off[i]) == v->cnt;
-    const int oc = (c.occ3 && v->cnt <= 9) ? 1 : 0;
+    const int oc = c.occ3 ? 1 : 0;
     return (uniform && v->uniform[0][0][0]) ? v->uniform[streamed][ch][oc] : v->ragged[streamed][ch][oc];
 }
 
@@ -666,13 +666,15 @@ bool ldpc_chains_pay_off(int code_index) {
     return code_index >= 0 && code_index < 21 && table[code_index];
 }
 
-// Codes that run faster with the register allocation squeezed to 56 so that three CTAs share an SM (their shared
-// memory allows it): measured with tools/modcod_sweep.py, n1/4 -11 %, n1/3 -13 %, n2/5 -2 %, s1/4 -6 %, s1/3 -9 %,
-// s2/5 -10 %, s1/2 -5 %, s3/5 -7 %, s2/3 -10 % time; n1/2, n3/5, n2/3 cannot hold three (shared memory) and lose
-// 3-11 % to the tighter allocation.  Index = code table order B1..B11, C1..C10.
+// Codes that run faster with one more resident CTA per SM than the default and the register allocation squeezed
+// accordingly (three CTAs / 56 registers for CNT <= 9, two CTAs / 80 registers above): their shared memory
+// allows it.  Measured with tools/modcod_sweep.py: n1/4 -11 %, n1/3 -13 %, n2/5 -2 %, s1/4 -6 %, s1/3 -9 %,
+// s2/5 -10 %, s1/2 -5 %, s3/5 -7 %, s2/3 -10 %, s3/4 -11 %, s4/5 -25 % time.  n1/2, n3/5, n2/3 and the normal
+// codes above cannot hold the extra CTA (shared memory) and lose 3-11 % (up to 2x with spills) to the tighter
+// allocation; s5/6 and s8/9 spill too much (216-312 B) to gain.  Index = code table order B1..B11, C1..C10.
 bool ldpc_ctas_wanted3(int code_index) {
     static const bool table[21] = {true,  true,  true,  false, false, false, false, false, false, false, false,
-                                   true,  true,  true,  true,  true,  true,  false, false, false, false};
+                                   true,  true,  true,  true,  true,  true,  true,  true,  false, false};
     static const int force = [] { const char* e = getenv("DVBS2FEC_LDPC_OCC3"); return e ? atoi(e) : -1; }();
     if (force >= 0) return force != 0;
     return code_index >= 0 && code_index < 21 && table[code_index];

@@ -35,7 +35,7 @@ struct LdpcDev {
     int max_cnt;   // data links per row (max over layers)
     int sg;        // uint4 message slot-groups per row in the workspace: ldpc_slot_groups(max_cnt)
     bool chains;   // run chained layers in three phases (ldpc_chains_pay_off(code index))
-    bool occ3;     // kernel variant compiled for three CTAs per SM (ldpc_ctas_wanted3(code index))
+    bool occ3;     // kernel variant compiled for one more CTA per SM than the default (ldpc_ctas_wanted3(code index))
     // HOST pointers: copied into the kernel parameter block (constant bank) at every launch
     const uint32_t* links;       // per layer: (group << 16) | shift
     const int* layer_off;        // [q + 1]
