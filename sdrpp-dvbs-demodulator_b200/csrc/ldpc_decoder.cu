@@ -48,13 +48,14 @@ static cudaError_t allow_max_smem(KernelFn fn) {
 
 // Codes for which the three-phase treatment of chained layers beats the level-by-level one.  Measured with
 // tools/modcod_sweep.py (2048 normal / 8192 short frames, fixed noise) against the same kernel without it:
-// n1/3 -9 %, n2/3 -3..-6 %, n3/4 -12 %, n8/9 -20 %, s2/5 -12 %, s1/2 -3 %, s2/3 -9 %, s3/4 -10 % time; within +-2 %
+// n1/3 -9 %, n2/3 -3..-6 %, n3/4 -12 %, n8/9 -20 %, s2/5 -12 %, s1/2 -3 %, s2/3 -9 % time (s3/4 -10 %, but it
+// gains more from a second CTA with the lean row update, which has no chained mode); within +-2 %
 // or slower for the others (few layers with many levels, or their other conflicted layers dominate; for n1/2
 // the co-resident CTA already hides the level steps at full load).  Only layers with at least eight levels are
 // chained: the three phases cost about two extra passes over the rows.  Index = code table order B1..B11, C1..C10.
 bool ldpc_chains_pay_off(int code_index) {
     static const bool table[21] = {false, true,  false, false, false, true,  true,  false, false, true,  false,
-                                   false, false, true,  true,  false, true,  true,  false, false, false};
+                                   false, false, true,  true,  false, true,  false, false, false, false};
     static const int force = [] { const char* e = getenv("DVBS2FEC_LDPC_CHAINS"); return e ? atoi(e) : -1; }();
     if (force >= 0) return force != 0;
     return code_index >= 0 && code_index < 21 && table[code_index];
@@ -63,12 +64,13 @@ bool ldpc_chains_pay_off(int code_index) {
 // Codes that run faster with one more resident CTA per SM than the default and the register allocation squeezed
 // accordingly (three CTAs / 56 registers for CNT <= 9, two CTAs / 80 registers above): their shared memory
 // allows it.  Measured with tools/modcod_sweep.py: n1/4 -11 %, n1/3 -13 %, n2/5 -2 %, s1/4 -6 %, s1/3 -9 %,
-// s2/5 -10 %, s1/2 -5 %, s3/5 -7 %, s2/3 -10 %, s3/4 -11 %, s4/5 -25 % time.  n1/2, n3/5, n2/3 and the normal
-// codes above cannot hold the extra CTA (shared memory) and lose 3-11 % (up to 2x with spills) to the tighter
-// allocation; s5/6 and s8/9 spill too much (216-312 B) to gain.  Index = code table order B1..B11, C1..C10.
+// s2/5 -10 %, s1/2 -5 %, s3/5 -7 %, s2/3 -10 %, s3/4 -17 %, s4/5 -25 %, s5/6 -19 % time (above CNT = 9 with the
+// lean row update, row_update_lean, which keeps them from spilling).  n1/2, n3/5, n2/3 and the normal codes
+// above cannot hold the extra CTA (shared memory) and lose 3-11 % (up to 2x with spills) to the tighter
+// allocation; s8/9 still spills 216 B and loses.  Index = code table order B1..B11, C1..C10.
 bool ldpc_ctas_wanted3(int code_index) {
     static const bool table[21] = {true,  true,  true,  false, false, false, false, false, false, false, false,
-                                   true,  true,  true,  true,  true,  true,  true,  true,  false, false};
+                                   true,  true,  true,  true,  true,  true,  true,  true,  true,  false};
     static const int force = [] { const char* e = getenv("DVBS2FEC_LDPC_OCC3"); return e ? atoi(e) : -1; }();
     if (force >= 0) return force != 0;
     return code_index >= 0 && code_index < 21 && table[code_index];

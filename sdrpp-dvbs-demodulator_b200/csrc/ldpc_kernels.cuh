@@ -181,6 +181,78 @@ __device__ __forceinline__ void row_update(uint8_t* __restrict__ vbytes, const i
     }
 }
 
+// row_update with the smallest register footprint: instead of prefix/suffix minima (three arrays of D words) it
+// keeps the two smallest |t| and picks per link ("|t| == min0 ? min1 : min0", the reference's own form,
+// algorithms.hh:242-255).  A few more instructions per link, about 2 D fewer live registers: what lets the
+// kernels with many links per row fit two CTAs on an SM without spilling.  No chained-layer modes.
+template <int CNT, bool EXACT, bool BOTH>
+__device__ __forceinline__ void row_update_lean(uint8_t* __restrict__ vbytes, const int (&voff)[CNT], int cnt,
+                                                uint32_t (&msg)[(CNT + 3) / 2], uint32_t& pown, uint32_t& psec,
+                                                bool has2, int lf) {
+    constexpr int D = CNT + 2;
+    constexpr uint32_t kNeutralT = 0x00FF00FFu;
+    uint32_t tu[D];
+    uint32_t sx = ((D + 1) & 1) ? 0x00800080u : 0u;
+    uint32_t m1 = 0x00FF00FFu, m2 = 0x00FF00FFu;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        uint32_t u;
+        bool present = true;
+        if (c < CNT) {
+            present = EXACT || c < cnt;
+            u = present ? unpack_u01(*reinterpret_cast<const uint16_t*>(vbytes + voff[c])) : 0u;
+        } else if (c == CNT) {
+            u = unpack_u01(pown);
+        } else {
+            present = has2;
+            u = unpack_u01(psec);
+        }
+        const uint32_t mw = msg[c >> 1];
+        const uint32_t m = (c & 1) ? unpack23(mw) : unpack01(mw);
+        uint32_t x = sat_add_u8x2(u, __vsub2(0u, m));
+        if (!(EXACT && c < CNT) && c != CNT) x = present ? x : kNeutralT;
+        tu[c] = x;
+        const uint32_t a = __vabsdiffu4(x, 0x00800080u);
+        m2 = __vminu2(m2, __vmaxu2(m1, a));
+        m1 = __vminu2(m1, a);
+        sx ^= x;
+    }
+    uint32_t prev = 0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        uint32_t mo = 0;
+        if (!(c < CNT && !EXACT && c >= cnt)) {
+            const uint32_t x = tu[c];
+            const uint32_t a = __vabsdiffu4(x, 0x00800080u);
+            const uint32_t eq = __vcmpeq2(a, m1);
+            const uint32_t ex = (m2 & eq) | (m1 & ~eq);
+            const uint32_t om = __viaddmin_s16x2_relu(ex, kM1, kP32);
+            const uint32_t neg = prmt(sx ^ x, 0, 0xAA88);
+            mo = __viaddmin_s16x2(om ^ neg, neg & 0x00010001u, kP31);
+            const uint32_t pk = pack1(sat_add_u8x2(x, mo));
+            if (c < CNT) {
+                if (BOTH)
+                    *reinterpret_cast<uint16_t*>(vbytes + voff[c]) = (uint16_t)pk;
+                else
+                    vbytes[voff[c] + lf] = (uint8_t)(pk >> (8 * lf));
+            } else {
+                uint32_t& dst = (c == CNT) ? pown : psec;
+                if (BOTH) {
+                    dst = pk;
+                } else {
+                    const uint32_t keep = lf ? 0x00FFu : 0xFF00u;
+                    dst = (dst & keep) | (pk & ~keep & 0xFFFFu);
+                }
+            }
+        }
+        if (c & 1)
+            msg[c >> 1] = pack2(prev, mo);
+        else if (c == D - 1)
+            msg[c >> 1] = pack2(mo, 0u);
+        prev = mo;
+    }
+}
+
 // ---- chained layers ---------------------------------------------------------------------------
 // A layer in which exactly two links X, Y fall into the same 360-bit group makes row j and row j+d share one bit
 // (row j's X bit is row j+d's Y bit, d = (shift_Y - shift_X) mod 360 taken <= 180).  The reference visits rows in
@@ -507,7 +579,13 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_pair_kernel(const __gr
                 } else
                 for (int lvl = 0; lvl < nlev; ++lvl) {
                     if (active && mylev == lvl) {
-                        if (live == 3)
+                        constexpr bool LEAN = CNT > 9 && OCC == 2 && !CHAINS;   // two CTAs where one used to be
+                        if (LEAN) {
+                            if (live == 3)
+                                row_update_lean<CNT, UNIFORM, true>(vbytes, voff, cnt, msg, pown, psec, has2, 0);
+                            else
+                                row_update_lean<CNT, UNIFORM, false>(vbytes, voff, cnt, msg, pown, psec, has2, lf);
+                        } else if (live == 3)
                             row_update<CNT, UNIFORM, true>(vbytes, voff, cnt, msg, pown, psec, has2, 0);
                         else
                             row_update<CNT, UNIFORM, false>(vbytes, voff, cnt, msg, pown, psec, has2, lf);
