@@ -1,63 +1,198 @@
-// Which issue pipe do the candidate instructions use on sm_100a?  Each kernel runs long unrolled chains of
-// independent ops; mixes that overlap on different pipes finish in max() of the parts, same-pipe mixes in the sum.
+// Issue-rate microbenchmark for the instructions the LDPC kernel is built from (sm_100a), plus shared-memory
+// wavefront rates.  One CTA of 512 threads (4 warps per sub-partition) per SM; every thread runs 8 independent
+// dependency chains of the instruction under test, so a pipe that accepts one warp instruction every r cycles per
+// sub-partition shows 4/r warp-instructions per clock per SM.  Cycles come from clock64() inside the kernel
+// (slowest CTA), so the figures do not depend on the SM clock.  Mixes of two instructions show whether they
+// share a pipe (rates add up to the single-instruction rate) or issue side by side (up to 4 per clock per SM).
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipes pipes.cu && ./pipes [out.json]
+//
+// The SASS of every mode was checked with cuobjdump (the instruction named is the one in the loop).
 #include <cstdio>
 #include <cstdint>
+#include <cstring>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
-#define ITER 4096
+
+#define ITER 2048
+#define NCHAIN 8
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+    uint32_t d;
+    asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+enum Mode {
+    M_LOP3, M_PRMT, M_SHF, M_IADD3, M_VIADD16, M_VIMNMX_S, M_VIMNMX_U, M_VIMNMX3, M_VIADDMNMX, M_VIADDMNMX_RELU,
+    M_VABSDIFF4, M_ISETP_SEL, M_HMNMX2, M_IMAD, M_IMAD_IADD, M_HADD2, M_HFMA2, M_HFMA2_RELU, M_FFMA, M_VIBMAX,
+    MX_VIMNMX_IMAD, MX_VIMNMX_HFMA2, MX_LOP3_IMAD, MX_VIADDMNMX_HADD2, MX_HMNMX2_IMAD, MX_PRMT_IMAD, MX_VIMNMX_LOP3,
+    M_COUNT
+};
+static const char* kNames[M_COUNT] = {
+    "LOP3", "PRMT", "SHF", "IADD3", "VIADD.16x2", "VIMNMX.S16x2", "VIMNMX.U16x2", "VIMNMX3.S16x2", "VIADDMNMX.S16x2",
+    "VIADDMNMX.S16x2.RELU", "VABSDIFF4", "ISETP+SEL", "HMNMX2", "IMAD", "mad.lo(x,1,c) pairs -> IADD3", "HADD2", "HFMA2", "HFMA2.RELU",
+    "FFMA", "VIBMAX(pred: VIMNMX+VIADD+P2R/4)", "VIMNMX+IMAD", "VIMNMX+HFMA2", "LOP3+IMAD", "VIADDMNMX+HADD2", "HMNMX2+IMAD", "PRMT+IMAD",
+    "VIMNMX+LOP3"};
+
+#define A2(ptx) { uint32_t r; asm volatile(ptx : "=r"(r) : "r"(x), "r"(c)); return r; }
+#define A3(ptx) { uint32_t r; asm volatile(ptx : "=r"(r) : "r"(x), "r"(c), "r"(d)); return r; }
+// one instruction of the kind under test: x = f(x, c, d); `i` = chain index, `r` = repeat index (both compile-time)
 template <int MODE>
-__global__ void k(uint32_t* out, uint32_t seed) {
-    uint32_t a[8];
+__device__ __forceinline__ uint32_t op(uint32_t x, uint32_t c, uint32_t d, int i, int rr) {
+    switch (MODE) {
+        case M_LOP3: A3("lop3.b32 %0, %1, %2, %3, 0xE8;")
+        case M_PRMT: A2("prmt.b32 %0, %1, %2, 0x9180;")
+        case M_SHF: A2("shf.r.wrap.b32 %0, %1, %2, 7;")
+        case M_IADD3: A3("{.reg .b32 t; add.u32 t, %1, %2; add.u32 %0, t, %3;}")
+        case M_VIADD16: A2("add.s16x2 %0, %1, %2;")
+        case M_VIMNMX_S: if (rr & 1) A2("min.s16x2 %0, %1, %2;") else A2("max.s16x2 %0, %2, %1;")
+        case M_VIMNMX_U: if (rr & 1) A2("min.u16x2 %0, %1, %2;") else A2("max.u16x2 %0, %2, %1;")
+        case M_VIMNMX3: A3("{.reg .b32 t; min.s16x2 t, %1, %2; min.s16x2 %0, t, %3;}")
+        case M_VIADDMNMX: A3("{.reg .b32 t; add.s16x2 t, %1, %2; min.s16x2 %0, t, %3;}")
+        case M_VIADDMNMX_RELU: A3("{.reg .b32 t; add.s16x2 t, %1, %2; min.s16x2.relu %0, t, %3;}")
+        case M_VABSDIFF4: return __vabsdiffu4(x, c);
+        case M_ISETP_SEL: A3("{.reg .pred p; setp.lt.u32 p, %1, %2; selp.b32 %0, %3, %1, p;}")
+        case M_HMNMX2: if (rr & 1) A2("min.f16x2 %0, %1, %2;") else A2("max.f16x2 %0, %2, %1;")
+        case M_IMAD: A3("mad.lo.u32 %0, %1, %2, %3;")
+        case M_IMAD_IADD: A2("mad.lo.u32 %0, %1, 1, %2;")
+        case M_HADD2: A2("add.f16x2 %0, %1, %2;")
+        case M_HFMA2: A3("fma.rn.f16x2 %0, %1, %2, %3;")
+        case M_HFMA2_RELU: A3("fma.rn.relu.f16x2 %0, %1, %2, %3;")
+        case M_FFMA: { float r; asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(__uint_as_float(x)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))); return __float_as_uint(r); }
+        case M_VIBMAX: { bool ph, pl; uint32_t r = __vibmax_s16x2(x, c, &ph, &pl); return r + (ph ? 1u : 0u); }
+        // mixes: even chains one instruction, odd chains the other
+        case MX_VIMNMX_IMAD: if (i & 1) A3("mad.lo.u32 %0, %1, %2, %3;") else return op<M_VIMNMX_S>(x, c, d, i, rr);
+        case MX_VIMNMX_HFMA2: if (i & 1) A3("fma.rn.f16x2 %0, %1, %2, %3;") else return op<M_VIMNMX_S>(x, c, d, i, rr);
+        case MX_LOP3_IMAD: if (i & 1) A3("mad.lo.u32 %0, %1, %2, %3;") else A3("lop3.b32 %0, %1, %2, %3, 0xE8;")
+        case MX_VIADDMNMX_HADD2: if (i & 1) A2("add.f16x2 %0, %1, %2;") else A3("{.reg .b32 t; add.s16x2 t, %1, %2; min.s16x2.relu %0, t, %3;}")
+        case MX_HMNMX2_IMAD: if (i & 1) A3("mad.lo.u32 %0, %1, %2, %3;") else return op<M_HMNMX2>(x, c, d, i, rr);
+        case MX_PRMT_IMAD: if (i & 1) A3("mad.lo.u32 %0, %1, %2, %3;") else A2("prmt.b32 %0, %1, %2, 0x9180;")
+        case MX_VIMNMX_LOP3: if (i & 1) A3("lop3.b32 %0, %1, %2, %3, 0xE8;") else return op<M_VIMNMX_S>(x, c, d, i, rr);
+    }
+    return x;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) pipe_kernel(uint32_t* out, long long* cycles, uint32_t seed) {
+    uint32_t a[NCHAIN];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = seed + threadIdx.x * 8 + i;
-    uint32_t c = seed | 0x00010001u;
+    for (int i = 0; i < NCHAIN; ++i) a[i] = seed * (threadIdx.x + 1) + i * 0x01010101u;
+    const uint32_t c = seed | 0x00010001u, d = seed * 7u + 0x00030003u;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < NCHAIN; ++i) a[i] = op<MODE>(a[i], c, d, i, r);
+    }
+    const long long t1 = clock64();
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < NCHAIN; ++i) s ^= a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// ---- shared memory: wavefronts per clock per SM ------------------------------------------------------------------
+// W = access width in bytes (2, 4, 8, 16); ST = stores instead of loads.  Consecutive lanes touch consecutive
+// W-byte items (no bank conflicts), 8 independent accesses in flight per thread.
+template <int W, bool ST>
+__global__ void __launch_bounds__(512, 1) smem_kernel(uint32_t* out, long long* cycles, uint32_t seed) {
+    extern __shared__ __align__(16) uint8_t buf[];
+    constexpr uint32_t kBuf = 512 * 16 * 8;
+    for (int x = threadIdx.x; x < (int)kBuf / 4; x += 512) reinterpret_cast<uint32_t*>(buf)[x] = x * seed;
+    __syncthreads();
+    uint32_t acc = 0;
+    uint32_t off = threadIdx.x * W;
+    const long long t0 = clock64();
+#pragma unroll 1
     for (int it = 0; it < ITER; ++it) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (MODE == 0 && (i & 1) == 0) { uint32_t lo = __vmins2(a[i], a[i + 1]) + 1u, hi = __vmaxs2(a[i], a[i + 1]) ^ c; a[i] = hi; a[i + 1] = lo; }   // 2 VIMNMX (+2 cheap)
-            if (MODE == 1 && (i & 1) == 0) { __half2 x = *(__half2*)&a[i], y = *(__half2*)&a[i + 1]; __half2 lo = __hmin2(x, y), hi = __hmax2(x, y); a[i] = (*(uint32_t*)&hi) ^ c; a[i + 1] = (*(uint32_t*)&lo) + 1u; }  // 2 HMNMX2 (+2 cheap)
-            if (MODE == 2) { __half2 h = __hadd2(*(__half2*)&a[i], *(__half2*)&c); a[i] = *(uint32_t*)&h; }  // HADD2
-            if (MODE == 3) a[i] = a[i] * 3u + c;                                       // IMAD
-            if (MODE == 4 && (i & 1) == 0) { uint32_t lo = a[i] + 1u, hi = a[i + 1] ^ c; a[i] = hi; a[i + 1] = lo; }   // the 2 cheap ops alone (IADD + LOP3)
-            if (MODE == 5 && (i & 3) == 0) { uint32_t lo = __vmins2(a[i], a[i + 1]) + 1u, hi = __vmaxs2(a[i], a[i + 1]) ^ c; a[i] = hi; a[i + 1] = lo;
-                                             __half2 x = *(__half2*)&a[i + 2], y = *(__half2*)&a[i + 3]; __half2 l2 = __hmin2(x, y), h2 = __hmax2(x, y); a[i + 2] = (*(uint32_t*)&h2) ^ c; a[i + 3] = (*(uint32_t*)&l2) + 1u; }
-            if (MODE == 6) { a[i] = __vmins2(a[i], c); i++; __half2 h = __hadd2(*(__half2*)&a[i], *(__half2*)&c); a[i] = *(uint32_t*)&h; }  // VIMNMX + HADD2
-            if (MODE == 7) { a[i] = __vmins2(a[i], c); i++; a[i] = a[i] * 3u + c; }   // VIMNMX + IMAD
-            if (MODE == 8) { __half2 h = __hmin2(*(__half2*)&a[i], *(__half2*)&c); a[i] = *(uint32_t*)&h; i++; __half2 g = __hadd2(*(__half2*)&a[i], *(__half2*)&c); a[i] = *(uint32_t*)&g; }  // HMNMX2 + HADD2
-            if (MODE == 9) { __half2 h = __hfma2_relu(*(__half2*)&a[i], *(__half2*)&c, *(__half2*)&c); a[i] = *(uint32_t*)&h; }  // HFMA2.RELU
-            if (MODE == 10) a[i] = __viaddmin_s16x2_relu(a[i], c, 0x00ff00ffu);        // VIADDMNMX.RELU
-            if (MODE == 11) { a[i] = __viaddmin_s16x2_relu(a[i], c, 0x00ff00ffu); i++; __half2 h = __hfma2_relu(*(__half2*)&a[i], *(__half2*)&c, *(__half2*)&c); a[i] = *(uint32_t*)&h; }
-            if (MODE == 12) a[i] = __vabsdiffu4(a[i], c);                              // VABSDIFF4
-            if (MODE == 13) { uint32_t d; asm("prmt.b32 %0,%1,%2,0x9180;" : "=r"(d) : "r"(a[i]), "r"(c)); a[i] = d; }  // PRMT
+            const uint32_t o = (off + i * 512 * W) & (kBuf - 1);
+            if (ST) {
+                if (W == 2) *reinterpret_cast<volatile uint16_t*>(buf + o) = (uint16_t)(acc + i);
+                if (W == 4) *reinterpret_cast<volatile uint32_t*>(buf + o) = acc + i;
+                if (W == 8) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(buf + o)), "r"(acc), "r"(acc + i)); }
+                if (W == 16) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(buf + o)), "r"(acc), "r"(acc + i)); }
+            } else {
+                if (W == 2) acc += *reinterpret_cast<volatile uint16_t*>(buf + o);
+                if (W == 4) acc += *reinterpret_cast<volatile uint32_t*>(buf + o);
+                if (W == 8) { uint32_t p, q; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(p), "=r"(q) : "r"((uint32_t)__cvta_generic_to_shared(buf + o))); acc += p ^ q; }
+                if (W == 16) { uint32_t p, q, r, s; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p), "=r"(q), "=r"(r), "=r"(s) : "r"((uint32_t)__cvta_generic_to_shared(buf + o))); acc += p ^ q ^ r ^ s; }
+            }
         }
+        off = (off + 16 * 32) & (kBuf - 1);
     }
-    uint32_t s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s ^= a[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    const long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
+
+static int g_sms = 148;
+static double max_cycles(const long long* h, int n) {
+    long long m = 0;
+    for (int i = 0; i < n; ++i) m = h[i] > m ? h[i] : m;
+    return (double)m;
+}
+
 template <int MODE>
-float run(uint32_t* d) {
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k<MODE><<<148 * 4, 256>>>(d, 12345u);
-    cudaEventRecord(e0);
-    k<MODE><<<148 * 4, 256>>>(d, 12345u);
-    cudaEventRecord(e1);
-    cudaEventSynchronize(e1);
-    float ms; cudaEventElapsedTime(&ms, e0, e1);
-    return ms;
+double run_pipe(uint32_t* d, long long* dc, long long* hc) {
+    pipe_kernel<MODE><<<g_sms, 512>>>(d, dc, 12345u);
+    pipe_kernel<MODE><<<g_sms, 512>>>(d, dc, 12345u);
+    cudaMemcpy(hc, dc, g_sms * sizeof(long long), cudaMemcpyDeviceToHost);
+    double winst = 16.0 * ITER * 8 * NCHAIN;   // warp instructions per SM
+    if (MODE == M_IMAD_IADD) winst *= 0.5;      // ptxas merges two of these adds into one IADD3
+    return winst / max_cycles(hc, g_sms);
 }
-int main() {
-    uint32_t* d; cudaMalloc(&d, 148 * 4 * 256 * 4);
-    const char* names[] = {"VIMNMX.S16x2", "HMNMX2", "HADD2", "IMAD", "LOP3", "VIMNMX+HMNMX2", "VIMNMX+HADD2", "VIMNMX+IMAD",
-                           "HMNMX2+HADD2", "HFMA2.RELU", "VIADDMNMX.RELU", "VIADDMNMX.RELU+HFMA2.RELU", "VABSDIFF4", "PRMT"};
-    float t[14];
-    t[0] = run<0>(d); t[1] = run<1>(d); t[2] = run<2>(d); t[3] = run<3>(d); t[4] = run<4>(d); t[5] = run<5>(d); t[6] = run<6>(d);
-    t[7] = run<7>(d); t[8] = run<8>(d); t[9] = run<9>(d); t[10] = run<10>(d); t[11] = run<11>(d); t[12] = run<12>(d); t[13] = run<13>(d);
-    // ops per kernel: 148*4 blocks * 8 warps * ITER * 8 warp-instr
-    double winst = 148.0 * 4 * 8 * ITER * 8;
-    for (int i = 0; i < 14; ++i)
-        printf("%-28s %.3f ms  -> %.2f warp-instr/clk/SM at 1.965 GHz\n", names[i], t[i], winst / 148 / (t[i] * 1e-3 * 1.965e9));
+template <int W, bool ST>
+double run_smem(uint32_t* d, long long* dc, long long* hc) {
+    cudaFuncSetAttribute(smem_kernel<W, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 16 * 8);
+    smem_kernel<W, ST><<<g_sms, 512, 512 * 16 * 8>>>(d, dc, 12345u);
+    smem_kernel<W, ST><<<g_sms, 512, 512 * 16 * 8>>>(d, dc, 12345u);
+    cudaMemcpy(hc, dc, g_sms * sizeof(long long), cudaMemcpyDeviceToHost);
+    const double winst = 16.0 * ITER * 8;
+    return winst / max_cycles(hc, g_sms);
+}
+
+template <int MODE>
+void all_pipes(uint32_t* d, long long* dc, long long* hc, double* r) {
+    r[MODE] = run_pipe<MODE>(d, dc, hc);
+    if constexpr (MODE + 1 < M_COUNT) all_pipes<MODE + 1>(d, dc, hc, r);
+}
+
+int main(int argc, char** argv) {
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, 0);
+    g_sms = prop.multiProcessorCount;
+    uint32_t* d;
+    long long *dc, *hc = new long long[g_sms];
+    cudaMalloc(&d, (size_t)g_sms * 512 * 4);
+    cudaMalloc(&dc, g_sms * sizeof(long long));
+    double r[M_COUNT];
+    all_pipes<0>(d, dc, hc, r);
+    double s[8];
+    s[0] = run_smem<2, false>(d, dc, hc); s[1] = run_smem<4, false>(d, dc, hc);
+    s[2] = run_smem<8, false>(d, dc, hc); s[3] = run_smem<16, false>(d, dc, hc);
+    s[4] = run_smem<2, true>(d, dc, hc);  s[5] = run_smem<4, true>(d, dc, hc);
+    s[6] = run_smem<8, true>(d, dc, hc);  s[7] = run_smem<16, true>(d, dc, hc);
+    const char* sn[8] = {"LDS.U16", "LDS.32", "LDS.64", "LDS.128", "STS.U16", "STS.32", "STS.64", "STS.128"};
+    const int sw[8] = {2, 4, 8, 16, 2, 4, 8, 16};
+    if (cudaDeviceSynchronize() != cudaSuccess) { fprintf(stderr, "CUDA error\n"); return 1; }
+    FILE* f = argc > 1 ? fopen(argv[1], "w") : stdout;
+    fprintf(f, "{\n \"gpu\": \"%s\", \"sms\": %d,\n \"unit\": \"warp instructions per clock per SM (4 sub-partitions)\",\n \"issue\": {\n", prop.name, g_sms);
+    for (int i = 0; i < M_COUNT; ++i) fprintf(f, "  \"%s\": %.3f%s\n", kNames[i], r[i], i + 1 < M_COUNT ? "," : "");
+    fprintf(f, " },\n \"shared_memory\": {\n");
+    for (int i = 0; i < 8; ++i)
+        fprintf(f, "  \"%s\": {\"warp_instr_per_clk_per_sm\": %.3f, \"bytes_per_clk_per_sm\": %.1f}%s\n", sn[i], s[i], s[i] * 32 * sw[i], i + 1 < 8 ? "," : "");
+    fprintf(f, " }\n}\n");
+    if (f != stdout) fclose(f);
     return 0;
 }
