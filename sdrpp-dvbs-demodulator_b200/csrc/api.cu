@@ -142,6 +142,7 @@ struct DevCtx {
     BchDev bchd{};
     DemapDev demap{};
     int grid = 0;
+    ~DevCtx() { ldpc_release(ldpc); }
 };
 
 }  // namespace
@@ -227,13 +228,15 @@ int setup_device_tables(dvbs2fec_handle* h, DevCtx& d) {
     L.ngroups = c.K / kGroup;
     L.max_cnt = c.max_cnt;
     L.sg = ldpc_slot_groups(c.max_cnt);
-    L.chains = ldpc_chains_pay_off(c.index);
+    L.v2 = ldpc_use_v2(c.index);
+    L.chains = !L.v2 && ldpc_chains_pay_off(c.index);
     L.occ3 = ldpc_ctas_wanted3(c.index);
     if (!L.sg) return fail(DVBS2FEC_EINVAL, "no LDPC kernel for %d links per row", c.max_cnt);
     L.links = h->h_links.data();
     L.layer_off = c.layer_off.data();
     L.layer_nlev = c.layer_nlev.data();
     L.row_level = cd.row_level.p;
+    if (int e = ldpc_prepare(L)) return fail(DVBS2FEC_ECUDA, "LDPC kernel set-up: %s", cudaGetErrorString((cudaError_t)e));
     int per_sm = ldpc_max_ctas_per_sm(L);
     if (per_sm <= 0) return fail(DVBS2FEC_ENODEV, "LDPC kernel does not fit on device %d (%s)", d.device,
                                  cudaGetErrorString(cudaGetLastError()));

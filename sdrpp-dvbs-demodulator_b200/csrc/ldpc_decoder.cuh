@@ -28,6 +28,9 @@ namespace s2 {
 
 constexpr int kLdpcThreads = 384;       // 12 warps: rows 0..359 + 24 idle lanes
 constexpr int kBitWords = 13;           // 360 hard bits = 12 words (last holds 8) + one zero pad word
+constexpr int16_t kLdpcItersNoInput = -2;   // iters_out value of a frame whose streamed input never arrived
+
+struct LdpcPlan;                        // the kernel parameter block and launch choice, built once per configuration
 
 struct LdpcDev {
     int N, K, R, q;
@@ -36,6 +39,8 @@ struct LdpcDev {
     int sg;        // uint4 message slot-groups per row in the workspace: ldpc_slot_groups(max_cnt)
     bool chains;   // run chained layers in three phases (ldpc_chains_pay_off(code index))
     bool occ3;     // kernel variant compiled for one more CTA per SM than the default (ldpc_ctas_wanted3(code index))
+    bool v2;       // second-generation kernel (ldpc_v2.cuh) instead of the first (ldpc_kernels.cuh): ldpc_use_v2(code index)
+    const LdpcPlan* plan;   // ldpc_prepare(); owned by the caller of ldpc_prepare (ldpc_release)
     // HOST pointers: copied into the kernel parameter block (constant bank) at every launch
     const uint32_t* links;       // per layer: (group << 16) | shift
     const int* layer_off;        // [q + 1]
@@ -47,6 +52,11 @@ struct LdpcDev {
 int ldpc_slot_groups(int max_cnt);
 bool ldpc_chains_pay_off(int code_index);   // measured per code, see ldpc_decoder.cu
 bool ldpc_ctas_wanted3(int code_index);     // likewise
+bool ldpc_use_v2(int code_index);           // likewise
+// Builds the parameter block (layer tables, barrier elision, chains) and opts the kernel in to the device's full
+// shared memory, once; ldpc_launch then only patches the per-launch pointers.  Returns cudaError_t as int.
+int ldpc_prepare(LdpcDev& code);
+void ldpc_release(LdpcDev& code);
 
 struct LdpcArgs {
     LdpcDev code;
@@ -68,6 +78,7 @@ inline size_t ldpc_workspace_bytes(const LdpcDev& c) {
 inline size_t ldpc_smem_bytes(const LdpcDev& c) {
     // LLR pairs, bit planes, slack; with chained layers also their 360 x 16 B hand-over words
     const size_t base = (size_t)c.K * 2 + (size_t)2 * (c.ngroups + c.q) * kBitWords * 4;
+    if (c.v2) return base + 768 + 64;       // + the 361 pty[q-1][.] pairs handed between neighbouring threads
     return c.chains ? ((base + 15) & ~(size_t)15) + 360 * 16 + 64 : base + 64;
 }
 

@@ -39,4 +39,36 @@ struct Variant {
 extern const Variant kLdpcVariantsA[], kLdpcVariantsB[], kLdpcVariantsC[], kLdpcVariantsD[];
 extern const int kLdpcVariantsA_n, kLdpcVariantsB_n, kLdpcVariantsC_n, kLdpcVariantsD_n;
 
+// ---- second-generation kernel (ldpc_v2.cuh) ----------------------------------------------------------------------
+struct LdpcParams2 {
+    int N, K, R, q, ngroups, sg;
+    int nframes, max_trials, hard_stride, pad_;
+    long long wait_budget;            // SM clocks a CTA waits for streamed input before it reports kLdpcItersNoInput
+    const int8_t* llr_in;
+    uint8_t* hard_out;
+    int16_t* iters_out;
+    int8_t* llr_out;
+    uint8_t* workspace;
+    unsigned long long ws_stride;
+    unsigned int* work_counter;
+    const unsigned int* arrived;
+    const uint8_t* row_level;
+    uint16_t layer_off[kMaxLayers + 1];
+    uint8_t layer_nlev[kMaxLayers];
+    uint8_t layer_sync[kMaxLayers];   // 1: a CTA barrier must follow this layer
+    uint8_t link_group[kMaxLinks];    // data-bit group g of the link; its LLR pairs start at byte 720 g of the shared array
+    uint16_t link_add[kMaxLinks];     // 720 - 2 * shift: row j reads byte 720 g + ((2 j + link_add) mod 720)
+};
+static_assert(sizeof(LdpcParams2) <= 4096, "kernel parameter block must stay within the 4 KB constant window");
+
+using KernelFn2 = void (*)(const LdpcParams2);
+struct Variant2 {
+    int cnt;
+    // [streamed input][one more CTA per SM]
+    KernelFn2 uniform[2][2];
+    KernelFn2 ragged[2][2];
+};
+extern const Variant2 kLdpc2VariantsA[], kLdpc2VariantsB[], kLdpc2VariantsC[], kLdpc2VariantsD[];
+extern const int kLdpc2VariantsA_n, kLdpc2VariantsB_n, kLdpc2VariantsC_n, kLdpc2VariantsD_n;
+
 }  // namespace s2
