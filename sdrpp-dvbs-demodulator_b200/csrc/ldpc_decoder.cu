@@ -158,7 +158,7 @@ bool ldpc_chains_pay_off(int code_index) {
 // accordingly (three CTAs / 56 registers for CNT <= 9, two CTAs / 80 registers above): their shared memory
 // allows it.  Index = code table order B1..B11, C1..C10.
 bool ldpc_ctas_wanted3(int code_index) {
-    static const bool table[21] = {true,  true,  true,  false, false, false, false, false, false, false, false,
+    static const bool table[21] = {true,  true,  true,  true,  false, false, false, false, false, false, false,
                                    true,  true,  true,  true,  true,  true,  true,  true,  true,  false};
     static const int force = env_int("DVBS2FEC_LDPC_OCC3", -1);
     if (force >= 0) return force != 0;

@@ -73,12 +73,16 @@ struct LdpcArgs {
 };
 
 inline size_t ldpc_workspace_bytes(const LdpcDev& c) {
-    return (((size_t)c.q * c.sg * 360 * 16 + (size_t)c.R * 2) + 255) & ~(size_t)255;
+    // message records, parity LLR pairs; second-generation kernel: also the bit planes of the full termination test
+    size_t b = (size_t)c.q * c.sg * 360 * 16 + (((size_t)c.R * 2 + 15) & ~(size_t)15);
+    if (c.v2) b += (size_t)2 * (c.ngroups + c.q) * kBitWords * 4;
+    return (b + 255) & ~(size_t)255;
 }
 inline size_t ldpc_smem_bytes(const LdpcDev& c) {
     // LLR pairs, bit planes, slack; with chained layers also their 360 x 16 B hand-over words
+    // second generation: LLR pairs + the 361 pty[q-1][.] pairs handed between neighbouring threads + layer descriptors
+    if (c.v2) return (size_t)c.K * 2 + 768 + (size_t)c.q * ((1 + 2 * c.max_cnt + 3) & ~3) * 4 + 64;
     const size_t base = (size_t)c.K * 2 + (size_t)2 * (c.ngroups + c.q) * kBitWords * 4;
-    if (c.v2) return base + 768 + 64;       // + the 361 pty[q-1][.] pairs handed between neighbouring threads
     return c.chains ? ((base + 15) & ~(size_t)15) + 360 * 16 + 64 : base + 64;
 }
 

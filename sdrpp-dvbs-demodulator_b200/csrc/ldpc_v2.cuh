@@ -135,9 +135,11 @@ __device__ __forceinline__ void exclusive_min(const uint32_t (&a)[D], uint32_t (
 //   a = |t|                      (the reference's max(|max(t,-127)|-1, 0) is monotone in a, applied after the minimum)
 //   ex = min of a over the other links;  om = clamp(ex - 1, 0, 32)
 //   m' = -om if an odd number of the other t is negative, else min(om, 31);  llr' = sat8(t + m')
+// keep: word whose upper half is stored in the upper half of the last message word when the number of slots is odd
+//       (the record's spare bytes; the caller keeps the row level there).
 template <int CNT, bool FIRST, bool RAGGED>
 __device__ __forceinline__ void row_update(const uint32_t (&off)[CNT], int cnt, uint32_t (&mw)[(CNT + 3) / 2],
-                                           uint32_t& pown, uint32_t& psec) {
+                                           uint32_t& pown, uint32_t& psec, uint32_t keep) {
     constexpr int D = CNT + 2;
     uint32_t tu[D], a[D], ex[D];
     // bit 7 of tu is set for t >= 0.  The product of the OTHER signs of link k is negative iff
@@ -180,7 +182,7 @@ __device__ __forceinline__ void row_update(const uint32_t (&off)[CNT], int cnt, 
         if (c & 1)
             mw[c >> 1] = pack_two(prev, beta);
         else if (c == D - 1)
-            mw[c >> 1] = pack_two(beta, 0u);
+            mw[c >> 1] = prmt(beta, keep, 0x7620);      // beta.A, beta.B, keep.byte2, keep.byte3
         prev = beta;
     }
 }
@@ -188,11 +190,12 @@ __device__ __forceinline__ void row_update(const uint32_t (&off)[CNT], int cnt, 
 // ---- the termination test on bit planes (full form; see the screen in the kernel) -----------------------------
 
 // bits [o, o+32) of the 360-periodic extension of a 360-bit vector stored in 12 words (+1 zero word)
+// (the planes live in the CTA's workspace in global memory: L2-coherent accesses)
 __device__ __forceinline__ uint32_t win360(const uint32_t* H, int o) {
     int w = o >> 5, s = o & 31;
-    uint32_t r = __funnelshift_r(H[w], H[w + 1], s);
+    uint32_t r = __funnelshift_r(__ldcg(H + w), __ldcg(H + w + 1), s);
     int over = o + 32 - 360;
-    if (over > 0) r |= H[0] << (32 - over);
+    if (over > 0) r |= __ldcg(H) << (32 - over);
     return r;
 }
 // Hard decisions + zero test of 8 consecutive offset-binary LLR pairs (one uint4: A0 B0 A1 B1 ...).
@@ -219,8 +222,8 @@ __device__ __forceinline__ void harvest_planes(const uint4* src, int n360, uint3
         uint4 w = GLOBAL ? __ldcg(src + t) : src[t];
         uint32_t bits = harvest8(w, nzacc);
         int g = t / 45, k = t - g * 45;
-        Hb[g * (kBitWords * 4) + k] = (uint8_t)bits;
-        Hb[(gstride + g) * (kBitWords * 4) + k] = (uint8_t)(bits >> 8);
+        __stcg(&Hb[g * (kBitWords * 4) + k], (uint8_t)bits);
+        __stcg(&Hb[(gstride + g) * (kBitWords * 4) + k], (uint8_t)(bits >> 8));
     }
 }
 
@@ -242,26 +245,49 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
     constexpr int MW = (SLOTS + 1) / 2;     // message words per row in registers
     constexpr int SG = (SLOTS + 7) / 8;     // uint4 groups per row in the workspace
     static_assert(16 * SG >= 2 * SLOTS + 2, "the message record needs two spare bytes (row level)");
+    constexpr int DW = (1 + 2 * CNT + 3) & ~3;   // words per layer descriptor (multiple of 4: read with 128-bit loads)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int q = p.q, K = p.K, N = p.N, R = p.R;
     uint16_t* vdata = reinterpret_cast<uint16_t*>(smem_raw);
-    uint32_t* HD = reinterpret_cast<uint32_t*>(smem_raw + (size_t)K * 2);     // [2][ngroups][13]
-    uint32_t* HP = HD + 2 * p.ngroups * kBitWords;                            // [2][q][13]
-    uint16_t* X = reinterpret_cast<uint16_t*>(HP + 2 * q * kBitWords);        // X[j + 1] = pty[q-1][j], X[0] unused
+    uint16_t* X = reinterpret_cast<uint16_t*>(smem_raw + (size_t)K * 2);      // X[j + 1] = pty[q-1][j], X[0] unused
+    // Layer descriptors, built once per CTA: word 0 = levels | barrier-after << 8 | data links << 16, then per data
+    // link the shared-memory address of its group's first LLR pair and 720 - 2 shift.  One or a few 128-bit loads per
+    // layer replace a dozen dependent constant-bank reads and the arithmetic on them.
+    uint32_t* desc = reinterpret_cast<uint32_t*>(smem_raw + (size_t)K * 2 + 768);
     __shared__ unsigned int s_pair;
     __shared__ int s_bad[2];
 
     const int tid = threadIdx.x;
-    const int j = tid;
-    const bool active = j < 360;
+    const bool active = tid < 360;
+    // Threads 360..383 shadow row 359: they read and write exactly what thread 359 (same warp) does, so the pass
+    // needs no "row exists" predicate anywhere.  Everything that must count rows once uses `active`.
+    const int j = active ? tid : 359;
     const uint32_t vbase = (uint32_t)__cvta_generic_to_shared(vdata);
+    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(desc);
     const uint32_t j2 = 2u * (uint32_t)j;
     uint4* wmsg = reinterpret_cast<uint4*>(p.workspace + (size_t)blockIdx.x * p.ws_stride);
     uint16_t* wpty = reinterpret_cast<uint16_t*>(p.workspace + (size_t)blockIdx.x * p.ws_stride + (size_t)q * SG * 360 * 16);
+    // bit planes of the full termination test (hard decisions, 360 bits per group in 13 words): in the workspace too --
+    // with the screen the full test runs about twice per frame, and without the planes a third CTA fits on the SM
+    uint32_t* HD = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(wpty) + (((size_t)R * 2 + 15) & ~(size_t)15));  // [2][ngroups][13]
+    uint32_t* HP = HD + 2 * p.ngroups * kBitWords;                                                                       // [2][q][13]
+    for (int x = tid; x < q * DW; x += kLdpcThreads) {
+        const int i = x / DW, w = x - i * DW;
+        const int loff = p.layer_off[i], cnt = (int)p.layer_off[i + 1] - loff;
+        uint32_t v = 0;
+        if (w == 0) {
+            v = (uint32_t)p.layer_nlev[i] | (uint32_t)p.layer_sync[i] << 8 | (uint32_t)cnt << 16;
+        } else if (w <= 2 * CNT) {
+            const int c = (w - 1) >> 1;
+            const int k = loff + (c < cnt ? c : 0);
+            v = ((w - 1) & 1) ? (uint32_t)p.link_add[k] : vbase + 720u * p.link_group[k];
+        }
+        desc[x] = v;
+    }
     const int npairs = (p.nframes + 1) >> 1;
 
     // zero the bit planes once: bytes 45..51 of every 360-bit group are never written and must read as 0
-    for (int x = tid; x < 2 * (p.ngroups + q) * kBitWords; x += kLdpcThreads) HD[x] = 0;
+    for (int x = tid; x < 2 * (p.ngroups + q) * kBitWords; x += kLdpcThreads) __stcg(&HD[x], 0u);
 
     for (;;) {
         __syncthreads();
@@ -292,8 +318,8 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
         const int8_t* inA = p.llr_in + (size_t)fa * N;
         const int8_t* inB = p.llr_in + (size_t)(hasB ? fb : fa) * N;
         // column j of the parity part: pty[i][j] = v[K + q j + i], contiguous in i
-        const int8_t* colA = inA + K + (size_t)q * (active ? j : 0);
-        const int8_t* colB = inB + K + (size_t)q * (active ? j : 0);
+        const int8_t* colA = inA + K + (size_t)q * j;
+        const int8_t* colB = inB + K + (size_t)q * j;
         auto in_pair = [&](int i) -> uint32_t {   // parity LLR pair of row (i, j) from the input, packed offset binary
             const uint32_t a = STREAMED ? (uint8_t)__ldcg(colA + i) : (uint8_t)__ldg(colA + i);
             const uint32_t b = STREAMED ? (uint8_t)__ldcg(colB + i) : (uint8_t)__ldg(colB + i);
@@ -313,7 +339,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
             reinterpret_cast<uint4*>(vdata)[x] = o;
         }
         uint32_t pown = 0, psec = 0;      // unpacked parity LLRs of the row being worked on
-        if (active) {
+        {
             const uint32_t last = in_pair(q - 1);
             X[j + 1] = (uint16_t)last;
             pown = unpack_lo(last);
@@ -323,21 +349,23 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
 
         int live = hasB ? 3 : 1;          // bit f set: frame f still iterating
         uint32_t off[CNT];                // shared-memory addresses of the data links of the current layer
+        uint32_t lw0 = 0;                 // word 0 of the current layer's descriptor
         auto link_addresses = [&](int i) {
-            const int loff = p.layer_off[i];
+            uint32_t dw[DW];
 #pragma unroll
-            for (int c = 0; c < CNT; ++c) {
-                const int k = loff + ((!RAGGED || c < (int)p.layer_off[i + 1] - loff) ? c : 0);
-                // byte offset 720 group + 2 ((j - shift) mod 360): the wrap is min(x, x - 720) in unsigned arithmetic
-                off[c] = vbase + 720u * p.link_group[k] + addmin_u32(j2 + p.link_add[k], (uint32_t)-720);
-            }
+            for (int x = 0; x < DW; x += 4)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dw[x]), "=r"(dw[x + 1]), "=r"(dw[x + 2]), "=r"(dw[x + 3])
+                             : "r"(dbase + (uint32_t)(i * DW + x) * 4u));
+            lw0 = dw[0];
+#pragma unroll
+            for (int c = 0; c < CNT; ++c)   // address of pair (j - shift) mod 360 of the group: the wrap is min(x, x - 720), unsigned
+                off[c] = dw[1 + 2 * c] + addmin_u32(j2 + dw[2 + 2 * c], (uint32_t)-720);
         };
         // Screen of LDPCDecoder::bad: row (q-1, j) with the parity LLRs in pown (pty[q-1][j]) and psec (pty[q-2][j]).
         // Returns bit f set when the row is bad for frame f (sign product not positive or a zero LLR).
         auto screen = [&]() -> int {
-            if (!active) return 0;
             link_addresses(q - 1);
-            const int cnt = (int)p.layer_off[q] - (int)p.layer_off[q - 1];
+            const int cnt = (int)(lw0 >> 16);
             uint32_t sx = pown ^ psec, mn = minu2(__vabsdiffu4(pown, kC128), __vabsdiffu4(psec, kC128));
             int nl = 2;
 #pragma unroll
@@ -354,7 +382,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
             int bad = 0;
             if ((sx & 0x80u) || (mn & 0xFFFFu) == 0) bad |= 1;
             if ((sx & 0x800000u) || (mn >> 16) == 0) bad |= 2;
-            return bad;
+            return bad;       // (threads 360..383 repeat row 359's verdict)
         };
 
         __syncthreads();
@@ -364,7 +392,6 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
             // ---- LDPCDecoder::bad (layered_decoder.hh:28-45): screen first, full bit-plane test only when the
             //      screen found nothing for a frame that is still iterating
             int bad = (__syncthreads_or(scr & 1) ? 1 : 0) | (__syncthreads_or(scr & 2) ? 2 : 0);
-            bool planes_fresh = false;
             if (live & ~bad) {
                 uint32_t nzacc = 0xFFFFFFFFu;
                 if (n > 0) {
@@ -378,8 +405,8 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                         const unsigned ba = __ballot_sync(0xFFFFFFFFu, !(w & 0x80u));
                         const unsigned bb = __ballot_sync(0xFFFFFFFFu, !(w & 0x8000u));
                         if (lane == 0) {
-                            HP[i * kBitWords + wid] = ba;
-                            HP[(q + i) * kBitWords + wid] = bb;
+                            __stcg(&HP[i * kBitWords + wid], ba);
+                            __stcg(&HP[(q + i) * kBitWords + wid], bb);
                         }
                         if ((w & 0xFFu) == 0x80u) nzacc &= ~0x00800080u;
                         if ((w & 0xFF00u) == 0x8000u) nzacc &= ~0x80008000u;
@@ -393,15 +420,15 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                 for (int task = tid; task < q * 12; task += kLdpcThreads) {
                     const int ii = task / 12, w = task - ii * 12;
                     const int loff = p.layer_off[ii], cnt = (int)p.layer_off[ii + 1] - loff;
-                    uint32_t sA = HP[ii * kBitWords + w], sB = HP[(q + ii) * kBitWords + w];
+                    uint32_t sA = __ldcg(&HP[ii * kBitWords + w]), sB = __ldcg(&HP[(q + ii) * kBitWords + w]);
                     if (ii > 0) {
-                        sA ^= HP[(ii - 1) * kBitWords + w];
-                        sB ^= HP[(q + ii - 1) * kBitWords + w];
+                        sA ^= __ldcg(&HP[(ii - 1) * kBitWords + w]);
+                        sB ^= __ldcg(&HP[(q + ii - 1) * kBitWords + w]);
                     } else {  // row (0,j) uses pty[q-1][j-1], row (0,0) has no second parity link
                         const uint32_t* ta = &HP[(q - 1) * kBitWords];
                         const uint32_t* tb = &HP[(2 * q - 1) * kBitWords];
-                        sA ^= (ta[w] << 1) | (w ? ta[w - 1] >> 31 : 0u);
-                        sB ^= (tb[w] << 1) | (w ? tb[w - 1] >> 31 : 0u);
+                        sA ^= (__ldcg(ta + w) << 1) | (w ? __ldcg(ta + w - 1) >> 31 : 0u);
+                        sB ^= (__ldcg(tb + w) << 1) | (w ? __ldcg(tb + w - 1) >> 31 : 0u);
                     }
                     for (int c = 0; c < cnt; ++c) {
                         // bit (32 w + b) of the row vector is data bit (32 w + b - shift) mod 360 of the group
@@ -420,7 +447,6 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                 }
                 __syncthreads();
                 bad = (s_bad[0] ? 1 : 0) | (s_bad[1] ? 2 : 0);
-                planes_fresh = true;
             }
             // ---- while (bad() && --trials >= 0) update();  (layered_decoder.hh:127-128), per frame
             int fin = 0;
@@ -436,22 +462,18 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
             if (fin) {
                 // results of the frames that stop here: iteration count, MSB-first hard decisions of the K
                 // systematic bits (module_dvbs2_demod.cpp:357-360), optionally the posterior LLRs
-                if (!planes_fresh) {
-                    uint32_t nz = 0xFFFFFFFFu;
-                    harvest_planes<false>(reinterpret_cast<const uint4*>(vdata), p.ngroups, HD, p.ngroups, tid, nz);
-                    __syncthreads();
-                }
+                // hard decisions straight from the LLR pairs: 8 pairs (one uint4) give one byte of each frame
                 const int kbytes = K / 8;
+                for (int b = tid; b < kbytes; b += kLdpcThreads) {
+                    uint32_t nz = 0xFFFFFFFFu;
+                    const uint32_t bits = harvest8(reinterpret_cast<const uint4*>(vdata)[b], nz);
+                    if (fin & 1) p.hard_out[(size_t)fa * p.hard_stride + b] = (uint8_t)(__brev(bits & 0xFFu) >> 24);
+                    if (fin & 2) p.hard_out[(size_t)fb * p.hard_stride + b] = (uint8_t)(__brev((bits >> 8) & 0xFFu) >> 24);
+                }
                 for (int f = 0; f < 2; ++f) {
                     if (!(fin >> f & 1)) continue;
                     const int fr = f ? fb : fa;
                     if (tid == 0) p.iters_out[fr] = (int16_t)res[f];
-                    uint8_t* dst = p.hard_out + (size_t)fr * p.hard_stride;
-                    for (int b = tid; b < kbytes; b += kLdpcThreads) {
-                        const int g = b / 45, k = b - g * 45;
-                        const uint32_t word = HD[(f * p.ngroups + g) * kBitWords + (k >> 2)];
-                        dst[b] = (uint8_t)(__brev((word >> (8 * (k & 3))) & 0xFFu) >> 24);
-                    }
                     if (p.llr_out) {
                         int8_t* lo = p.llr_out + (size_t)fr * N;
                         const uint8_t* vb = reinterpret_cast<const uint8_t*>(vdata) + f;
@@ -480,91 +502,93 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                 uint32_t pnext = 0, pnext_b = 0;   // parity LLR pair of the next layer's own parity bit (FIRST: raw bytes of A, B)
 #pragma unroll
                 for (int x = 0; x < MW; ++x) mw[x] = 0;
-                if (active) {
-                    psec = unpack_lo(X[j]);    // pty[q-1][j-1]; thread 0 reads the +127 stand-in of the missing link
-                    if (FIRST) {
-                        pnext = STREAMED ? (uint8_t)__ldcg(colA) : (uint8_t)__ldg(colA);
-                        pnext_b = STREAMED ? (uint8_t)__ldcg(colB) : (uint8_t)__ldg(colB);
-                    } else {
-                        pnext = __ldcg(&wpty[j]);
+                // running pointers: this thread's message record and own parity LLR pair of the layer being worked on
+                uint4* rp = wmsg + j;
+                uint16_t* pp = wpty + j;
+                const int8_t* ca = colA;
+                const int8_t* cb = colB;
+                psec = unpack_lo(X[j]);    // pty[q-1][j-1]; thread 0 reads the +127 stand-in of the missing link
+                if (FIRST) {
+                    pnext = STREAMED ? (uint8_t)__ldcg(ca) : (uint8_t)__ldg(ca);
+                    pnext_b = STREAMED ? (uint8_t)__ldcg(cb) : (uint8_t)__ldg(cb);
+                } else {
+                    pnext = __ldcg(pp);
 #pragma unroll
-                        for (int s = 0; s < SG; ++s) nxt[s] = __ldcg(&wmsg[(size_t)s * 360 + j]);
-                    }
+                    for (int s = 0; s < SG; ++s) nxt[s] = __ldcg(rp + s * 360);
                 }
                 // Dependency level of this thread's row inside the layer.  The first pass takes it from the table in
                 // global memory and leaves it in the top byte of the row's message record (the record has at least two
                 // spare bytes), so the later passes get it with the messages: no separate load whose scoreboard slot
                 // the prefetches would share.
-                constexpr int LW = 4 * SG - 1;     // word of the record that carries the level
-                int lev_next = (FIRST && active && p.layer_nlev[0] > 1) ? p.row_level[j] : 0;
+                uint32_t lev_next = (FIRST && p.layer_nlev[0] > 1) ? (uint32_t)p.row_level[j] << 24 : 0u;
                 for (int i = 0; i < q; ++i) {
                     // everything loaded during the previous layer is consumed HERE, before this layer's prefetches
-                    int mylev = lev_next;
-                    if (active) {
-                        if (!FIRST) {
+                    uint32_t keep = lev_next;          // top byte: the row's level
+                    if (!FIRST) {
 #pragma unroll
-                            for (int s = 0; s < SG; ++s) {
-                                if (4 * s + 0 < MW) mw[4 * s + 0] = nxt[s].x;
-                                if (4 * s + 1 < MW) mw[4 * s + 1] = nxt[s].y;
-                                if (4 * s + 2 < MW) mw[4 * s + 2] = nxt[s].z;
-                                if (4 * s + 3 < MW) mw[4 * s + 3] = nxt[s].w;
-                            }
-                            mylev = (int)(nxt[SG - 1].w >> 24);
+                        for (int s = 0; s < SG; ++s) {
+                            if (4 * s + 0 < MW) mw[4 * s + 0] = nxt[s].x;
+                            if (4 * s + 1 < MW) mw[4 * s + 1] = nxt[s].y;
+                            if (4 * s + 2 < MW) mw[4 * s + 2] = nxt[s].z;
+                            if (4 * s + 3 < MW) mw[4 * s + 3] = nxt[s].w;
                         }
-                        // pty[q-1][j] was updated in layer 0 by thread j+1 (at least one barrier ago: layer_sync)
-                        const uint32_t pw = FIRST ? ((pnext | (pnext_b << 8)) ^ 0x8080u) : pnext;
-                        pown = unpack_lo(i == q - 1 ? (uint32_t)X[j + 1] : pw);
-                        if (i + 1 < q) {   // prefetch the next layer's row while this one computes
-                            if (FIRST) {
-                                pnext = STREAMED ? (uint8_t)__ldcg(colA + i + 1) : (uint8_t)__ldg(colA + i + 1);
-                                pnext_b = STREAMED ? (uint8_t)__ldcg(colB + i + 1) : (uint8_t)__ldg(colB + i + 1);
-                            } else {
-                                pnext = __ldcg(&wpty[360 * (i + 1) + j]);
+                        keep = nxt[SG - 1].w;
+                    }
+                    // pty[q-1][j] was updated in layer 0 by thread j+1 (at least one barrier ago: layer_sync)
+                    const uint32_t pw = FIRST ? ((pnext | (pnext_b << 8)) ^ 0x8080u) : pnext;
+                    pown = unpack_lo(i == q - 1 ? (uint32_t)X[j + 1] : pw);
+                    if (i + 1 < q) {   // prefetch the next layer's row while this one computes
+                        if (FIRST) {
+                            pnext = STREAMED ? (uint8_t)__ldcg(ca + 1) : (uint8_t)__ldg(ca + 1);
+                            pnext_b = STREAMED ? (uint8_t)__ldcg(cb + 1) : (uint8_t)__ldg(cb + 1);
+                        } else {
+                            pnext = __ldcg(pp + 360);
 #pragma unroll
-                                for (int s = 0; s < SG; ++s) nxt[s] = __ldcg(&wmsg[((size_t)(i + 1) * SG + s) * 360 + j]);
-                            }
+                            for (int s = 0; s < SG; ++s) nxt[s] = __ldcg(rp + (SG + s) * 360);
                         }
                     }
-                    const int cnt = RAGGED ? (int)p.layer_off[i + 1] - (int)p.layer_off[i] : CNT;
-                    const int nlev = p.layer_nlev[i];
-                    if (FIRST) lev_next = (i + 1 < q && active && p.layer_nlev[i + 1] > 1) ? p.row_level[(i + 1) * 360 + j] : 0;
                     link_addresses(i);
+                    const int cnt = RAGGED ? (int)(lw0 >> 16) : CNT;
+                    const int nlev = (int)(lw0 & 0xFFu);
+                    if (FIRST) lev_next = (i + 1 < q && p.layer_nlev[i + 1] > 1) ? (uint32_t)p.row_level[(i + 1) * 360 + j] << 24 : 0u;
                     if (nlev == 1) {
-                        if (active) row_update<CNT, FIRST, RAGGED>(off, cnt, mw, pown, psec);
+                        row_update<CNT, FIRST, RAGGED>(off, cnt, mw, pown, psec, keep);
                         // barriers separate layers only where a later layer touches a bit group that a layer since the
                         // last barrier also touches (rows on disjoint bits commute)
-                        if (p.layer_sync[i]) __syncthreads();
+                        if (lw0 & 0x100u) __syncthreads();
                     } else {
+                        const int mylev = (int)(keep >> 24);
                         for (int lvl = 0; lvl < nlev; ++lvl) {
-                            if (active && mylev == lvl) row_update<CNT, FIRST, RAGGED>(off, cnt, mw, pown, psec);
+                            if (mylev == lvl) row_update<CNT, FIRST, RAGGED>(off, cnt, mw, pown, psec, keep);
                             __syncthreads();
                         }
                     }
                     // write the row's messages back; retire the parity LLR that just got its last update
-                    if (active) {
 #pragma unroll
-                        for (int s = 0; s < SG; ++s) {
-                            uint4 o;
-                            o.x = (4 * s + 0 < MW) ? mw[4 * s + 0] : 0u;
-                            o.y = (4 * s + 1 < MW) ? mw[4 * s + 1] : 0u;
-                            o.z = (4 * s + 2 < MW) ? mw[4 * s + 2] : 0u;
-                            o.w = (4 * s + 3 < MW) ? mw[4 * s + 3] : 0u;
-                            if (s == SG - 1) o.w = (o.w & 0x00FFFFFFu) | ((uint32_t)mylev << 24);
-                            __stcg(&wmsg[((size_t)i * SG + s) * 360 + j], o);
-                        }
-                        if (i == 0) {
-                            if (j > 0) X[j] = (uint16_t)pack_pair(psec);   // pty[q-1][j-1], updated again in layer q-1
-                        } else {
-                            __stcg(&wpty[360 * (i - 1) + j], (uint16_t)pack_pair(psec));
-                        }
+                    for (int s = 0; s < SG; ++s) {
+                        uint4 o;
+                        o.x = (4 * s + 0 < MW) ? mw[4 * s + 0] : 0u;
+                        o.y = (4 * s + 1 < MW) ? mw[4 * s + 1] : 0u;
+                        o.z = (4 * s + 2 < MW) ? mw[4 * s + 2] : 0u;
+                        o.w = (4 * s + 3 < MW) ? mw[4 * s + 3] : 0u;
+                        if (s == SG - 1 && 4 * s + 3 >= MW) o.w = keep & 0xFF000000u;   // (else row_update kept it)
+                        __stcg(rp + s * 360, o);
                     }
+                    if (i == 0)
+                        X[j] = (uint16_t)pack_pair(psec);     // pty[q-1][j-1], updated again in layer q-1 (X[0]: scratch of thread 0)
+                    else
+                        __stcg(pp - 360, (uint16_t)pack_pair(psec));
                     if (i + 1 < q) psec = pown;
+                    rp += SG * 360;
+                    pp += 360;
+                    ca += 1;
+                    cb += 1;
                 }
                 // after the last layer: psec = pty[q-2][j] (stored above), pown = pty[q-1][j], both final for this pass
-                if (active) {
+                {
                     const uint16_t pk = (uint16_t)pack_pair(pown);
                     X[j + 1] = pk;
-                    __stcg(&wpty[360 * (q - 1) + j], pk);
+                    __stcg(pp - 360, pk);
                 }
             };
             if (n == 0) pass(std::true_type{});
