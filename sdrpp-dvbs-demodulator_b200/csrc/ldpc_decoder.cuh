@@ -75,7 +75,7 @@ struct LdpcArgs {
 inline size_t ldpc_workspace_bytes(const LdpcDev& c) {
     // message records, parity LLR pairs; second-generation kernel: also the bit planes of the full termination test
     size_t b = (size_t)c.q * c.sg * 360 * 16 + (((size_t)c.R * 2 + 15) & ~(size_t)15);
-    if (c.v2) b += (size_t)2 * (c.ngroups + c.q) * kBitWords * 4;
+    if (c.v2) b += (size_t)2 * (c.ngroups + c.q) * kBitWords * 4 + 32 + (size_t)kLdpcThreads * 16;   // + per-thread constants
     return (b + 255) & ~(size_t)255;
 }
 inline size_t ldpc_smem_bytes(const LdpcDev& c) {

@@ -137,9 +137,11 @@ __device__ __forceinline__ void exclusive_min(const uint32_t (&a)[D], uint32_t (
 //   m' = -om if an odd number of the other t is negative, else min(om, 31);  llr' = sat8(t + m')
 // keep: word whose upper half is stored in the upper half of the last message word when the number of slots is odd
 //       (the record's spare bytes; the caller keeps the row level there).
+// m1  : 0xFFFFFFFF in a register the compiler cannot see through, so that 64 - bm is issued as a multiply-add on
+//       the FMA pipe (as a subtraction ptxas puts it on the ALU pipe, which is the one this kernel saturates).
 template <int CNT, bool FIRST, bool RAGGED>
 __device__ __forceinline__ void row_update(const uint32_t (&off)[CNT], int cnt, uint32_t (&mw)[(CNT + 3) / 2],
-                                           uint32_t& pown, uint32_t& psec, uint32_t keep) {
+                                           uint32_t& pown, uint32_t& psec, uint32_t keep, uint32_t m1) {
     constexpr int D = CNT + 2;
     uint32_t tu[D], a[D], ex[D];
     // bit 7 of tu is set for t >= 0.  The product of the OTHER signs of link k is negative iff
@@ -171,7 +173,8 @@ __device__ __forceinline__ void row_update(const uint32_t (&off)[CNT], int cnt, 
         const uint32_t bias = neg * 0xFFFEFFFFu + kP32;                // 32 + [neg] per lane (0xFFFF * 0xFFFEFFFF = 1)
         const uint32_t bm = addmin(om ^ neg, bias, kP63);              // m' + 32 = 32 - om | min(32 + om, 63)
         const uint32_t un = addmin_relu(tu[c] + bm, kM32, kC255);      // llr' = sat8(t + m')
-        const uint32_t beta = kP64 - bm;                               // 32 - m'
+        uint32_t beta;                                                 // 32 - m' = 64 - bm
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(beta) : "r"(bm), "r"(m1), "r"(kP64));
         if (c < CNT) {
             if (!RAGGED || c < cnt) sts_u16(off[c], pack_pair(un));
         } else if (c == CNT) {
@@ -263,14 +266,23 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
     // needs no "row exists" predicate anywhere.  Everything that must count rows once uses `active`.
     const int j = active ? tid : 359;
     const uint32_t vbase = (uint32_t)__cvta_generic_to_shared(vdata);
-    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(desc);
-    const uint32_t j2 = 2u * (uint32_t)j;
+    uint32_t dbase = (uint32_t)__cvta_generic_to_shared(desc);
+    uint32_t j2 = 2u * (uint32_t)j;
+    uint32_t xaddr = (uint32_t)__cvta_generic_to_shared(X) + j2;   // shared address of X[j]
+    uint32_t m1 = 0xFFFFFFFFu;
     uint4* wmsg = reinterpret_cast<uint4*>(p.workspace + (size_t)blockIdx.x * p.ws_stride);
     uint16_t* wpty = reinterpret_cast<uint16_t*>(p.workspace + (size_t)blockIdx.x * p.ws_stride + (size_t)q * SG * 360 * 16);
     // bit planes of the full termination test (hard decisions, 360 bits per group in 13 words): in the workspace too --
     // with the screen the full test runs about twice per frame, and without the planes a third CTA fits on the SM
     uint32_t* HD = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(wpty) + (((size_t)R * 2 + 15) & ~(size_t)15));  // [2][ngroups][13]
     uint32_t* HP = HD + 2 * p.ngroups * kBitWords;                                                                       // [2][q][13]
+    {   // Per-thread constants that ptxas would otherwise rematerialise from %tid and the shared-window base in every
+        // layer (it does so under the register limit of the three-CTA variants): a round trip through memory makes
+        // them plain values.  The words lie behind the bit planes in this CTA's workspace.
+        volatile uint4* opq = reinterpret_cast<volatile uint4*>(HP + 2 * q * kBitWords + 4) + tid;
+        opq->x = j2; opq->y = xaddr; opq->z = dbase; opq->w = m1;
+        j2 = opq->x; xaddr = opq->y; dbase = opq->z; m1 = opq->w;
+    }
     for (int x = tid; x < q * DW; x += kLdpcThreads) {
         const int i = x / DW, w = x - i * DW;
         const int loff = p.layer_off[i], cnt = (int)p.layer_off[i + 1] - loff;
@@ -500,6 +512,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                 uint32_t mw[MW];
                 uint4 nxt[SG];
                 uint32_t pnext = 0, pnext_b = 0;   // parity LLR pair of the next layer's own parity bit (FIRST: raw bytes of A, B)
+                uint32_t pprev = 0;
 #pragma unroll
                 for (int x = 0; x < MW; ++x) mw[x] = 0;
                 // running pointers: this thread's message record and own parity LLR pair of the layer being worked on
@@ -507,7 +520,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                 uint16_t* pp = wpty + j;
                 const int8_t* ca = colA;
                 const int8_t* cb = colB;
-                psec = unpack_lo(X[j]);    // pty[q-1][j-1]; thread 0 reads the +127 stand-in of the missing link
+                psec = unpack_lo(lds_u16(xaddr));    // X[j] = pty[q-1][j-1]; thread 0 reads the +127 stand-in of the missing link
                 if (FIRST) {
                     pnext = STREAMED ? (uint8_t)__ldcg(ca) : (uint8_t)__ldg(ca);
                     pnext_b = STREAMED ? (uint8_t)__ldcg(cb) : (uint8_t)__ldg(cb);
@@ -536,7 +549,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                     }
                     // pty[q-1][j] was updated in layer 0 by thread j+1 (at least one barrier ago: layer_sync)
                     const uint32_t pw = FIRST ? ((pnext | (pnext_b << 8)) ^ 0x8080u) : pnext;
-                    pown = unpack_lo(i == q - 1 ? (uint32_t)X[j + 1] : pw);
+                    pown = unpack_lo(i == q - 1 ? lds_u16(xaddr + 2) : pw);   // X[j + 1]
                     if (i + 1 < q) {   // prefetch the next layer's row while this one computes
                         if (FIRST) {
                             pnext = STREAMED ? (uint8_t)__ldcg(ca + 1) : (uint8_t)__ldg(ca + 1);
@@ -552,14 +565,14 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                     const int nlev = (int)(lw0 & 0xFFu);
                     if (FIRST) lev_next = (i + 1 < q && p.layer_nlev[i + 1] > 1) ? (uint32_t)p.row_level[(i + 1) * 360 + j] << 24 : 0u;
                     if (nlev == 1) {
-                        row_update<CNT, FIRST, RAGGED>(off, cnt, mw, pown, psec, keep);
+                        row_update<CNT, FIRST, RAGGED>(off, cnt, mw, pown, psec, keep, m1);
                         // barriers separate layers only where a later layer touches a bit group that a layer since the
                         // last barrier also touches (rows on disjoint bits commute)
                         if (lw0 & 0x100u) __syncthreads();
                     } else {
                         const int mylev = (int)(keep >> 24);
                         for (int lvl = 0; lvl < nlev; ++lvl) {
-                            if (mylev == lvl) row_update<CNT, FIRST, RAGGED>(off, cnt, mw, pown, psec, keep);
+                            if (mylev == lvl) row_update<CNT, FIRST, RAGGED>(off, cnt, mw, pown, psec, keep, m1);
                             __syncthreads();
                         }
                     }
@@ -575,19 +588,21 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                         __stcg(rp + s * 360, o);
                     }
                     if (i == 0)
-                        X[j] = (uint16_t)pack_pair(psec);     // pty[q-1][j-1], updated again in layer q-1 (X[0]: scratch of thread 0)
+                        sts_u16(xaddr, pack_pair(psec));      // X[j] = pty[q-1][j-1], updated again in layer q-1 (X[0]: scratch of thread 0)
                     else
                         __stcg(pp - 360, (uint16_t)pack_pair(psec));
-                    if (i + 1 < q) psec = pown;
+                    pprev = psec;
+                    psec = pown;
                     rp += SG * 360;
                     pp += 360;
                     ca += 1;
                     cb += 1;
                 }
-                // after the last layer: psec = pty[q-2][j] (stored above), pown = pty[q-1][j], both final for this pass
+                // after the last layer: pprev = pty[q-2][j] (stored above), pown = pty[q-1][j], both final for this pass
+                psec = pprev;
                 {
                     const uint16_t pk = (uint16_t)pack_pair(pown);
-                    X[j + 1] = pk;
+                    sts_u16(xaddr + 2, pk);
                     __stcg(pp - 360, pk);
                 }
             };
