@@ -98,7 +98,10 @@ int dvbs2fec_decode_batch(dvbs2fec_handle* h, const int8_t* llr, int n, uint8_t*
 int dvbs2fec_decode_plframes(dvbs2fec_handle* h, const float* plframes, int n, uint8_t* bb_out,
                              dvbs2fec_result* results);
 /* device-resident variant on the handle's first device: all pointers are device pointers, work is
- * enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) and NOT synchronised. */
+ * enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) and NOT synchronised.  The call owns a
+ * scratch area of its own (never shared with the synchronous entry points); calls issued on different streams
+ * are chained on the device through an event, so they may be issued freely but do not overlap each other.  The
+ * caller must keep d_llr, d_bb_out and d_results alive until its stream has passed the enqueued work. */
 int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n, uint8_t* d_bb_out,
                                  dvbs2fec_result* d_results, void* cuda_stream);
 /* number of kernel launches the last decode_batch* call on this handle enqueued */

@@ -130,7 +130,11 @@ struct BchTabDev {
 struct DevCtx {
     int device = 0;
     int sms = 0;
-    Slot slot[2 * kSlots];  // [0,kSlots): synchronous entry points; [kSlots,2 kSlots): the frame queue's worker
+    // [0,kSlots): synchronous entry points; [kSlots,2 kSlots): the frame queue's worker; [2 kSlots]: the device entry
+    // point (dvbs2fec_decode_batch_device), whose users on different streams are chained through slot.done
+    Slot slot[2 * kSlots + 1];
+    std::mutex dev_mu;
+    bool dev_used = false;
     std::map<int, CodeDev> codes;
     std::map<int, BchTabDev> bch;           // key m*100+t
     DevBuf<uint16_t> gf_log[2], gf_exp[2];  // [0]: m=14, [1]: m=16
@@ -694,7 +698,7 @@ int dvbs2fec_create(const dvbs2fec_config* cfg, dvbs2fec_handle** out) {
             return fail(DVBS2FEC_ENODEV, "device %d is sm_%d%d; this library carries sm_100a code only", id, prop.major,
                         prop.minor);
         d->sms = prop.multiProcessorCount;
-        for (int k = 0; k < 2 * kSlots; ++k) {
+        for (int k = 0; k < 2 * kSlots + 1; ++k) {
             CU(cudaStreamCreateWithFlags(&d->slot[k].stream, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&d->slot[k].done, cudaEventDisableTiming));
             CU(cudaStreamCreateWithFlags(&d->slot[k].copy, cudaStreamNonBlocking));
@@ -721,7 +725,8 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
     for (auto& dp : h->devs) {
         DevCtx& d = *dp;
         cudaSetDevice(d.device);
-        for (int k = 0; k < 2 * kSlots; ++k) {
+        cudaDeviceSynchronize();   // work enqueued on caller-owned streams by the device entry point
+        for (int k = 0; k < 2 * kSlots + 1; ++k) {
             Slot& s = d.slot[k];
             if (s.copy) cudaStreamSynchronize(s.copy);
             if (s.stream) cudaStreamSynchronize(s.stream);
@@ -938,20 +943,26 @@ int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n,
                                  dvbs2fec_result* d_results, void* cuda_stream) {
     if (!h || !h->configured || !d_llr || n < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
     DevCtx& d = *h->devs[0];
-    Slot& s = d.slot[0];
+    // Own scratch (LDPC workspace, hard decisions, work counter), never shared with the synchronous entry points.
+    // Calls may come on different streams: each one waits for the previous user of the scratch, so they are
+    // serialised on the device (not on the host) and none of them can race on it.
+    Slot& s = d.slot[2 * kSlots];
+    std::lock_guard<std::mutex> serial(d.dev_mu);
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (d.dev_used) CU(cudaStreamWaitEvent(st, s.done, 0));
     const int chunk = std::min(n, std::max(h->cfg.max_batch, 1));
     int rc = reserve_slot(h, d, s, chunk, false, false);
     if (rc) return rc;
     const size_t kb = h->code->kbch / 8;
     h->last_launches = 0;
-    for (int f0 = 0; f0 < n; f0 += chunk) {
+    for (int f0 = 0; f0 < n && !rc; f0 += chunk) {
         int m = std::min(chunk, n - f0);
         rc = enqueue_chain(h, d, s, nullptr, d_llr + (size_t)f0 * h->code->N, m, d_bb_out ? d_bb_out + (size_t)f0 * kb : nullptr,
                            d_results ? d_results + f0 : nullptr, st, &h->last_launches, (uint64_t)f0);
-        if (rc) return rc;
     }
-    return 0;
+    CU(cudaEventRecord(s.done, st));
+    d.dev_used = true;
+    return rc;
 }
 
 static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym, uint64_t tag) {

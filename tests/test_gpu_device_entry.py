@@ -1,0 +1,134 @@
+"""dvbs2fec_decode_batch_device -- the entry point whose time bench.py reports as `value` -- at the bench's own shape:
+thousands of QPSK 1/2 normal frames at Es/N0 2.2 dB resident in device memory, one launch with every CTA of the
+persistent grid handing itself several frame pairs.  Results (LDPC iteration counts, BCH correction counts, BBFRAME
+bytes) are compared with the CPU oracle on the slowest frames and on random ones; the rest is covered by the
+encode -> decode round trip."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orclib
+from fec import pkg
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _pool(modcod, short, n, esn0, seed, ncodes=32):
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(seed)
+    info = pkg.modcod_info(modcod, short)
+    payloads = rng.integers(0, 256, (ncodes, info["kbch"] // 8), dtype=np.uint8)
+    codes = np.stack([pkg.encode_fecframe(modcod, short, p) for p in payloads])
+    a, sigma2 = 1 / np.sqrt(2.0), 1.0 / (2.0 * 10 ** (esn0 / 10.0))
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    cw = torch.from_numpy(codes).to(dev)
+    idx = torch.arange(n, device=dev) % ncodes
+    pool = torch.empty((n, info["nldpc"]), dtype=torch.int8, device=dev)
+    for f0 in range(0, n, 512):
+        sl = idx[f0:f0 + 512]
+        y = (1.0 - 2.0 * cw[sl].float()) * a
+        y += torch.randn(y.shape, generator=g, device=dev) * float(np.sqrt(sigma2))
+        pool[f0:f0 + 512] = torch.clamp(torch.round(4.0 * 2.0 * a * y / sigma2), -127, 127).to(torch.int8)
+    return pool, payloads, idx.cpu().numpy(), info
+
+
+def _oracle_check(short, rate, llr_rows, bb_rows, res_rows, kbch):
+    o = orclib.oracle()
+    want = np.zeros(kbch // 8, np.uint8)
+    for k in range(llr_rows.shape[0]):
+        it, co = C.c_int(), C.c_int()
+        o.orc_decode_frame(short, rate, llr_rows[k].copy(), 25, want, C.byref(it), C.byref(co))
+        assert (int(res_rows["ldpc_iters"][k]), int(res_rows["bch_corr"][k])) == (it.value, co.value), k
+        assert np.array_equal(bb_rows[k], want), k
+
+
+def test_decode_batch_device_at_the_bench_shape():
+    n = 4096
+    pool, payloads, idx, info = _pool(4, False, n, 2.2, 11)
+    dev = pool.device
+    dec = pkg.DVBS2Decoder(devices=[0], max_batch=n, max_trials=25)
+    dec.setDemodParams(4, False, False, 25)
+    d_bb = torch.empty((n, info["kbch"] // 8), dtype=torch.uint8, device=dev)
+    d_res = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    dec.decode_batch_device(pool.data_ptr(), n, d_bb.data_ptr(), d_res.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    res = d_res.cpu().numpy().view(pkg.RESULT_DTYPE).reshape(-1)
+    bb = d_bb.cpu().numpy()
+    it = res["ldpc_iters"].astype(np.int32)
+    # every frame: round trip (a decoded frame is the payload that was encoded)
+    ok = res["bch_corr"] >= 0
+    assert ok.mean() > 0.995
+    assert np.array_equal(bb[ok], payloads[idx][ok])
+    assert 6.5 < np.where(it < 0, 25, it).mean() < 8.5          # the bench's operating point
+    # oracle: the 24 slowest frames, the 8 fastest, 40 random ones
+    order = np.argsort(np.where(it < 0, 26, it), kind="stable")
+    pick = sorted(set(order[-24:].tolist()) | set(order[:8].tolist()) |
+                  set(np.random.default_rng(1).choice(n, 40, replace=False).tolist()))
+    rows = torch.tensor(pick, device=dev)
+    _oracle_check(0, 3, pool[rows].cpu().numpy(), bb[pick], res[pick], info["kbch"])
+    # the same frames again, odd count (last pair has one frame) and a different grid occupancy: identical results
+    m = 1001
+    dec.decode_batch_device(pool.data_ptr(), m, d_bb.data_ptr(), d_res.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    res2 = d_res.cpu().numpy().view(pkg.RESULT_DTYPE).reshape(-1)[:m]
+    assert np.array_equal(res2["ldpc_iters"], res["ldpc_iters"][:m])
+    assert np.array_equal(res2["bch_corr"], res["bch_corr"][:m])
+    assert np.array_equal(d_bb.cpu().numpy()[:m], bb[:m])
+    dec.close()
+
+
+def test_decode_batch_device_high_iteration_regime():
+    """8PSK 3/5 normal (code n3/5) near threshold: most frames need 15-25 iterations, some fail (config 2's regime)."""
+    n = 600
+    pool, payloads, idx, info = _pool(5, False, n, 2.5, 12)    # QPSK-style LLRs on the n3/5 code, just above its threshold
+    dev = pool.device
+    dec = pkg.DVBS2Decoder(devices=[0], max_batch=n, max_trials=25)
+    dec.setDemodParams(5, False, False, 25)
+    d_bb = torch.empty((n, info["kbch"] // 8), dtype=torch.uint8, device=dev)
+    d_res = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    dec.decode_batch_device(pool.data_ptr(), n, d_bb.data_ptr(), d_res.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    res = d_res.cpu().numpy().view(pkg.RESULT_DTYPE).reshape(-1)
+    it = res["ldpc_iters"].astype(np.int32)
+    assert np.where(it < 0, 25, it).mean() > 9
+    pick = sorted(np.random.default_rng(2).choice(n, 24, replace=False).tolist())
+    rows = torch.tensor(pick, device=dev)
+    _oracle_check(0, 4, pool[rows].cpu().numpy(), d_bb.cpu().numpy()[pick], res[pick], info["kbch"])
+    dec.close()
+
+
+def test_device_entry_on_two_streams_and_between_sync_calls():
+    """a device call on one stream, another on a second stream and a synchronous host call issued while
+    they may still be running must not share scratch buffers: every result equals the serial one."""
+    n = 512
+    pool, payloads, idx, info = _pool(4, True, n, 2.6, 13)
+    dev = pool.device
+    dec = pkg.DVBS2Decoder(devices=[0], max_batch=n, max_trials=25)
+    dec.setDemodParams(4, True, False, 25)
+    kb = info["kbch"] // 8
+    host_llr = pool.cpu().numpy()
+    want_bb, want_res = dec.decode_batch(host_llr)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for rep in range(3):
+        a_bb = torch.zeros((n, kb), dtype=torch.uint8, device=dev)
+        a_res = torch.zeros((n, 16), dtype=torch.uint8, device=dev)
+        b_bb = torch.zeros((n, kb), dtype=torch.uint8, device=dev)
+        b_res = torch.zeros((n, 16), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        dec.decode_batch_device(pool.data_ptr(), n, a_bb.data_ptr(), a_res.data_ptr(), s1.cuda_stream)
+        dec.decode_batch_device(pool.data_ptr(), n - 7, b_bb.data_ptr(), b_res.data_ptr(), s2.cuda_stream)
+        c_bb, c_res = dec.decode_batch(host_llr[: 100 + rep])      # synchronous entry point in between
+        torch.cuda.synchronize()
+        outs.append((a_bb.cpu().numpy(), a_res.cpu().numpy().view(pkg.RESULT_DTYPE).reshape(-1),
+                     b_bb.cpu().numpy(), b_res.cpu().numpy().view(pkg.RESULT_DTYPE).reshape(-1), c_bb, c_res))
+    for a_bb, a_res, b_bb, b_res, c_bb, c_res in outs:
+        assert np.array_equal(a_bb, want_bb) and np.array_equal(a_res["ldpc_iters"], want_res["ldpc_iters"])
+        assert np.array_equal(b_bb[: n - 7], want_bb[: n - 7]) and np.array_equal(b_res["bch_corr"][: n - 7], want_res["bch_corr"][: n - 7])
+        assert np.array_equal(c_bb, want_bb[: len(c_bb)]) and np.array_equal(c_res["ldpc_iters"], want_res["ldpc_iters"][: len(c_bb)])
+    dec.close()

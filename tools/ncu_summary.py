@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """Turn an .ncu-rep (one kernel, `--set full`) into the short summary kept under profiles/.
-    python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/r01_ldpc  -> .md and .json"""
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/r02_ldpc [frames [links_per_frame mean_iters]]  -> .md and .json
+With frames, links per frame and the mean iteration count of the profiled launch it also derives what bench.py
+needs for its on-chip roofline: ALU-pipe warp instructions and shared-memory wavefronts per edge update."""
 import csv
 import io
 import json
@@ -31,8 +33,10 @@ KEYS = {
     "lts__t_bytes.sum": "l2_bytes",
     "lts__t_sector_hit_rate.pct": "l2_hit_rate_pct",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct",
+    "sm__cycles_active.sum": "sm_cycles_active_sum",
+    "sm__cycles_elapsed.avg.per_second": "sm_clock_hz",
 }
-UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "byte": 1.0,
+UNIT = {"Ghz": 1e9, "Mhz": 1e6, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "byte": 1.0,
         "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "second": 1.0}
 
 
@@ -60,6 +64,19 @@ def main():
     if len(sys.argv) > 3:
         res["frames_in_launch"] = int(sys.argv[3])
         res["dram_traffic_bytes_per_frame"] = res.get("dram_traffic_bytes", 0.0) / int(sys.argv[3])
+    if len(sys.argv) > 5:
+        links, iters = int(sys.argv[4]), float(sys.argv[5])
+        edge_updates = res["frames_in_launch"] * links * iters
+        res["links_per_frame"], res["mean_iters"], res["edge_updates_in_launch"] = links, iters, edge_updates
+        # pipe_alu: per cent of the ALU pipe's peak (2 warp instructions per clock per SM, profiles/r02_onchip_peaks.json)
+        alu_instr = res["alu_pipe_pct"] / 100.0 * 2.0 * res["sm_cycles_active_sum"]
+        res["alu_warp_instr_in_launch"] = alu_instr
+        res["alu_warp_instr_per_edge_update"] = alu_instr / edge_updates
+        res["warp_instr_per_edge_update"] = res["warp_instructions"] / edge_updates
+        res["smem_wavefronts_per_edge_update"] = res["shared_wavefronts"] / edge_updates
+    for k in ("sm_clock_hz",):
+        if k in res and res.get(k + "_unit"):
+            res.pop(k + "_unit")
     json.dump(res, open(out + ".json", "w"), indent=1)
     with open(out + ".md", "w") as f:
         f.write("# ncu --set full summary: %s\n\nsource: `%s` (one launch, `--clock-control none`)\n\n| metric | value |\n|---|---|\n" % (res["kernel"][:80], rep))
