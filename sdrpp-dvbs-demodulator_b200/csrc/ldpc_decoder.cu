@@ -15,6 +15,7 @@ namespace s2 {
 // Everything a launch needs that depends only on the configured code: built by ldpc_prepare, read by ldpc_launch.
 struct LdpcPlan {
     bool v2 = false;
+    int threads = kLdpcThreads;
     KernelFn fn1[2] = {nullptr, nullptr};    // [streamed]
     KernelFn2 fn2[2] = {nullptr, nullptr};
     LdpcParams p1;
@@ -45,6 +46,14 @@ const Variant2* pick2(int max_cnt) {
             if (parts[k][i].cnt >= max_cnt) return &parts[k][i];
     return nullptr;
 }
+const VariantL* pickl(int max_cnt) {
+    const VariantL* parts[2] = {kLdpc2lVariantsA, kLdpc2lVariantsB};
+    const int counts[2] = {kLdpc2lVariantsA_n, kLdpc2lVariantsB_n};
+    for (int k = 0; k < 2; ++k)
+        for (int i = 0; i < counts[k]; ++i)
+            if (parts[k][i].cnt == max_cnt) return &parts[k][i];
+    return nullptr;
+}
 bool is_uniform(const LdpcDev& c, int cnt) {
     bool uniform = cnt == c.max_cnt;
     for (int i = 0; i < c.q && uniform; ++i) uniform = (c.layer_off[i + 1] - c.layer_off[i]) == cnt;
@@ -57,6 +66,11 @@ KernelFn pick_fn(const LdpcDev& c, bool streamed) {
     return (is_uniform(c, v->cnt) && v->uniform[0][0][0]) ? v->uniform[streamed][ch][oc] : v->ragged[streamed][ch][oc];
 }
 KernelFn2 pick_fn2(const LdpcDev& c, bool streamed) {
+    if (c.lanes2) {
+        const VariantL* v = pickl(c.max_cnt);
+        if (!v) return nullptr;
+        return (is_uniform(c, v->cnt) && v->uniform[0]) ? v->uniform[streamed] : v->ragged[streamed];
+    }
     const Variant2* v = pick2(c.max_cnt);
     if (!v) return nullptr;
     const int oc = c.occ3 ? 1 : 0;
@@ -178,6 +192,25 @@ int ldpc_slot_groups(int max_cnt) {
     const Variant* v = pick(max_cnt);
     return v ? (v->cnt + 2 + 7) / 8 : 0;
 }
+int ldpc_slot_groups_for(int max_cnt, bool lanes2) {
+    if (!lanes2) return ldpc_slot_groups(max_cnt);
+    if (!pickl(max_cnt)) return 0;
+    const int dh = (max_cnt + 1) / 2 + 1;     // slots per half row
+    return 2 * ((dh + 7) / 8);
+}
+
+// Codes that run faster with two threads per row (ldpc_v2l.cuh).  Measured with tools/modcod_sweep.py (2048 normal /
+// 8192 short frames, fixed noise) against the one-thread-per-row kernel: n3/4 -8 %, n4/5 -8 %, n5/6 -9 %, n8/9 -11 %,
+// n9/10 -15 %, s5/6 -14 %, s8/9 -11 % time; the codes with up to eleven data links per row lose 5-30 % (the two
+// shuffles and the longer minimum chain outweigh the shorter level steps).  DVBS2FEC_LDPC_LANES2=0|1 overrides (1:
+// every code that has such a kernel).  Index = code table order B1..B11, C1..C10.
+bool ldpc_use_lanes2(int code_index) {
+    static const bool table[21] = {false, false, false, false, false, false, true,  true,  true,  true,  true,
+                                   false, false, false, false, false, false, false, false, true,  true};
+    static const int force = env_int("DVBS2FEC_LDPC_LANES2", -1);
+    if (force >= 0) return force != 0;
+    return code_index >= 0 && code_index < 21 && table[code_index];
+}
 
 int ldpc_prepare(LdpcDev& c) {
     ldpc_release(c);
@@ -188,10 +221,10 @@ int ldpc_prepare(LdpcDev& c) {
     pl->v2 = c.v2;
     cudaError_t e = cudaSuccess;
     if (c.v2) {
-        const Variant2* v = pick2(c.max_cnt);
         pl->fn2[0] = pick_fn2(c, false);
         pl->fn2[1] = pick_fn2(c, true);
-        if (!v || !pl->fn2[0] || !pl->fn2[1] || (v->cnt + 2 + 7) / 8 != c.sg) {
+        pl->threads = c.lanes2 ? 736 : kLdpcThreads;
+        if (!pl->fn2[0] || !pl->fn2[1] || ldpc_slot_groups_for(c.max_cnt, c.lanes2) != c.sg) {
             delete pl;
             return (int)cudaErrorInvalidValue;
         }
@@ -248,7 +281,7 @@ int ldpc_max_ctas_per_sm(const LdpcDev& c) {
     if (!c.plan) return 0;
     int n = 0;
     if (c.plan->v2)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, c.plan->fn2[0], kLdpcThreads, c.plan->smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, c.plan->fn2[0], c.plan->threads, c.plan->smem);
     else
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, c.plan->fn1[0], kLdpcThreads, c.plan->smem);
     return n;
@@ -263,7 +296,7 @@ int ldpc_launch(const LdpcArgs& a, int grid, cudaStream_t stream) {
         p.nframes = a.nframes; p.max_trials = a.max_trials; p.hard_stride = a.hard_stride;
         p.llr_in = a.llr_in; p.hard_out = a.hard_out; p.iters_out = a.iters_out; p.llr_out = a.llr_out;
         p.workspace = a.workspace; p.work_counter = a.work_counter; p.arrived = a.arrived;
-        pl->fn2[st]<<<grid, kLdpcThreads, pl->smem, stream>>>(p);
+        pl->fn2[st]<<<grid, pl->threads, pl->smem, stream>>>(p);
     } else {
         LdpcParams p = pl->p1;
         p.nframes = a.nframes; p.max_trials = a.max_trials; p.hard_stride = a.hard_stride;

@@ -40,6 +40,7 @@ struct LdpcDev {
     bool chains;   // run chained layers in three phases (ldpc_chains_pay_off(code index))
     bool occ3;     // kernel variant compiled for one more CTA per SM than the default (ldpc_ctas_wanted3(code index))
     bool v2;       // second-generation kernel (ldpc_v2.cuh) instead of the first (ldpc_kernels.cuh): ldpc_use_v2(code index)
+    bool lanes2;   // ... in its two-threads-per-row form (ldpc_v2l.cuh): ldpc_use_lanes2(code index); implies v2
     const LdpcPlan* plan;   // ldpc_prepare(); owned by the caller of ldpc_prepare (ldpc_release)
     // HOST pointers: copied into the kernel parameter block (constant bank) at every launch
     const uint32_t* links;       // per layer: (group << 16) | shift
@@ -53,6 +54,9 @@ int ldpc_slot_groups(int max_cnt);
 bool ldpc_chains_pay_off(int code_index);   // measured per code, see ldpc_decoder.cu
 bool ldpc_ctas_wanted3(int code_index);     // likewise
 bool ldpc_use_v2(int code_index);           // likewise
+bool ldpc_use_lanes2(int code_index);       // likewise
+// uint4 message slot-groups per row for the given kernel choice (0 = unsupported)
+int ldpc_slot_groups_for(int max_cnt, bool lanes2);
 // Builds the parameter block (layer tables, barrier elision, chains) and opts the kernel in to the device's full
 // shared memory, once; ldpc_launch then only patches the per-launch pointers.  Returns cudaError_t as int.
 int ldpc_prepare(LdpcDev& code);
@@ -75,12 +79,13 @@ struct LdpcArgs {
 inline size_t ldpc_workspace_bytes(const LdpcDev& c) {
     // message records, parity LLR pairs; second-generation kernel: also the bit planes of the full termination test
     size_t b = (size_t)c.q * c.sg * 360 * 16 + (((size_t)c.R * 2 + 15) & ~(size_t)15);
-    if (c.v2) b += (size_t)2 * (c.ngroups + c.q) * kBitWords * 4 + 32 + (size_t)kLdpcThreads * 16;   // + per-thread constants
+    if (c.v2) b += (size_t)2 * (c.ngroups + c.q) * kBitWords * 4 + 32 + (size_t)768 * 16;   // + per-thread constants
     return (b + 255) & ~(size_t)255;
 }
 inline size_t ldpc_smem_bytes(const LdpcDev& c) {
     // LLR pairs, bit planes, slack; with chained layers also their 360 x 16 B hand-over words
     // second generation: LLR pairs + the 361 pty[q-1][.] pairs handed between neighbouring threads + layer descriptors
+    if (c.v2 && c.lanes2) return (size_t)c.K * 2 + 768 + (size_t)c.q * (4 + 2 * ((2 * ((c.max_cnt + 1) / 2) + 3) & ~3)) * 4 + 64;
     if (c.v2) return (size_t)c.K * 2 + 768 + (size_t)c.q * ((1 + 2 * c.max_cnt + 3) & ~3) * 4 + 64;
     const size_t base = (size_t)c.K * 2 + (size_t)2 * (c.ngroups + c.q) * kBitWords * 4;
     return c.chains ? ((base + 15) & ~(size_t)15) + 360 * 16 + 64 : base + 64;

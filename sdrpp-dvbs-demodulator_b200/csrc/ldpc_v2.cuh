@@ -71,6 +71,11 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v));
 }
@@ -217,16 +222,125 @@ __device__ __forceinline__ uint32_t harvest8(uint4 w, uint32_t& nzacc) {
 }
 // bit planes of n360 groups of 360 LLR pairs starting at src: plane A at H[g*13 words], plane B at
 // H[(gstride + g)*13 words], byte k of a group = bits 8k..8k+7
-template <bool GLOBAL>
+template <bool GLOBAL, int THREADS>
 __device__ __forceinline__ void harvest_planes(const uint4* src, int n360, uint32_t* H, int gstride, int tid,
                                                uint32_t& nzacc) {
     uint8_t* Hb = reinterpret_cast<uint8_t*>(H);
-    for (int t = tid; t < n360 * 45; t += kLdpcThreads) {
+    for (int t = tid; t < n360 * 45; t += THREADS) {
         uint4 w = GLOBAL ? __ldcg(src + t) : src[t];
         uint32_t bits = harvest8(w, nzacc);
         int g = t / 45, k = t - g * 45;
         __stcg(&Hb[g * (kBitWords * 4) + k], (uint8_t)bits);
         __stcg(&Hb[(gstride + g) * (kBitWords * 4) + k], (uint8_t)(bits >> 8));
+    }
+}
+
+// The full LDPCDecoder::bad (layered_decoder.hh:28-45) for both frames of the pair: a row is bad when its sign product
+// is not positive, i.e. odd parity of hard decisions or any zero LLR.  Hard decisions are gathered into bit planes
+// (parity part from the workspace after a pass, straight from the input before the first one), each layer's 360
+// checks are then 12 words of rotate-and-XOR.  Returns bit f set when frame f is bad.  All threads of the CTA call it.
+template <bool STREAMED, int THREADS>
+__device__ __noinline__ int full_test(const LdpcParams2& p, bool after_pass, const uint16_t* wpty, uint32_t* HP, uint32_t* HD,
+                                      const uint4* vdata4, const int8_t* inA, const int8_t* inB, int* s_bad) {
+    const int tid = threadIdx.x, q = p.q, K = p.K;
+    uint32_t nzacc = 0xFFFFFFFFu;
+    if (after_pass) {
+        harvest_planes<true, THREADS>(reinterpret_cast<const uint4*>(wpty), q, HP, q, tid, nzacc);
+    } else {
+        // parity planes straight from the input: one ballot per layer and frame (a frame that is a codeword before
+        // the first pass is the only way to get here); thread r < 360 reads column r: pty[i][r] = v[K + q r + i]
+        const int wid = tid >> 5, lane = tid & 31;
+        if (wid < 12) {
+            const bool row = tid < 360;
+            const int8_t* ca = inA + K + (size_t)q * (row ? tid : 0);
+            const int8_t* cb = inB + K + (size_t)q * (row ? tid : 0);
+            for (int i = 0; i < q; ++i) {
+                uint32_t w = 0x8181u;
+                if (row) {
+                    const uint32_t a = STREAMED ? (uint8_t)__ldcg(ca + i) : (uint8_t)__ldg(ca + i);
+                    const uint32_t b = STREAMED ? (uint8_t)__ldcg(cb + i) : (uint8_t)__ldg(cb + i);
+                    w = (a | (b << 8)) ^ 0x8080u;
+                }
+                const unsigned ba = __ballot_sync(0xFFFFFFFFu, !(w & 0x80u));
+                const unsigned bb = __ballot_sync(0xFFFFFFFFu, !(w & 0x8000u));
+                if (lane == 0) {
+                    __stcg(&HP[i * kBitWords + wid], ba);
+                    __stcg(&HP[(q + i) * kBitWords + wid], bb);
+                }
+                if ((w & 0xFFu) == 0x80u) nzacc &= ~0x00800080u;
+                if ((w & 0xFF00u) == 0x8000u) nzacc &= ~0x80008000u;
+            }
+        }
+    }
+    harvest_planes<false, THREADS>(vdata4, p.ngroups, HD, p.ngroups, tid, nzacc);
+    if (tid < 2) s_bad[tid] = 0;
+    __syncthreads();
+    if (~nzacc & 0x00800080u) atomicOr(&s_bad[0], 1);
+    if (~nzacc & 0x80008000u) atomicOr(&s_bad[1], 1);
+    for (int task = tid; task < q * 12; task += THREADS) {
+        const int ii = task / 12, w = task - ii * 12;
+        const int loff = p.layer_off[ii], cnt = (int)p.layer_off[ii + 1] - loff;
+        uint32_t sA = __ldcg(&HP[ii * kBitWords + w]), sB = __ldcg(&HP[(q + ii) * kBitWords + w]);
+        if (ii > 0) {
+            sA ^= __ldcg(&HP[(ii - 1) * kBitWords + w]);
+            sB ^= __ldcg(&HP[(q + ii - 1) * kBitWords + w]);
+        } else {  // row (0,j) uses pty[q-1][j-1], row (0,0) has no second parity link
+            const uint32_t* ta = &HP[(q - 1) * kBitWords];
+            const uint32_t* tb = &HP[(2 * q - 1) * kBitWords];
+            sA ^= (__ldcg(ta + w) << 1) | (w ? __ldcg(ta + w - 1) >> 31 : 0u);
+            sB ^= (__ldcg(tb + w) << 1) | (w ? __ldcg(tb + w - 1) >> 31 : 0u);
+        }
+        for (int c = 0; c < cnt; ++c) {
+            // bit (32 w + b) of the row vector is data bit (32 w + b - shift) mod 360 of the group
+            int o = 32 * w + (int)(p.link_add[loff + c] >> 1) - 360;   // (720 - 2 shift) / 2 - 360 = -shift
+            o += (o < 0) ? 360 : 0;
+            const int g = p.link_group[loff + c];
+            sA ^= win360(&HD[g * kBitWords], o);
+            sB ^= win360(&HD[(p.ngroups + g) * kBitWords], o);
+        }
+        if (w == 11) {
+            sA &= 0xFFu;
+            sB &= 0xFFu;
+        }
+        if (sA) atomicOr(&s_bad[0], 1);
+        if (sB) atomicOr(&s_bad[1], 1);
+    }
+    __syncthreads();
+    return (s_bad[0] ? 1 : 0) | (s_bad[1] ? 2 : 0);
+}
+
+// Results of the frames that stop here (bit f of fin): iteration count, MSB-first hard decisions of the K systematic
+// bits (module_dvbs2_demod.cpp:357-360) straight from the LLR pairs (8 pairs = one uint4 give one byte of each frame),
+// optionally the posterior LLRs (what BBFrameLDPC::decode leaves in place).
+template <int THREADS>
+__device__ __noinline__ void emit_results(const LdpcParams2& p, int fin, const int (&res)[2], int fa, int fb, bool after_pass,
+                                          const uint16_t* wpty, const uint4* vdata4, const int8_t* inA, const int8_t* inB) {
+    const int tid = threadIdx.x, q = p.q, K = p.K, N = p.N, R = p.R;
+    const int kbytes = K / 8;
+    for (int b = tid; b < kbytes; b += THREADS) {
+        uint32_t nz = 0xFFFFFFFFu;
+        const uint32_t bits = harvest8(vdata4[b], nz);
+        if (fin & 1) p.hard_out[(size_t)fa * p.hard_stride + b] = (uint8_t)(__brev(bits & 0xFFu) >> 24);
+        if (fin & 2) p.hard_out[(size_t)fb * p.hard_stride + b] = (uint8_t)(__brev((bits >> 8) & 0xFFu) >> 24);
+    }
+    for (int f = 0; f < 2; ++f) {
+        if (!(fin >> f & 1)) continue;
+        const int fr = f ? fb : fa;
+        if (tid == 0) p.iters_out[fr] = (int16_t)res[f];
+        if (p.llr_out) {
+            int8_t* lo = p.llr_out + (size_t)fr * N;
+            const uint8_t* vb = reinterpret_cast<const uint8_t*>(vdata4) + f;
+            for (int x = tid; x < K; x += THREADS) lo[x] = (int8_t)(vb[2 * x] ^ 0x80u);
+            if (after_pass) {
+                for (int x = tid; x < R; x += THREADS) {
+                    const int jj = x / q, ii = x - jj * q;
+                    lo[K + x] = (int8_t)((__ldcg(&wpty[360 * ii + jj]) >> (8 * f)) ^ 0x80u);
+                }
+            } else {
+                const int8_t* in = f ? inB : inA;
+                for (int x = tid; x < R; x += THREADS) lo[K + x] = in[K + x];
+            }
+        }
     }
 }
 
@@ -404,62 +518,8 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
             // ---- LDPCDecoder::bad (layered_decoder.hh:28-45): screen first, full bit-plane test only when the
             //      screen found nothing for a frame that is still iterating
             int bad = (__syncthreads_or(scr & 1) ? 1 : 0) | (__syncthreads_or(scr & 2) ? 2 : 0);
-            if (live & ~bad) {
-                uint32_t nzacc = 0xFFFFFFFFu;
-                if (n > 0) {
-                    harvest_planes<true>(reinterpret_cast<const uint4*>(wpty), q, HP, q, tid, nzacc);
-                } else {
-                    // parity planes straight from the input: one ballot per layer and frame (a frame that is a
-                    // codeword before the first pass is the only way to get here)
-                    const int wid = tid >> 5, lane = tid & 31;
-                    for (int i = 0; i < q; ++i) {
-                        const uint32_t w = active ? in_pair(i) : 0x8181u;
-                        const unsigned ba = __ballot_sync(0xFFFFFFFFu, !(w & 0x80u));
-                        const unsigned bb = __ballot_sync(0xFFFFFFFFu, !(w & 0x8000u));
-                        if (lane == 0) {
-                            __stcg(&HP[i * kBitWords + wid], ba);
-                            __stcg(&HP[(q + i) * kBitWords + wid], bb);
-                        }
-                        if ((w & 0xFFu) == 0x80u) nzacc &= ~0x00800080u;
-                        if ((w & 0xFF00u) == 0x8000u) nzacc &= ~0x80008000u;
-                    }
-                }
-                harvest_planes<false>(reinterpret_cast<const uint4*>(vdata), p.ngroups, HD, p.ngroups, tid, nzacc);
-                if (tid < 2) s_bad[tid] = 0;
-                __syncthreads();
-                if (~nzacc & 0x00800080u) atomicOr(&s_bad[0], 1);
-                if (~nzacc & 0x80008000u) atomicOr(&s_bad[1], 1);
-                for (int task = tid; task < q * 12; task += kLdpcThreads) {
-                    const int ii = task / 12, w = task - ii * 12;
-                    const int loff = p.layer_off[ii], cnt = (int)p.layer_off[ii + 1] - loff;
-                    uint32_t sA = __ldcg(&HP[ii * kBitWords + w]), sB = __ldcg(&HP[(q + ii) * kBitWords + w]);
-                    if (ii > 0) {
-                        sA ^= __ldcg(&HP[(ii - 1) * kBitWords + w]);
-                        sB ^= __ldcg(&HP[(q + ii - 1) * kBitWords + w]);
-                    } else {  // row (0,j) uses pty[q-1][j-1], row (0,0) has no second parity link
-                        const uint32_t* ta = &HP[(q - 1) * kBitWords];
-                        const uint32_t* tb = &HP[(2 * q - 1) * kBitWords];
-                        sA ^= (__ldcg(ta + w) << 1) | (w ? __ldcg(ta + w - 1) >> 31 : 0u);
-                        sB ^= (__ldcg(tb + w) << 1) | (w ? __ldcg(tb + w - 1) >> 31 : 0u);
-                    }
-                    for (int c = 0; c < cnt; ++c) {
-                        // bit (32 w + b) of the row vector is data bit (32 w + b - shift) mod 360 of the group
-                        int o = 32 * w + (int)(p.link_add[loff + c] >> 1) - 360;   // (720 - 2 shift) / 2 - 360 = -shift
-                        o += (o < 0) ? 360 : 0;
-                        const int g = p.link_group[loff + c];
-                        sA ^= win360(&HD[g * kBitWords], o);
-                        sB ^= win360(&HD[(p.ngroups + g) * kBitWords], o);
-                    }
-                    if (w == 11) {
-                        sA &= 0xFFu;
-                        sB &= 0xFFu;
-                    }
-                    if (sA) atomicOr(&s_bad[0], 1);
-                    if (sB) atomicOr(&s_bad[1], 1);
-                }
-                __syncthreads();
-                bad = (s_bad[0] ? 1 : 0) | (s_bad[1] ? 2 : 0);
-            }
+            if (live & ~bad)
+                bad = full_test<STREAMED, kLdpcThreads>(p, n > 0, wpty, HP, HD, reinterpret_cast<const uint4*>(vdata), inA, inB, s_bad);
             // ---- while (bad() && --trials >= 0) update();  (layered_decoder.hh:127-128), per frame
             int fin = 0;
             for (int f = 0; f < 2; ++f) {
@@ -472,35 +532,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                 }
             }
             if (fin) {
-                // results of the frames that stop here: iteration count, MSB-first hard decisions of the K
-                // systematic bits (module_dvbs2_demod.cpp:357-360), optionally the posterior LLRs
-                // hard decisions straight from the LLR pairs: 8 pairs (one uint4) give one byte of each frame
-                const int kbytes = K / 8;
-                for (int b = tid; b < kbytes; b += kLdpcThreads) {
-                    uint32_t nz = 0xFFFFFFFFu;
-                    const uint32_t bits = harvest8(reinterpret_cast<const uint4*>(vdata)[b], nz);
-                    if (fin & 1) p.hard_out[(size_t)fa * p.hard_stride + b] = (uint8_t)(__brev(bits & 0xFFu) >> 24);
-                    if (fin & 2) p.hard_out[(size_t)fb * p.hard_stride + b] = (uint8_t)(__brev((bits >> 8) & 0xFFu) >> 24);
-                }
-                for (int f = 0; f < 2; ++f) {
-                    if (!(fin >> f & 1)) continue;
-                    const int fr = f ? fb : fa;
-                    if (tid == 0) p.iters_out[fr] = (int16_t)res[f];
-                    if (p.llr_out) {
-                        int8_t* lo = p.llr_out + (size_t)fr * N;
-                        const uint8_t* vb = reinterpret_cast<const uint8_t*>(vdata) + f;
-                        for (int x = tid; x < K; x += kLdpcThreads) lo[x] = (int8_t)(vb[2 * x] ^ 0x80u);
-                        if (n > 0) {
-                            for (int x = tid; x < R; x += kLdpcThreads) {
-                                const int jj = x / q, ii = x - jj * q;
-                                lo[K + x] = (int8_t)((__ldcg(&wpty[360 * ii + jj]) >> (8 * f)) ^ 0x80u);
-                            }
-                        } else {
-                            const int8_t* in = f ? inB : inA;
-                            for (int x = tid; x < R; x += kLdpcThreads) lo[K + x] = in[K + x];
-                        }
-                    }
-                }
+                emit_results<kLdpcThreads>(p, fin, res, fa, fb, n > 0, wpty, reinterpret_cast<const uint4*>(vdata), inA, inB);
                 live &= ~fin;
             }
             if (!live) break;

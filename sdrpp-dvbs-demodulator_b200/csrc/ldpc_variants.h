@@ -71,4 +71,13 @@ struct Variant2 {
 extern const Variant2 kLdpc2VariantsA[], kLdpc2VariantsB[], kLdpc2VariantsC[], kLdpc2VariantsD[];
 extern const int kLdpc2VariantsA_n, kLdpc2VariantsB_n, kLdpc2VariantsC_n, kLdpc2VariantsD_n;
 
+// two threads per row (ldpc_v2l.cuh), for the codes with many links per check
+struct VariantL {
+    int cnt;
+    KernelFn2 uniform[2];   // [streamed input]
+    KernelFn2 ragged[2];
+};
+extern const VariantL kLdpc2lVariantsA[], kLdpc2lVariantsB[];
+extern const int kLdpc2lVariantsA_n, kLdpc2lVariantsB_n;
+
 }  // namespace s2
