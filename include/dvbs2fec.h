@@ -35,7 +35,8 @@ extern "C" {
 typedef struct dvbs2fec_handle dvbs2fec_handle;
 
 typedef struct {
-    int32_t n_devices;      /* 0 = device 0 only; otherwise devices[0..n_devices) share the frames of every batch */
+    int32_t n_devices;      /* 0 = the calling thread's current CUDA device (cudaGetDevice; device 0 unless the caller chose another);
+                               otherwise devices[0..n_devices) share the frames of every batch */
     int32_t devices[8];
     int32_t max_batch;      /* frames per kernel launch and per device (default 1024) */
     int32_t max_latency_us; /* submit/collect queue: launch a partial batch after this long (default 2000) */
@@ -128,8 +129,8 @@ int dvbs2fec_flush(dvbs2fec_handle* h);
  * Frames are then taken with dvbs2fec_collect_ts instead of dvbs2fec_collect. */
 int dvbs2fec_set_ts_output(dvbs2fec_handle* h, int on);
 /* TS packets of finished frames, in order: returns the bytes written (a multiple of 188, <= cap).  results
- * (optional, room for max_results records) receives one record per frame, batch by batch, together with the last
- * packets of the batch; *nresults the count. */
+ * (optional, room for max_results records) receives one record per frame, in submission order, each batch's
+ * records following its last packets (as many as fit; the rest with the next call); *nresults the count. */
 int dvbs2fec_collect_ts(dvbs2fec_handle* h, uint8_t* ts_out, int cap, dvbs2fec_result* results, int max_results,
                         int* nresults, int timeout_us);
 

@@ -204,10 +204,15 @@ int orc_ts_work(orc_ts_parser* p, const uint8_t* bbframes, int cnt, uint8_t* out
                 memcpy(out + o + 1, unit, 187);
                 o += 188;
             }
-            if (left > 0) {
+            if (left >= 188) {
+                /* only after running out of room.  The reference overruns packet_reassembly here and carries
+                 * count >= 188 into the next call (a negative memcpy length): undefined.  Domain completion shared
+                 * with the device parser: drop out of sync, pick up again at the next frame's SYNCD. */
+                p->synched = 0;
+                p->count = 0;
+            } else if (left > 0) {
                 p->count = left;
-                memcpy(p->unit, df, left < 188 ? left : 188); /* left >= 188 only after running out of room,
-                                                                 where the reference overruns its buffer */
+                memcpy(p->unit, df, left);
             }
             if (out_cap - o <= 188) break;
         } else if (ts_gs == 1) {

@@ -198,7 +198,7 @@ struct dvbs2fec_handle {
         PinBuf<uint8_t> in, bb, ts;
         PinBuf<dvbs2fec_result> res;
         PinBuf<int> ts_len;
-        int ts_taken = 0;
+        int ts_taken = 0, res_taken = 0;
         bool has_ts = false;
         std::vector<uint64_t> tags;
         int n = 0, taken = 0, cap = 0;
@@ -460,6 +460,27 @@ int run_device_share(dvbs2fec_handle* h, DevCtx& d, const int8_t* llr, const flo
     const bool pin_in = is_pinned(in);
     const bool pin_out = (!bb || is_pinned(bb)) && (!res || is_pinned(res));
     int which = 0, rc = 0;
+    // Error exit: nothing asynchronous may outlive the call -- copies into the caller's buffers that were already
+    // enqueued are waited for, and no slot keeps a pointer to them (a later call would copy into freed memory).
+    struct Abort {
+        DevCtx& d;
+        bool armed = true;
+        ~Abort() {
+            if (!armed) return;
+            char keep[sizeof(g_err)];
+            memcpy(keep, g_err, sizeof keep);
+            for (int k = 0; k < kSlots; ++k) {
+                Slot& s = d.slot[k];
+                cudaStreamSynchronize(s.copy);
+                cudaStreamSynchronize(s.stream);
+                s.pending = 0;
+                s.user_bb = nullptr;
+                s.user_res = nullptr;
+            }
+            cudaGetLastError();
+            memcpy(g_err, keep, sizeof keep);
+        }
+    } abort_guard{d};
     for (int f0 = 0; f0 < n; f0 += chunk, which ^= 1) {
         Slot& s = d.slot[which];
         const int m = std::min(chunk, n - f0);
@@ -492,6 +513,7 @@ int run_device_share(dvbs2fec_handle* h, DevCtx& d, const int8_t* llr, const flo
     }
     for (int k = 0; k < kSlots; ++k)
         if ((rc = finish_slot(h, d.slot[k]))) return rc;
+    abort_guard.armed = false;
     return 0;
 }
 
@@ -571,8 +593,8 @@ void launch_stage(dvbs2fec_handle* h, int st, int which) {
             CU(cudaMemcpyAsync(S.res.p + f0, s.res.p, (size_t)m * sizeof(dvbs2fec_result), cudaMemcpyDeviceToHost, s.stream));
             if (S.has_ts) {   // K6 behind K3, on the BBFRAMEs still in device memory; its state runs through all batches
                 dvbs2fec_ts_parser* tp = h->ts;
-                const int ts_cap = (int)((size_t)m * S.kb + 188);
-                CU(s.ts.reserve((size_t)h->cfg.max_batch * S.kb + 188));
+                const int ts_cap = (int)((size_t)m * S.kb + 376);   // room for everything: see dvbs2fec_ts_work
+                CU(s.ts.reserve((size_t)std::max(m, h->cfg.max_batch) * S.kb + 376));
                 CU(s.ts_len.reserve(1));
                 CU(tp->plan.reserve(std::max(m, h->cfg.max_batch)));
                 CU(tp->meta.reserve(std::max(m, h->cfg.max_batch)));
@@ -599,8 +621,10 @@ void launch_stage(dvbs2fec_handle* h, int st, int which) {
             return 0;
         };
         int rc = body();
-        if (rc) {   // this share never got its completion callback
+        if (rc) {   // this share never got its completion callback; what it did enqueue still writes into the stage
             S.rc = rc;
+            cudaStreamSynchronize(s.stream);
+            cudaGetLastError();
             S.outstanding.fetch_sub(1);
         }
     }
@@ -988,6 +1012,7 @@ static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym
         S.is_sym = is_sym;
         S.n = S.taken = 0;
         S.ts_taken = 0;
+        S.res_taken = 0;
         S.has_ts = h->ts_output;
         S.tags.clear();
         // page-locked allocation may synchronise with the device, and stream callbacks take h->mu: allocate unlocked
@@ -997,7 +1022,7 @@ static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym
         if (e == cudaSuccess) e = S.in.reserve((size_t)S.cap * S.in_bytes);
         if (e == cudaSuccess) e = S.bb.reserve((size_t)S.cap * S.kb);
         if (e == cudaSuccess) e = S.res.reserve(S.cap);
-        if (e == cudaSuccess && S.has_ts) e = S.ts.reserve((size_t)S.cap * S.kb + 188);
+        if (e == cudaSuccess && S.has_ts) e = S.ts.reserve((size_t)S.cap * S.kb + 376);
         if (e == cudaSuccess && S.has_ts) e = S.ts_len.reserve(1);
         lk.lock();
         if (e != cudaSuccess) {
@@ -1108,15 +1133,15 @@ int dvbs2fec_collect_ts(dvbs2fec_handle* h, uint8_t* ts_out, int cap, dvbs2fec_r
     while (!h->st_done.empty()) {
         dvbs2fec_handle::Stage& S = h->stages[h->st_done.front()];
         if (!S.has_ts) return fail(DVBS2FEC_EINVAL, "frames decoded before dvbs2fec_set_ts_output: use dvbs2fec_collect");
-        if (results && max_results - nres < S.n) break;   // a batch's results go out with the end of its packets
         const int total = S.rc ? 0 : *S.ts_len.p;
         const int take = std::min(total - S.ts_taken, (cap - bytes) / 188 * 188);
         memcpy(ts_out + bytes, S.ts.p + S.ts_taken, (size_t)take);
         S.ts_taken += take;
         bytes += take;
         if (S.ts_taken < total) break;   // no room for the rest: next call
-        if (results)
-            for (int i = 0; i < S.n; ++i) {
+        if (results) {                   // the batch's records follow its last packets, as many as fit
+            const int k = std::min(max_results - nres, S.n - S.res_taken);
+            for (int i = S.res_taken; i < S.res_taken + k; ++i) {
                 dvbs2fec_result r = S.res.p[i];
                 r.tag = S.tags[i];
                 if (S.rc) {
@@ -1126,6 +1151,9 @@ int dvbs2fec_collect_ts(dvbs2fec_handle* h, uint8_t* ts_out, int cap, dvbs2fec_r
                 }
                 results[nres++] = r;
             }
+            S.res_taken += k;
+            if (S.res_taken < S.n) break;   // the rest of the records: next call
+        }
         h->st_free.push_back(h->st_done.front());
         h->st_done.pop_front();
     }
@@ -1221,12 +1249,14 @@ int dvbs2fec_ts_work(dvbs2fec_ts_parser* p, const uint8_t* bbframes, int cnt, ui
     if (cnt < 0 || (cnt && !bbframes) || !tsframes || buffer_outsize < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
     CU(cudaSetDevice(p->device));
     const size_t in_bytes = (size_t)cnt * p->kb;
-    // every frame yields fewer output bytes than it has input bytes, plus one carried unit
-    const size_t out_need = std::min((size_t)buffer_outsize, in_bytes + 188);
+    // A call emits at most in_bytes - 10 cnt + 187 bytes (every frame spends 10 bytes on its BBHEADER; one unit may
+    // have been carried in).  With in_bytes + 376 bytes of room no test of the room rule (:176,208-211) can fail, so
+    // a larger caller buffer is equivalent to that much -- and the kernels are told the size that is really allocated.
+    const size_t out_alloc = std::min((size_t)buffer_outsize, in_bytes + 376);
     CU(p->bb.reserve(std::max<size_t>(in_bytes, 1)));
-    CU(p->out.reserve(std::max<size_t>(out_need, 1)));
+    CU(p->out.reserve(std::max<size_t>(out_alloc, 1)));
     if (in_bytes) CU(cudaMemcpyAsync(p->bb.p, bbframes, in_bytes, cudaMemcpyHostToDevice, p->stream));
-    int rc = dvbs2fec_ts_work_device(p, p->bb.p, cnt, p->out.p, buffer_outsize, nullptr, p->stream);
+    int rc = dvbs2fec_ts_work_device(p, p->bb.p, cnt, p->out.p, (int)out_alloc, nullptr, p->stream);
     if (rc) return rc;
     CU(cudaMemcpyAsync(p->h_produced.p, &p->state.p->produced, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));

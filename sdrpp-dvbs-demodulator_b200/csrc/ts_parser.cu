@@ -108,7 +108,13 @@ __device__ void ts_plan_serial(const TsArgs& a, const uint32_t* meta, int st, in
                         consumed += 188 * whole;
                     }
                     o += 188 * p.npk;
-                    if (left > 0) {
+                    if (left >= 188) {
+                        // only when the room test stopped the loop.  The reference then copies `left` bytes into its
+                        // 188-byte packet_reassembly and carries count >= 188 into the next call (:203-207: a buffer
+                        // overrun, then a negative memcpy length) -- undefined there; here the parser drops out of
+                        // sync and picks up again at the next frame's SYNCD.
+                        count = -1;
+                    } else if (left > 0) {
                         count = left;
                         car_src = f;
                         car_off = off + consumed;

@@ -23,9 +23,10 @@ def compare(kbch, batches, cap=65536 * 10):
     o = OrcParser(kbch)
     g = pkg.BBFrameTSParser()
     g.setFrameSize(kbch)
-    for frames in batches:
-        want = o.work(frames, cap)
-        got = g.work(frames, len(frames), cap)
+    for k, frames in enumerate(batches):
+        c = cap[k] if isinstance(cap, (list, tuple)) else cap
+        want = o.work(frames, c)
+        got = g.work(frames, len(frames), c)
         assert np.array_equal(got, want)
         st = o.stats()
         assert (g.last_bb_cnt, g.last_bb_proc) == (st["cnt"], st["proc"])
@@ -60,6 +61,17 @@ def test_ts_output_room_rule_matches_oracle():
     frames, _ = bbstream.ts_bbframes(kbch, bbstream.ts_packets(200, rng))
     for cap in (0, 188, 189, 190, 188 * 7 + 5, 188 * 21, 188 * 21 + 1, 188 * 22, 188 * 43):
         compare(kbch, [frames[:3]], cap=cap)
+
+
+def test_ts_parser_recovers_after_running_out_of_room():
+    """a call that stops on the room rule with >= 188 bytes of its frame unconsumed (the reference overruns its
+    reassembly buffer there): the parser drops sync instead of carrying an impossible byte count, and the
+    following calls -- ample room, and out of room again -- stay exact and in bounds"""
+    rng = np.random.default_rng(16)
+    for kbch in (KBCH["n1/2"], KBCH["s1/4"]):
+        frames, _ = bbstream.ts_bbframes(kbch, bbstream.ts_packets(400, rng), first_byte=7)
+        for cap0 in (0, 188, 189, 188 * 3 + 1, 188 * 9):
+            compare(kbch, [frames[:4], frames[4:9], frames[9:12], frames[12:]], cap=[cap0, 65536 * 10, 188 * 2 + 5, 65536 * 10])
 
 
 def test_gse_frames_are_counted_not_unpacked():
@@ -192,5 +204,18 @@ def test_queue_delivers_ts_packets_fused_behind_the_decoder(modcod, scenario):
         d.flush()
         ts, res = d.collect_ts(timeout_us=2_000_000)
         assert np.array_equal(ts, OrcParser(kbch).work(frames[:6])) and len(res) == 6
+        # fewer result records per call than a batch holds: records trickle out, nothing is stuck
+        d.setDemodParams(modcod, short, False)
+        for i in range(8):
+            d.submit_llr(llr[i], 200 + i)
+        d.flush()
+        got, tags = [], []
+        for _ in range(20):
+            ts, res = d.collect_ts(max_results=3, timeout_us=500_000)
+            got.append(ts.copy()); tags += list(res["tag"])
+            if len(tags) == 8:
+                break
+        assert tags == list(range(200, 208))
+        assert np.array_equal(np.concatenate(got), OrcParser(kbch).work(frames[:8]))
     finally:
         d.close()
