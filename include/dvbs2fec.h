@@ -26,6 +26,7 @@ extern "C" {
 #define DVBS2FEC_ENODEV (-19)   /* no usable CUDA device / kernels missing: the library never falls back to the CPU */
 #define DVBS2FEC_ECUDA (-5)     /* a CUDA call failed; dvbs2fec_last_error() has the text */
 #define DVBS2FEC_EAGAIN (-11)   /* queue full (submit) */
+#define DVBS2FEC_ENOSPC (-28)   /* BBFRAME parser: GSE output does not fit the caller's buffer / descriptor pool */
 
 #define DVBS2FEC_FLAG_LDPC_FAIL 1u /* LDPC never met all parity checks (BBFrameLDPC::decode returned -1) */
 #define DVBS2FEC_FLAG_BCH_FAIL 2u  /* BBFrameBCH::decode returned -1 */
@@ -140,7 +141,7 @@ void dvbs2fec_free_pinned(void* p);
 
 /* ---- downstream of the decode stage: BBFRAME -> MPEG-TS packets ----
  * Mirrors BBFrameTSParser (dvbs2/bbframe_ts_parser.h:67-108) as main.cpp:538 uses it.  The parser is its own
- * object, like the reference's; its state (sync, unfinished packet) lives on the device between calls. */
+ * object, like the reference's; its state (sync, unfinished packet, GSE reassembly) lives on the device between calls. */
 typedef struct dvbs2fec_ts_parser dvbs2fec_ts_parser;
 typedef struct dvbs2fec_bbheader { /* BBHeader (bbframe_ts_parser.h:37-65) */
     uint8_t ts_gs, sis_mis, ccm_acm, issyi, npd, ro, isi, sync;
@@ -150,14 +151,28 @@ int dvbs2fec_ts_create(int device, dvbs2fec_ts_parser** out);
 void dvbs2fec_ts_destroy(dvbs2fec_ts_parser* p);
 /* BBFrameTSParser::setFrameSize (bbframe_ts_parser.cpp:31-43): kbch in bits; resets the parser state */
 int dvbs2fec_ts_set_frame_size(dvbs2fec_ts_parser* p, int kbch_bits);
-/* BBFrameTSParser::work (bbframe_ts_parser.cpp:100-392), TS frames: cnt BBFRAMEs of kbch/8 bytes in, 188-byte
- * packets out; returns the number of bytes written (a multiple of 188) or a negative error.  Host buffers.
- * Frames carrying GSE (ts_gs = 01) are accepted and counted but their PDUs are not extracted here. */
+/* BBFrameTSParser::work (bbframe_ts_parser.cpp:100-392): cnt BBFRAMEs of kbch/8 bytes in; out come 188-byte packets
+ * for TS frames (ts_gs = 11, :171-212) and GRE-wrapped PDUs for GSE frames (ts_gs = 01, :213-389: complete PDUs and
+ * PDUs reassembled from Start/Continuation/End fragments in three FragID slots, CRC-32 checked), in frame order.
+ * Returns the number of bytes written or a negative error.  Host buffers.  Where the reference is undefined the
+ * call is defined: GSE packets whose lengths lead outside the input are reported (malformed) and end the walk of
+ * their frame; a call with GSE frames whose output does not fit buffer_outsize returns DVBS2FEC_ENOSPC with nothing
+ * written (the reference writes PDUs without a room test); >= 188 unconsumed bytes behind the TS room rule drop sync. */
 int dvbs2fec_ts_work(dvbs2fec_ts_parser* p, const uint8_t* bbframes, int cnt, uint8_t* tsframes, int buffer_outsize);
 /* same on device buffers (e.g. straight from dvbs2fec_decode_batch_device), asynchronous on `stream`;
- * d_produced (optional, device int) receives the byte count */
+ * d_produced (optional, device int) receives the byte count (DVBS2FEC_ENOSPC as above, also when the call holds
+ * more GSE packets than the descriptor pool: see dvbs2fec_ts_set_gse) */
 int dvbs2fec_ts_work_device(dvbs2fec_ts_parser* p, const uint8_t* d_bbframes, int cnt, uint8_t* d_tsframes,
                             int buffer_outsize, int* d_produced, void* stream);
+/* GSE branch: max_packets_per_call < 0 -> GSE frames are accepted and counted but not unpacked; 0 (default) ->
+ * unpacked, descriptor pool sized exactly (host-buffer call) or 64 packets per frame + 1024 (device-buffer call,
+ * which cannot ask the device first); > 0 -> pool of that many packets for device-buffer calls.  The reassembly
+ * state survives dvbs2fec_ts_set_frame_size like the reference's. */
+int dvbs2fec_ts_set_gse(dvbs2fec_ts_parser* p, int max_packets_per_call);
+/* last_gse_crc_err (bbframe_ts_parser.h:73) and counters of the last call that held GSE frames: PDUs delivered,
+ * reassemblies that failed the CRC-32, frames with a malformed packet chain, fragments without a slot */
+int dvbs2fec_ts_gse_stats(dvbs2fec_ts_parser* p, int* last_gse_crc_err, int* pdus, int* crc_errors, int* malformed,
+                          int* dropped);
 /* public members after work() (bbframe_ts_parser.h:72-76): last_header (returns 0 if no frame was accepted
  * yet, 1 otherwise), last_bb_cnt, last_bb_proc; gse_frames = accepted GSE frames in the last call */
 int dvbs2fec_ts_stats(dvbs2fec_ts_parser* p, dvbs2fec_bbheader* last_header, int* last_bb_cnt, int* last_bb_proc,

@@ -23,7 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdvbs2fec.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "dvbs2fec.h")
 
-EINVAL, ENODEV, ECUDA, EAGAIN = -22, -19, -5, -11
+EINVAL, ENODEV, ECUDA, EAGAIN, ENOSPC = -22, -19, -5, -11, -28
 FLAG_LDPC_FAIL, FLAG_BCH_FAIL, FLAG_BBHEADER_CRC_FAIL = 1, 2, 4
 
 # reference dvbs2_code_rate_t numbering (dvbs2/dvbs2.h:11-25)
@@ -109,6 +109,8 @@ def lib():
     L.dvbs2fec_ts_work.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.dvbs2fec_ts_work_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]
     L.dvbs2fec_ts_stats.argtypes = [vp, C.POINTER(BBHeader), ip, ip, ip]
+    L.dvbs2fec_ts_set_gse.argtypes = [vp, C.c_int]
+    L.dvbs2fec_ts_gse_stats.argtypes = [vp, ip, ip, ip, ip, ip]
     _lib = L
     return L
 
@@ -345,14 +347,16 @@ class S2BBToSoft:
 
 
 class BBFrameTSParser:
-    """dvbs2/bbframe_ts_parser.h:67-108 on the device: BBFRAMEs in, 188-byte TS packets out (GSE frames are
-    accepted and counted, not unpacked).  Parser state persists between work() calls like the reference's."""
+    """dvbs2/bbframe_ts_parser.h:67-108 on the device: BBFRAMEs in; 188-byte TS packets and GRE-wrapped GSE PDUs
+    out.  Parser state (sync, unfinished packet, GSE reassembly) persists between work() calls like the reference's."""
 
     def __init__(self, device=0):
         self._p = C.c_void_p()
         _check(lib().dvbs2fec_ts_create(device, C.byref(self._p)))
         self.last_header = BBHeader()
         self.last_bb_cnt = self.last_bb_proc = self.gse_frames = 0
+        self.last_gse_crc_err = 0
+        self.gse_counters = dict(pdus=0, crc_errors=0, malformed=0, dropped=0)
         self.have_header = False
 
     def close(self):
@@ -374,6 +378,14 @@ class BBFrameTSParser:
         a, b, g = C.c_int(), C.c_int(), C.c_int()
         self.have_header = bool(_check(lib().dvbs2fec_ts_stats(self._p, C.byref(self.last_header), C.byref(a), C.byref(b), C.byref(g))))
         self.last_bb_cnt, self.last_bb_proc, self.gse_frames = a.value, b.value, g.value
+        v = [C.c_int() for _ in range(5)]
+        _check(lib().dvbs2fec_ts_gse_stats(self._p, *[C.byref(x) for x in v]))
+        self.last_gse_crc_err = v[0].value
+        self.gse_counters = dict(pdus=v[1].value, crc_errors=v[2].value, malformed=v[3].value, dropped=v[4].value)
+
+    def set_gse(self, max_packets_per_call=0):
+        """< 0: GSE frames are only counted; 0: unpacked (default); > 0: descriptor pool for work_device"""
+        _check(lib().dvbs2fec_ts_set_gse(self._p, max_packets_per_call))
 
     def work(self, bbframes, cnt=None, buffer_outsize=65536 * 10):
         """returns the TS bytes produced (uint8 array), like work()'s tsframes[:return value]"""

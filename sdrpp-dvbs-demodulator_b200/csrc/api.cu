@@ -161,6 +161,14 @@ struct dvbs2fec_ts_parser {
     DevBuf<uint32_t> meta;
     DevBuf<uint8_t> bb, out;
     PinBuf<int> h_produced;
+    // GSE branch (ts_parser.cu): reassembly state and buffers persist, the rest is per-call scratch
+    int gse_pool = 0;                  // < 0: GSE frames are only counted; 0: default sizing; > 0: packets per device-side call
+    DevBuf<GseState> gstate;
+    DevBuf<uint8_t> gbuf, g_sync;
+    DevBuf<int> g_doff, g_before, g_nxt, g_aux, g_aux2;
+    DevBuf<GseDesc> g_desc;
+    DevBuf<GseOut> g_out;
+    DevBuf<uint32_t> g_crc0, g_xpow;
 };
 
 struct dvbs2fec_handle {
@@ -215,6 +223,8 @@ struct dvbs2fec_handle {
     int st_fill = -1;
     uint64_t launch_seq = 0;
 };
+
+static int ts_args(dvbs2fec_ts_parser* p, const uint8_t* d_bb, int cnt, uint8_t* d_out, int out_cap, int* d_produced, TsArgs* out);
 
 namespace {
 
@@ -596,20 +606,13 @@ void launch_stage(dvbs2fec_handle* h, int st, int which) {
                 const int ts_cap = (int)((size_t)m * S.kb + 376);   // room for everything: see dvbs2fec_ts_work
                 CU(s.ts.reserve((size_t)std::max(m, h->cfg.max_batch) * S.kb + 376));
                 CU(s.ts_len.reserve(1));
-                CU(tp->plan.reserve(std::max(m, h->cfg.max_batch)));
-                CU(tp->meta.reserve(std::max(m, h->cfg.max_batch)));
                 CU(cudaStreamWaitEvent(s.stream, h->ts_done, 0));
-                TsArgs ta{};
-                ta.bb = s.bb.p;
-                ta.cnt = m;
-                ta.kb = tp->kb;
-                ta.max_dfl = tp->max_dfl;
-                ta.out = s.ts.p;
-                ta.out_cap = ts_cap;
-                ta.state = tp->state.p;
-                ta.plan = tp->plan.p;
-                ta.meta = tp->meta.p;
-                ta.produced_out = s.ts_len.p;
+                const int saved_pool = tp->gse_pool;
+                tp->gse_pool = -1;   // the fused queue output is TS only (GSE frames are counted): its room is sized for TS
+                TsArgs ta;
+                rc = ts_args(tp, s.bb.p, m, s.ts.p, ts_cap, s.ts_len.p, &ta);
+                tp->gse_pool = saved_pool;
+                if (rc) return rc;
                 int e = ts_launch(ta, s.stream);
                 if (e) return fail(DVBS2FEC_ECUDA, "ts launch: %s", cudaGetErrorString((cudaError_t)e));
                 h->last_launches += 3;
@@ -1189,8 +1192,11 @@ int dvbs2fec_ts_create(int device, dvbs2fec_ts_parser** out) {
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CU(p->state.reserve(1));
-    CU(p->h_produced.reserve(1));
+    CU(p->h_produced.reserve(4));
     CU(cudaMemset(p->state.p, 0, sizeof(TsState)));
+    CU(p->gstate.reserve(1));
+    CU(cudaMemset(p->gstate.p, 0, sizeof(GseState)));
+    CU(p->gbuf.reserve((size_t)2 * 3 * kGseBuf));
     *out = p.release();
     return 0;
 }
@@ -1208,6 +1214,9 @@ void dvbs2fec_ts_destroy(dvbs2fec_ts_parser* p) {
     p->bb.release();
     p->out.release();
     p->h_produced.release();
+    p->gstate.release(); p->gbuf.release(); p->g_sync.release(); p->g_doff.release(); p->g_before.release();
+    p->g_nxt.release(); p->g_aux.release(); p->g_aux2.release(); p->g_desc.release(); p->g_out.release();
+    p->g_crc0.release(); p->g_xpow.release();
     delete p;
 }
 
@@ -1221,26 +1230,67 @@ int dvbs2fec_ts_set_frame_size(dvbs2fec_ts_parser* p, int kbch_bits) {
     return 0;
 }
 
+}  // extern "C"
+
+// scratch that every call needs, and the argument block of the kernels
+static int ts_args(dvbs2fec_ts_parser* p, const uint8_t* d_bb, int cnt, uint8_t* d_out, int out_cap, int* d_produced, TsArgs* out) {
+    CU(p->plan.reserve(std::max(cnt, 1)));
+    CU(p->meta.reserve(std::max(cnt, 1)));
+    TsArgs a{};
+    a.bb = d_bb;
+    a.cnt = cnt;
+    a.kb = p->kb;
+    a.max_dfl = p->max_dfl;
+    a.out = d_out;
+    a.out_cap = out_cap;
+    a.state = p->state.p;
+    a.plan = p->plan.p;
+    a.meta = p->meta.p;
+    a.produced_out = d_produced;
+    if (p->gse_pool >= 0) {
+        CU(p->g_sync.reserve(std::max(cnt, 1)));
+        CU(p->g_doff.reserve(cnt + 1));
+        CU(p->g_before.reserve(cnt + 1));
+        a.gse.state = p->gstate.p;
+        a.gse.buf = p->gbuf.p;
+        a.gse.entry_sync = p->g_sync.p;
+        a.gse.doff = p->g_doff.p;
+        a.gse.before = p->g_before.p;
+    }
+    *out = a;
+    return 0;
+}
+static int gse_pool(dvbs2fec_ts_parser* p, int cap, TsArgs* a) {
+    cap = std::max(cap, 1);
+    CU(p->g_desc.reserve(cap)); CU(p->g_out.reserve(cap)); CU(p->g_crc0.reserve(cap)); CU(p->g_xpow.reserve(cap));
+    CU(p->g_nxt.reserve(cap)); CU(p->g_aux.reserve(cap)); CU(p->g_aux2.reserve(cap));
+    a->gse.desc = p->g_desc.p; a->gse.out = p->g_out.p; a->gse.crc0 = p->g_crc0.p; a->gse.xpow = p->g_xpow.p;
+    a->gse.nxt = p->g_nxt.p; a->gse.aux = p->g_aux.p; a->gse.aux2 = p->g_aux2.p;
+    a->gse.cap = cap;
+    return 0;
+}
+
+extern "C" {
+
 int dvbs2fec_ts_work_device(dvbs2fec_ts_parser* p, const uint8_t* d_bbframes, int cnt, uint8_t* d_tsframes,
                             int buffer_outsize, int* d_produced, void* stream) {
     if (!p || !p->kb) return fail(DVBS2FEC_EINVAL, "set_frame_size has not been called");
     if (cnt < 0 || (cnt && !d_bbframes) || !d_tsframes || buffer_outsize < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
     CU(cudaSetDevice(p->device));
-    CU(p->plan.reserve(std::max(cnt, 1)));
-    CU(p->meta.reserve(std::max(cnt, 1)));
-    TsArgs a{};
-    a.bb = d_bbframes;
-    a.cnt = cnt;
-    a.kb = p->kb;
-    a.max_dfl = p->max_dfl;
-    a.out = d_tsframes;
-    a.out_cap = buffer_outsize;
-    a.state = p->state.p;
-    a.plan = p->plan.p;
-    a.meta = p->meta.p;
-    a.produced_out = d_produced;
+    TsArgs a;
+    int rc = ts_args(p, d_bbframes, cnt, d_tsframes, buffer_outsize, d_produced, &a);
+    if (rc) return rc;
     int e = ts_launch(a, (cudaStream_t)stream);
     if (e) return fail(DVBS2FEC_ECUDA, "ts launch: %s", cudaGetErrorString((cudaError_t)e));
+    if (a.gse.state) {
+        // The host cannot know here whether the call holds GSE frames: the GSE pass is enqueued behind the TS pass and
+        // every kernel of it returns at once unless the plan kernel deferred the call (a few microseconds of launches).
+        // The descriptor pool is sized in advance; a call with more GSE packets than that is refused (kTsNoSpace).
+        if ((rc = gse_pool(p, p->gse_pool > 0 ? p->gse_pool : 64 * cnt + 1024, &a))) return rc;
+        e = gse_launch_count(a, (cudaStream_t)stream);
+        if (!e) e = gse_launch_rest(a, (cudaStream_t)stream);
+        if (e) return fail(DVBS2FEC_ECUDA, "gse launch: %s", cudaGetErrorString((cudaError_t)e));
+    }
     return 0;
 }
 
@@ -1249,23 +1299,65 @@ int dvbs2fec_ts_work(dvbs2fec_ts_parser* p, const uint8_t* bbframes, int cnt, ui
     if (cnt < 0 || (cnt && !bbframes) || !tsframes || buffer_outsize < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
     CU(cudaSetDevice(p->device));
     const size_t in_bytes = (size_t)cnt * p->kb;
-    // A call emits at most in_bytes - 10 cnt + 187 bytes (every frame spends 10 bytes on its BBHEADER; one unit may
-    // have been carried in).  With in_bytes + 376 bytes of room no test of the room rule (:176,208-211) can fail, so
-    // a larger caller buffer is equivalent to that much -- and the kernels are told the size that is really allocated.
-    const size_t out_alloc = std::min((size_t)buffer_outsize, in_bytes + 376);
+    // A call emits at most in_bytes - 10 cnt + 187 bytes of TS (every frame spends 10 bytes on its BBHEADER; one unit
+    // may have been carried in).  With in_bytes + 376 bytes of room no test of the room rule (:176,208-211) can fail,
+    // so a larger caller buffer is equivalent to that much -- and the kernels are told the size that is really
+    // allocated.  GSE: PDUs begun in earlier calls may complete in this one, at most one per reassembly slot.
+    const size_t gse_extra = p->gse_pool >= 0 ? 3 * (size_t)(kGseBuf + 4) : 0;
+    const size_t out_alloc = std::min((size_t)buffer_outsize, in_bytes + 376 + gse_extra);
     CU(p->bb.reserve(std::max<size_t>(in_bytes, 1)));
     CU(p->out.reserve(std::max<size_t>(out_alloc, 1)));
     if (in_bytes) CU(cudaMemcpyAsync(p->bb.p, bbframes, in_bytes, cudaMemcpyHostToDevice, p->stream));
-    int rc = dvbs2fec_ts_work_device(p, p->bb.p, cnt, p->out.p, (int)out_alloc, nullptr, p->stream);
+    TsArgs a;
+    int rc = ts_args(p, p->bb.p, cnt, p->out.p, (int)out_alloc, nullptr, &a);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(p->h_produced.p, &p->state.p->produced, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    int e = ts_launch(a, p->stream);
+    if (e) return fail(DVBS2FEC_ECUDA, "ts launch: %s", cudaGetErrorString((cudaError_t)e));
+    // produced and phase lie next to each other in TsState
+    CU(cudaMemcpyAsync(p->h_produced.p, &p->state.p->produced, 2 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
+    if (p->h_produced.p[1] == 1) {
+        // the call holds GSE frames and was deferred: count the packets, size the pool, run the GSE pass
+        TsArgs c = a;
+        c.gse.cap = 0x7FFFFFFF;
+        e = gse_launch_count(c, p->stream);
+        if (e) return fail(DVBS2FEC_ECUDA, "gse launch: %s", cudaGetErrorString((cudaError_t)e));
+        CU(cudaMemcpyAsync(p->h_produced.p + 2, &p->gstate.p->ndesc_wanted, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        if ((rc = gse_pool(p, p->h_produced.p[2], &a))) return rc;
+        e = gse_launch_rest(a, p->stream);
+        if (e) return fail(DVBS2FEC_ECUDA, "gse launch: %s", cudaGetErrorString((cudaError_t)e));
+        CU(cudaMemcpyAsync(p->h_produced.p, &p->state.p->produced, 2 * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+    }
     const int produced = *p->h_produced.p;
+    if (produced == kTsNoSpace)
+        return fail(DVBS2FEC_ENOSPC, "GSE output does not fit into %d bytes (the reference writes PDUs without a room test)", buffer_outsize);
     if (produced > 0) {
         CU(cudaMemcpyAsync(tsframes, p->out.p, (size_t)produced, cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
     }
     return produced;
+}
+
+int dvbs2fec_ts_set_gse(dvbs2fec_ts_parser* p, int max_packets_per_call) {
+    if (!p) return fail(DVBS2FEC_EINVAL, "parser is NULL");
+    p->gse_pool = max_packets_per_call;
+    return 0;
+}
+
+int dvbs2fec_ts_gse_stats(dvbs2fec_ts_parser* p, int* last_gse_crc_err, int* pdus, int* crc_errors, int* malformed,
+                          int* dropped) {
+    if (!p) return fail(DVBS2FEC_EINVAL, "parser is NULL");
+    CU(cudaSetDevice(p->device));
+    GseState g;
+    CU(cudaMemcpy(&g, p->gstate.p, sizeof g, cudaMemcpyDeviceToHost));
+    if (last_gse_crc_err) *last_gse_crc_err = g.last_crc_err;
+    if (pdus) *pdus = g.pdus;
+    if (crc_errors) *crc_errors = g.crc_errors;
+    if (malformed) *malformed = g.malformed;
+    if (dropped) *dropped = g.dropped;
+    return 0;
 }
 
 int dvbs2fec_ts_stats(dvbs2fec_ts_parser* p, dvbs2fec_bbheader* last_header, int* last_bb_cnt, int* last_bb_proc,

@@ -5,7 +5,18 @@
 // unfinished unit), which a three-phase scan over composable state maps delivers without walking the frames
 // one by one.  ts_copy_kernel (one CTA per frame, a warp per packet) moves the bytes.
 // HBM-bound: every BBFRAME byte is read once and every TS byte written once.
+//
+// GSE (ts_gs = 01): the packets of a data field are a linked list (every header says where the next one starts)
+// and fragments are reassembled in three FragID slots, so the reference's loop (:213-389) is sequential twice
+// over.  Here only what must be sequential is: a thread per frame walks its packet headers (count, then fill a
+// compact descriptor array), a thread per fragment computes the CRC-32 of its own bytes from a ZERO start value
+// plus x^(8 len) mod P -- CRC-32 is linear, crc(s, B) = s x^(8|B|) + crc(0, B) -- and one warp then replays the
+// slot logic over the descriptors in stream order with a 32-step polynomial multiplication per fragment instead
+// of touching any payload byte.  The payload moves afterwards, a CTA per delivered PDU.  A call that contains GSE
+// frames is deferred by the plan kernel (phase 1) and planned again once the GSE byte counts are known.
 #include "ts_parser.cuh"
+
+#include <algorithm>
 
 namespace s2 {
 namespace {
@@ -28,7 +39,11 @@ __device__ inline unsigned bbheader_crc8(const uint8_t* h) {
 enum { kInvalid = 0, kTs = 1, kGse = 2, kOther = 3 };
 
 // One frame's verdict in a word: kind | data-field bytes << 2 | resync skip (SYNCD/8 + 1) << 15
-__device__ inline uint32_t pack_meta(int kind, int dfl, int syncd) { return (uint32_t)kind | ((uint32_t)(dfl >> 3) << 2) | ((uint32_t)((syncd >> 3) + 1) << 15); }
+// | bit 30: GSE frame whose field is walked (no ISSY, no NPD, UPL = 0, :216)
+__device__ inline uint32_t pack_meta(int kind, int dfl, int syncd, int plain) {
+    return (uint32_t)kind | ((uint32_t)(dfl >> 3) << 2) | ((uint32_t)((syncd >> 3) + 1) << 15) | ((uint32_t)plain << 30);
+}
+__device__ inline int meta_skip(uint32_t m) { return (int)((m >> 15) & 0x7FFFu); }
 
 // Parser state seen from outside a frame: -1 = out of sync, else in sync with `st` bytes of an unfinished unit.
 // (The byte count of an out-of-sync parser is never read again: resynchronising zeroes it, :163.)
@@ -44,7 +59,7 @@ __device__ inline Step ts_step(uint32_t m, int st) {
     if (kind == kInvalid) return r;
     int left = (m >> 2) & 0x1FFF, count = st;
     if (st < 0) {   // enter just past the first sync byte (:157-168)
-        const int skip = (int)(m >> 15);
+        const int skip = meta_skip(m);
         r.off += skip;
         left -= skip;
         count = 0;
@@ -78,7 +93,7 @@ __device__ void ts_plan_serial(const TsArgs& a, const uint32_t* meta, int st, in
             } else {
                 int left = (m >> 2) & 0x1FFF, off = 10, count = st;
                 if (st < 0) {
-                    const int skip = (int)(m >> 15);
+                    const int skip = meta_skip(m);
                     off += skip;
                     left -= skip;
                     count = 0;
@@ -197,7 +212,8 @@ __global__ void __launch_bounds__(kHeaderThreads) ts_header_kernel(const TsArgs 
         const int ts_gs = b[0] >> 6;
         kind = ts_gs == 3 ? kTs : ts_gs == 1 ? kGse : kOther;
     }
-    a.meta[f] = pack_meta(kind, dfl, syncd);
+    const int plain = kind == kGse && !((b[0] >> 3) & 1) && !((b[0] >> 2) & 1) && ((b[2] << 8) | b[3]) == 0;
+    a.meta[f] = pack_meta(kind, dfl, syncd, plain);
 }
 
 constexpr int kMetaShared = 8192;   // frames whose verdict words are staged in shared memory
@@ -210,6 +226,8 @@ __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
     const int tid = threadIdx.x;
     TsState* S = a.state;
     const uint32_t* M = a.meta;
+    const bool final = a.mode == 2;          // second planning of a call that was deferred to the GSE pass
+    if (final && S->phase != 1) return;      // (uniform: phase is only written behind the barriers below)
     if (a.cnt <= kMetaShared) {
         for (int f = tid; f < a.cnt; f += kPlanThreads) s_meta[f] = a.meta[f];
         M = s_meta;
@@ -236,7 +254,7 @@ __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
     const int entry = map_apply(pre_map, st0);
     const int final_state = map_apply(total_map, st0);
     // (3) replay for the run's totals
-    int npk = 0, valid = 0, gse = 0, lastv = -1;
+    int npk = 0, valid = 0, gse = 0, gse_plain = 0, lastv = -1;
     unsigned long long writer = 0;   // (frame + 1) << 32 | offset of the carry it leaves; 0: none
     {
         int st = entry;
@@ -247,6 +265,7 @@ __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
                 ++valid;
                 lastv = f;
                 gse += (m & 3) == kGse;
+                gse_plain += (m >> 30) & 1;
             }
             npk += r.npk;
             if (r.tail_off >= 0) writer = ((unsigned long long)(f + 1) << 32) | (unsigned)r.tail_off;
@@ -262,10 +281,30 @@ __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
     const uint32_t npk_before = block_scan_exclusive((uint32_t)npk, 0u, add, s_w32, npk_total);
     block_scan_exclusive((uint32_t)valid, 0u, add, s_w32, valid_total);
     block_scan_exclusive((uint32_t)gse, 0u, add, s_w32, gse_total);
+    uint32_t gse_plain_total;   // GSE frames whose field is walked (the others put nothing out, :216,386-388)
+    block_scan_exclusive((uint32_t)gse_plain, 0u, add, s_w32, gse_plain_total);
     block_scan_exclusive((uint32_t)(lastv + 1), 0u, umax, s_w32, lastv_total);
     const unsigned long long writer_before = block_scan_exclusive(writer, 0ull, later, s_w64, writer_total);
+    if (!final && a.gse.state && gse_plain_total > 0) {
+        // GSE frames: what they put out is known only after the GSE pass.  Leave the state untouched, say which
+        // frames are entered in sync (a frame entered out of sync is walked from SYNCD/8 + 1, :157-168) and defer.
+        int st = entry;
+        for (int f = f0; f < f1; ++f) {
+            a.gse.entry_sync[f] = st >= 0;
+            st = ts_step(M[f], st).next;
+        }
+        if (tid == 0) {
+            S->phase = 1;
+            S->produced = 0;
+            if (a.produced_out) *a.produced_out = 0;
+        }
+        return;
+    }
+    const int og_total = final ? a.gse.before[a.cnt] : 0;
     // enough room for everything (no test of :176/:208 can fail)?  Otherwise one thread redoes it in frame order.
-    const bool roomy = a.out_cap - 188 * (int)npk_total > 188;
+    // With GSE output in the call there is no such fallback: the reference writes PDUs without looking at the
+    // room (it overruns the buffer), so the call is refused as a whole (kTsNoSpace) with the state advanced.
+    const bool roomy = a.out_cap - 188 * (int)npk_total - og_total > 188 && !(final && a.gse.state->ndesc < 0);
     if (tid == 0) {
         S->entry_buf = S->cur;
         s_fin[0] = final_state;
@@ -275,15 +314,15 @@ __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
         s_fin[4] = (int)lastv_total - 1;
         s_fin[5] = (int)(writer_total >> 32) - 1;
         s_fin[6] = (int)(writer_total & 0xFFFFFFFFu);
-        if (!roomy) ts_plan_serial(a, M, st0, s_fin[1], s_fin[2], s_fin[3], s_fin[4], s_fin[0], s_fin[5], s_fin[6]);
+        if (!roomy && !final) ts_plan_serial(a, M, st0, s_fin[1], s_fin[2], s_fin[3], s_fin[4], s_fin[0], s_fin[5], s_fin[6]);
     }
     // (5) replay once more, now writing what every frame contributes
-    if (roomy) {
+    if (roomy || final) {
         int st = entry, o = (int)npk_before;
         int wsrc = (int)(writer_before >> 32) - 1, woff = (int)(writer_before & 0xFFFFFFFFu);
         for (int f = f0; f < f1; ++f) {
             const Step r = ts_step(M[f], st);
-            TsPlan p{188 * o, r.off, -1, 0, (short)r.npk, 0};
+            TsPlan p{188 * o + (final ? a.gse.before[f] : 0), r.off, -1, 0, (short)r.npk, 0};
             if (r.npk > 0 && st > 0) {   // first unit starts with the carried bytes (st <= 0: entered clean or resynced)
                 p.head = (short)st;
                 p.head_src = wsrc;
@@ -307,8 +346,10 @@ __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
         S->last_bb_cnt = a.cnt;
         S->last_bb_proc = s_fin[2];
         S->gse_frames = s_fin[3];
-        S->produced = s_fin[1];
-        if (a.produced_out) *a.produced_out = s_fin[1];
+        const int produced = roomy ? s_fin[1] + og_total : (final ? kTsNoSpace : s_fin[1]);
+        S->produced = produced;
+        S->phase = final ? (roomy ? 2 : 3) : 0;
+        if (a.produced_out) *a.produced_out = produced;
         if (s_fin[4] >= 0) {
             S->have_header = 1;
             for (int i = 0; i < 10; ++i) S->last_header[i] = a.bb[(size_t)s_fin[4] * a.kb + i];
@@ -322,13 +363,14 @@ __global__ void __launch_bounds__(kPlanThreads) ts_plan_kernel(const TsArgs a) {
 
 __global__ void __launch_bounds__(kCopyThreads) ts_copy_kernel(const TsArgs a) {
     const int f = blockIdx.x;
+    if (a.state->phase != a.copy_phase) return;
     const TsPlan p = a.plan[f];
     if (p.npk == 0) return;
     const uint8_t* fr = a.bb + (size_t)f * a.kb;
     const uint8_t* carry = nullptr;
     if (p.head) carry = p.head_src < 0 ? a.state->unit[a.state->entry_buf] : a.bb + (size_t)p.head_src * a.kb + p.head_src_off;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool words = ((uintptr_t)a.out & 3) == 0;
+    const bool words = (((uintptr_t)a.out + (uintptr_t)p.out_off) & 3) == 0;   // (GSE bytes in front of a frame may be any number)
     const uint8_t* bb_end = a.bb + (size_t)a.cnt * a.kb;
     for (int u = warp; u < p.npk; u += kCopyThreads / 32) {
         uint8_t* dst = a.out + p.out_off + 188 * u;
@@ -366,12 +408,353 @@ __global__ void __launch_bounds__(kCopyThreads) ts_copy_kernel(const TsArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ GSE pass
+constexpr int kGseThreads = 128;
+constexpr uint32_t kCrc32Poly = 0x04C11DB7u;
+
+// The walk over one data field (:214-389): packet headers only.  FILL = false counts, FILL = true also writes the
+// descriptors.  A packet whose header or data would lie outside the BBFRAME array (the reference reads on, with
+// whatever follows its input) ends the walk and is reported as malformed.
+template <bool FILL>
+__device__ int gse_walk(const TsArgs& a, int f, GseDesc* out, int* malformed) {
+    const uint32_t m = a.meta[f];
+    if ((m & 3) != kGse || !((m >> 30) & 1)) return 0;
+    const size_t total = (size_t)a.cnt * a.kb;
+    const size_t field = (size_t)f * a.kb + 10 + (a.gse.entry_sync[f] ? 0 : meta_skip(m));
+    const unsigned df_bytes = (m >> 2) & 0x1FFFu;   // the full DFL/8 even behind a resync skip (:214)
+    unsigned at = 0;
+    int n = 0;
+    while (at < df_bytes) {
+        const size_t g = field + at;
+        if (g + 3 > total) { *malformed = 1; break; }
+        const unsigned h1 = a.bb[g], h2 = a.bb[g + 1];
+        const unsigned start = h1 >> 7, end = (h1 >> 6) & 1, label6 = (h1 & 0x30u) == 0;   // (:219: "(h1 & 0x30) >> 2" is 0, 4, 8 or 12)
+        if (!start && !end && label6) break;                                               // padding (:220-222)
+        unsigned len = ((h1 & 0x0Fu) << 8) | h2, hdr, kind;
+        if (start && end) { kind = 0; hdr = 4; len -= 2; }
+        else if (start) { kind = 1; hdr = 7; len -= 5; }
+        else { kind = end ? 3 : 2; hdr = 3; len -= 1; }
+        if (kind < 2 && label6) { hdr += 6; len -= 6; }
+        len &= 0xFFFFu;                                                                    // uint16_t gse_len
+        if (g + hdr + len > total || (kind == 3 && len < 4)) { *malformed = 1; break; }
+        if (FILL) {
+            GseDesc d;
+            d.src = (uint32_t)g;
+            d.len = (uint16_t)len;
+            d.kind = (uint8_t)kind;
+            d.hdr = (uint8_t)hdr;
+            d.proto = kind == 0 ? (uint16_t)((a.bb[g + 2] << 8) | a.bb[g + 3]) : kind == 1 ? (uint16_t)((a.bb[g + 5] << 8) | a.bb[g + 6]) : 0;
+            d.fragid = a.bb[g + 2];
+            d.label6 = (uint8_t)label6;
+            d.frame = (uint32_t)f;
+            out[n] = d;
+        }
+        ++n;
+        at += hdr + len;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(kGseThreads) gse_count_kernel(const TsArgs a) {
+    if (a.state->phase != 1) return;
+    const int f = blockIdx.x * kGseThreads + threadIdx.x;
+    if (f >= a.cnt) return;
+    int bad = 0;
+    a.gse.doff[f] = gse_walk<false>(a, f, nullptr, &bad);
+}
+
+// counts -> first descriptor of every frame, in place; doff[cnt] = GseState::ndesc_wanted = all of them
+__global__ void __launch_bounds__(kPlanThreads) gse_scan_kernel(const TsArgs a) {
+    __shared__ uint32_t s_w32[kPlanThreads / 32];
+    if (a.state->phase != 1) return;
+    const int tid = threadIdx.x;
+    const int per = (a.cnt + kPlanThreads - 1) / kPlanThreads;
+    const int f0 = min(a.cnt, tid * per), f1 = min(a.cnt, f0 + per);
+    uint32_t mine = 0;
+    for (int f = f0; f < f1; ++f) mine += (uint32_t)a.gse.doff[f];
+    uint32_t total;
+    auto add = [](uint32_t x, uint32_t y) { return x + y; };
+    uint32_t at = block_scan_exclusive(mine, 0u, add, s_w32, total);
+    for (int f = f0; f < f1; ++f) {
+        const uint32_t n = (uint32_t)a.gse.doff[f];
+        a.gse.doff[f] = (int)at;
+        at += n;
+    }
+    if (tid == 0) {
+        a.gse.doff[a.cnt] = (int)total;
+        a.gse.state->ndesc_wanted = (int)total;
+        a.gse.state->ndesc = (int)total <= a.gse.cap ? (int)total : -1;   // -1: the pool is too small, the call is refused
+        a.gse.state->malformed = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kGseThreads) gse_fill_kernel(const TsArgs a) {
+    if (a.state->phase != 1 || a.gse.state->ndesc < 0) return;
+    const int f = blockIdx.x * kGseThreads + threadIdx.x;
+    if (f >= a.cnt) return;
+    int bad = 0;
+    gse_walk<true>(a, f, a.gse.desc + a.gse.doff[f], &bad);
+    if (bad) atomicAdd(&a.gse.state->malformed, 1);
+}
+
+// crc32_checksum (:96-101) over a fragment's own bytes.  First fragment: from the all-ones start value over total
+// length, protocol type, label and data, which lie back to back from byte 3 of the packet (:320-327).  Later
+// fragments: from zero, together with x^(8 n) mod P, so that the sequential pass can continue the running value
+// without the bytes; the last one has the four received CRC bytes (:343-346) folded in: the PDU is good when the
+// continued value comes out as zero.
+__global__ void __launch_bounds__(kGseThreads) gse_crc_kernel(const TsArgs a) {
+    __shared__ uint32_t tab[256];
+    if (a.state->phase != 1) return;
+    const int nd = a.gse.state->ndesc;
+    for (int i = threadIdx.x; i < 256; i += kGseThreads) {   // crc32_init (:85-94)
+        uint32_t c = (uint32_t)i << 24;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) c = (c & 0x80000000u) ? (c << 1) ^ kCrc32Poly : (c << 1);
+        tab[i] = c;
+    }
+    __syncthreads();
+    for (int d = blockIdx.x * kGseThreads + threadIdx.x; d < nd; d += gridDim.x * kGseThreads) {
+        const GseDesc e = a.gse.desc[d];
+        if (e.kind == 0) continue;
+        uint32_t crc, xp = 1u;
+        const uint8_t* p;
+        int n;
+        if (e.kind == 1) {
+            crc = 0xFFFFFFFFu;
+            p = a.bb + e.src + 3;
+            n = (int)e.hdr - 3 + (int)e.len;
+        } else {
+            crc = 0u;
+            p = a.bb + e.src + e.hdr;
+            n = e.kind == 3 ? (int)e.len - 4 : (int)e.len;
+        }
+        for (int i = 0; i < n; ++i) {
+            crc = (crc << 8) ^ tab[((crc >> 24) ^ p[i]) & 0xFFu];
+            xp = (xp << 8) ^ tab[xp >> 24];
+        }
+        if (e.kind == 3) crc ^= ((uint32_t)p[n] << 24) | ((uint32_t)p[n + 1] << 16) | ((uint32_t)p[n + 2] << 8) | p[n + 3];
+        a.gse.crc0[d] = crc;
+        a.gse.xpow[d] = xp;
+    }
+}
+
+// a(x) b(x) mod P(x), bit k = x^k
+__device__ inline uint32_t crc32_mulmod(uint32_t x, uint32_t y) {
+    uint32_t r = 0;
+#pragma unroll 8
+    for (int i = 31; i >= 0; --i) {
+        r = (r << 1) ^ ((r & 0x80000000u) ? kCrc32Poly : 0u);
+        if ((y >> i) & 1u) r ^= x;
+    }
+    return r;
+}
+
+// The slot logic of :313-334 (first), :363-377 (middle) and :335-362 (last fragment) over the descriptors in stream
+// order; complete PDUs (:231-279) only advance the output offset.  One warp: the lanes fetch 32 descriptors at a
+// time, every lane replays the same sequence (the slot state is warp-uniform) and keeps the verdict of its own.
+__global__ void __launch_bounds__(32) gse_assemble_kernel(const TsArgs a) {
+    if (a.state->phase != 1) return;
+    GseState* G = a.gse.state;
+    const int lane = threadIdx.x;
+    const int nd = max(G->ndesc, 0);
+    int on[3], id[3], proto[3], ctr[3], head[3], tail[3], carry[3];
+    uint32_t crc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        on[r] = G->slot[r].on; id[r] = G->slot[r].id; proto[r] = G->slot[r].proto; ctr[r] = G->slot[r].ctr; crc[r] = G->slot[r].crc;
+        head[r] = tail[r] = -1;
+        carry[r] = on[r] ? ctr[r] : 0;
+    }
+    int og = 0, pdus = 0, errs = 0, dropped = 0, last_err = G->last_crc_err;
+    for (int base = 0; base < nd; base += 32) {
+        const int d = base + lane;
+        const bool have = d < nd;
+        uint32_t w0 = 0, w1 = 0, c0 = 0, xp = 0;
+        if (have) {
+            const GseDesc e = a.gse.desc[d];
+            w0 = (uint32_t)e.kind | (uint32_t)e.fragid << 8 | (uint32_t)e.proto << 16;
+            w1 = e.len;
+            if (e.kind) {
+                c0 = a.gse.crc0[d];
+                xp = a.gse.xpow[d];
+            }
+            a.gse.nxt[d] = -1;
+        }
+        __syncwarp();
+        GseOut mine{0, 0, -1, -1};
+        int myaux = -1, myaux2 = 0;
+        const int lim = min(32, nd - base);
+        for (int k = 0; k < lim; ++k) {
+            const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, w0, k);
+            const int len = (int)__shfl_sync(0xFFFFFFFFu, w1, k);
+            const uint32_t kc0 = __shfl_sync(0xFFFFFFFFu, c0, k), kxp = __shfl_sync(0xFFFFFFFFu, xp, k);
+            const int kind = v0 & 0xFF, fid = (v0 >> 8) & 0xFF, pr = (int)(v0 >> 16), me = base + k;
+            GseOut o{og, 0, -1, -1};
+            int aux = -1, aux2 = 0;
+            if (kind == 0) {
+                o.emit = ((pr == 0x0800 || pr == 0x86DD) ? 4 : 2) + len;
+                ++pdus;
+            } else if (kind == 1) {
+                int r = -1;
+#pragma unroll
+                for (int rr = 2; rr >= 0; --rr)
+                    if (!on[rr] || id[rr] == fid) r = rr;
+                if (r < 0) ++dropped;
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr)
+                    if (rr == r) {
+                        on[rr] = 1; id[rr] = fid; proto[rr] = pr; ctr[rr] = len; crc[rr] = kc0;
+                        head[rr] = tail[rr] = me;
+                        carry[rr] = 0;
+                        o.pos = 0;
+                    }
+            } else {
+                int r = -1;
+#pragma unroll
+                for (int rr = 2; rr >= 0; --rr)
+                    if (on[rr] && id[rr] == fid) r = rr;
+                bool taken = false;
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr)
+                    if (rr == r && ctr[rr] + len <= kGseBuf) {
+                        taken = true;
+                        o.pos = ctr[rr];
+                        if (tail[rr] >= 0) {
+                            if (lane == 0) a.gse.nxt[tail[rr]] = me;
+                        } else {
+                            head[rr] = me;
+                        }
+                        tail[rr] = me;
+                        crc[rr] = crc32_mulmod(crc[rr], kxp) ^ kc0;
+                        if (kind == 2) {
+                            ctr[rr] += len;
+                        } else {
+                            on[rr] = 0;
+                            ctr[rr] += len - 4;
+                            if (crc[rr] == 0) {
+                                last_err = 0;
+                                o.emit = ((proto[rr] == 0x0800 || proto[rr] == 0x86DD) ? 4 : 2) + ctr[rr];
+                                o.link = head[rr];
+                                aux = carry[rr] > 0 ? (rr | carry[rr] << 2) : -1;
+                                aux2 = proto[rr];
+                                ++pdus;
+                            } else {
+                                last_err = 1;
+                                ++errs;
+                            }
+                        }
+                    }
+                if (!taken) ++dropped;
+            }
+            og += o.emit;
+            if (lane == k) {
+                mine = o;
+                myaux = aux;
+                myaux2 = aux2;
+            }
+        }
+        if (have) {
+            a.gse.out[d] = mine;
+            a.gse.aux[d] = myaux;
+            a.gse.aux2[d] = myaux2;
+        }
+        __syncwarp();
+    }
+    // GSE bytes in front of every frame = in front of its first descriptor
+    for (int f = lane; f <= a.cnt; f += 32) {
+        const int d0 = (f < a.cnt && G->ndesc >= 0) ? a.gse.doff[f] : nd;
+        a.gse.before[f] = d0 < nd ? a.gse.out[d0].before : og;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            G->slot[r] = GseSlot{on[r], id[r], proto[r], ctr[r], crc[r]};
+            G->save[r] = GseSave{head[r], carry[r], on[r]};
+        }
+        G->old = G->cur;
+        G->cur ^= 1;
+        G->last_crc_err = last_err;
+        G->pdus = pdus;
+        G->crc_errors = errs;
+        G->dropped = dropped;
+        G->out_bytes = og;
+    }
+}
+
+__device__ inline void cta_copy(uint8_t* dst, const uint8_t* src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+// data bytes of the fragments of one chain, each to its place in the reassembled PDU
+__device__ inline void gse_copy_chain(const TsArgs& a, uint8_t* base, int first, int stop_at) {
+    for (int x = first; x >= 0; x = a.gse.nxt[x]) {
+        const GseDesc e = a.gse.desc[x];
+        cta_copy(base + a.gse.out[x].pos, a.bb + e.src + e.hdr, e.kind == 3 ? (int)e.len - 4 : (int)e.len);
+        if (x == stop_at) break;
+    }
+}
+
+// One CTA per delivered PDU: 2-byte zero GRE header, the protocol type when it is IPv4/IPv6 (:262-271,349-358), the
+// payload.  Three more CTAs save what the open slots carry into the next call.
+__global__ void __launch_bounds__(256) gse_copy_kernel(const TsArgs a) {
+    const int phase = a.state->phase;
+    if (phase != 2 && phase != 3) return;   // 3: no room for the output, but the slots moved on: their heads are still saved
+    const GseState* G = a.gse.state;
+    const int nd = max(G->ndesc, 0);
+    const uint8_t* oldbuf = a.gse.buf + (size_t)G->old * 3 * kGseBuf;
+    uint8_t* newbuf = a.gse.buf + (size_t)(G->old ^ 1) * 3 * kGseBuf;
+    for (int d = blockIdx.x; d < nd + 3; d += gridDim.x) {
+        if (d >= nd) {
+            const int r = d - nd;
+            const GseSave sv = G->save[r];
+            if (!sv.active) continue;
+            if (sv.carry > 0) cta_copy(newbuf + (size_t)r * kGseBuf, oldbuf + (size_t)r * kGseBuf, sv.carry);
+            gse_copy_chain(a, newbuf + (size_t)r * kGseBuf, sv.head, -1);
+            continue;
+        }
+        const GseOut o = a.gse.out[d];
+        if (o.emit == 0 || phase != 2) continue;
+        const GseDesc e = a.gse.desc[d];
+        uint8_t* dst = a.out + a.plan[e.frame].out_off + (o.before - a.gse.before[e.frame]);
+        const int proto = e.kind == 0 ? (int)e.proto : a.gse.aux2[d];
+        const int hl = (proto == 0x0800 || proto == 0x86DD) ? 4 : 2;
+        if (threadIdx.x < hl) dst[threadIdx.x] = threadIdx.x < 2 ? 0 : (threadIdx.x == 2 ? (uint8_t)(proto >> 8) : (uint8_t)proto);
+        if (e.kind == 0) {
+            cta_copy(dst + hl, a.bb + e.src + e.hdr, e.len);
+        } else {
+            const int aux = a.gse.aux[d];
+            if (aux >= 0) cta_copy(dst + hl, oldbuf + (size_t)(aux & 3) * kGseBuf, aux >> 2);
+            gse_copy_chain(a, dst + hl, o.link, d);
+        }
+    }
+}
+
 }  // namespace
 
 int ts_launch(const TsArgs& a, cudaStream_t stream) {
     if (a.cnt > 0) ts_header_kernel<<<(a.cnt + kHeaderThreads - 1) / kHeaderThreads, kHeaderThreads, 0, stream>>>(a);
     ts_plan_kernel<<<1, kPlanThreads, 0, stream>>>(a);   // also for cnt == 0: the counters are per call
     if (a.cnt > 0) ts_copy_kernel<<<a.cnt, kCopyThreads, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int gse_launch_count(const TsArgs& a, cudaStream_t stream) {
+    if (a.cnt > 0) gse_count_kernel<<<(a.cnt + kGseThreads - 1) / kGseThreads, kGseThreads, 0, stream>>>(a);
+    gse_scan_kernel<<<1, kPlanThreads, 0, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int gse_launch_rest(const TsArgs& a, cudaStream_t stream) {
+    const int per_frame = (a.cnt + kGseThreads - 1) / kGseThreads;
+    const int by_desc = std::max(1, std::min((a.gse.cap + kGseThreads - 1) / kGseThreads, 1184));
+    if (a.cnt > 0) gse_fill_kernel<<<per_frame, kGseThreads, 0, stream>>>(a);
+    gse_crc_kernel<<<by_desc, kGseThreads, 0, stream>>>(a);
+    gse_assemble_kernel<<<1, 32, 0, stream>>>(a);
+    TsArgs b = a;
+    b.mode = 2;
+    b.copy_phase = 2;
+    ts_plan_kernel<<<1, kPlanThreads, 0, stream>>>(b);
+    if (a.cnt > 0) ts_copy_kernel<<<a.cnt, kCopyThreads, 0, stream>>>(b);
+    gse_copy_kernel<<<std::max(1, std::min(a.gse.cap + 3, 2368)), 256, 0, stream>>>(b);
     return (int)cudaGetLastError();
 }
 

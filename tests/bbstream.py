@@ -185,3 +185,72 @@ def random_ts_scenario(rng, kbch, nframes=80):
         else:
             f[i, :10] = bbheader(0xF0, 1504, 8 * int(rng.integers(1, 3)), 0x47, 0)     # DFL of 8 or 16 bits
     return f
+
+
+def random_gse_scenario(rng, kbch, nframes=40, ts_every=0):
+    """random GSE stream: complete PDUs (with and without label, known and unknown protocol types) and fragmented
+    PDUs whose pieces are spread over the following frames, up to five FragIDs in flight at once (the parser has
+    three slots: the others are dropped), FragIDs restarted before their last fragment, CRC-32 failures, tiny
+    fragments.  ts_every > 0: every ts_every-th frame is a TS frame, and now and then a frame with a broken header
+    followed by the all-padding frame a resynchronising parser needs (it enters the next field one byte late).
+    Returns frames [n][kbch/8]."""
+    kb = kbch // 8
+    room_full = kb - 10
+    protos = [0x0800, 0x86DD, 0x88B5, 0x0806]
+    lab = bytes(range(0x10, 0x16))
+    pending = []            # queues of fragments still to be sent, one list per PDU in flight
+    fields = [[]]           # the parser starts out of sync: an all-padding frame first
+    for f in range(nframes):
+        room = room_full - int(rng.integers(0, 40))
+        pk = []
+        # fragments of PDUs in flight first, in random order, at most one piece of each per frame
+        order = list(rng.permutation(len(pending)))
+        for k in order:
+            q = pending[k]
+            if q and len(q[0]) <= room and rng.random() < 0.8:
+                pk.append(q.pop(0))
+                room -= len(pk[-1])
+        pending = [q for q in pending if q]
+        while room > 40 and rng.random() < 0.85:
+            kind = rng.random()
+            label = lab if rng.random() < 0.5 else None
+            proto = int(rng.choice(protos))
+            if kind < 0.55 or len(pending) >= 5:
+                n = int(rng.integers(1, min(1500, room - 14)))
+                pk.append(gse_complete(rng.integers(0, 256, n, dtype=np.uint8).tobytes(), proto, label=label))
+            else:
+                n = int(rng.integers(30, 6000))
+                pdu = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+                nparts = int(rng.integers(2, 6))
+                cuts = sorted(set(int(x) for x in rng.integers(1, n, nparts - 1)))
+                # every piece must fit a data field together with its header
+                while any(b - a > room_full - 60 for a, b in zip([0] + cuts, cuts + [n])):
+                    cuts = sorted(set(cuts + [int(x) for x in rng.integers(1, n, 2)]))
+                frag_id = int(rng.choice([3, 7, 9, 200, 255, 0]))
+                parts = gse_fragments(pdu, proto, frag_id, cuts, label=label)
+                r = rng.random()
+                if r < 0.15:      # CRC-32 failure
+                    parts[-1] = parts[-1][:-1] + bytes([parts[-1][-1] ^ 0x40])
+                elif r < 0.25:    # the last fragment never comes
+                    parts = parts[:-1]
+                if len(parts[0]) > room:
+                    break
+                pk.append(parts.pop(0))
+                pending.append(parts)
+            room -= len(pk[-1])
+        fields.append(pk)
+    frames = gse_bbframes(kbch, fields)
+    if ts_every:
+        tsf, _ = ts_bbframes(kbch, ts_packets(nframes * (kb // 188 + 2), rng), first_byte=int(rng.integers(0, 188)))
+        out, t = [], 0
+        for f in range(len(frames)):
+            if f % ts_every == ts_every - 1:
+                out.append(tsf[t]); t += 1
+                if rng.random() < 0.3:                          # sync loss, then the padding frame
+                    bad = tsf[t].copy(); t += 1
+                    bad[9] ^= 0x55
+                    out.append(bad)
+                    out.append(gse_bbframes(kbch, [[]])[0])
+            out.append(frames[f])
+        frames = np.stack(out)
+    return frames

@@ -44,7 +44,7 @@ def test_oracle_reproduces_reference_chain(name):
     assert len(set(g["iters"].tolist())) >= 2
 
 
-TS_FIXTURES = ["tsparse_ts_n12", "tsparse_odd_s14", "tsparse_gse_n12"]
+TS_FIXTURES = ["tsparse_ts_n12", "tsparse_odd_s14", "tsparse_gse_n12", "tsparse_gsemix_s12"]
 
 
 def _ts_header_fields(h):

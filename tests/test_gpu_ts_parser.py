@@ -30,6 +30,7 @@ def compare(kbch, batches, cap=65536 * 10):
         assert np.array_equal(got, want)
         st = o.stats()
         assert (g.last_bb_cnt, g.last_bb_proc) == (st["cnt"], st["proc"])
+        assert g.last_gse_crc_err == st["gse_err"]
         assert g.have_header == bool(st["have"])
         if st["have"]:
             assert gpu_header_fields(g.last_header) == header_fields(st["hdr"])
@@ -74,19 +75,104 @@ def test_ts_parser_recovers_after_running_out_of_room():
             compare(kbch, [frames[:4], frames[4:9], frames[9:12], frames[12:]], cap=[cap0, 65536 * 10, 188 * 2 + 5, 65536 * 10])
 
 
-def test_gse_frames_are_counted_not_unpacked():
+def test_gse_frames_can_be_counted_without_unpacking():
     rng = np.random.default_rng(8)
     kbch = KBCH["n1/2"]
     frames = bbstream.gse_bbframes(kbch, bbstream.gse_scenario(rng))
     g = pkg.BBFrameTSParser()
     g.setFrameSize(kbch)
+    g.set_gse(-1)
     out = g.work(frames)
     assert len(out) == 0 and g.last_bb_proc == len(frames) and g.gse_frames == len(frames)
     assert g.last_header.ts_gs == 1
     g.close()
 
 
-@pytest.mark.parametrize("name", ["tsparse_ts_n12", "tsparse_odd_s14"])
+def test_gse_pdus_match_oracle():
+    """the scenario of the oracle's own test (complete PDUs, three interleaved reassemblies, a CRC-32 failure), as one
+    call, frame by frame (every reassembly crosses calls: heads carried in the device-side buffers), and in between"""
+    rng = np.random.default_rng(8)
+    for name in ("n1/2", "n9/10"):
+        kbch = KBCH[name]
+        frames = bbstream.gse_bbframes(kbch, bbstream.gse_scenario(rng))
+        compare(kbch, [frames])
+        compare(kbch, [frames[i:i + 1] for i in range(len(frames))])
+        compare(kbch, [frames[:2], frames[2:3], frames[3:]])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_gse_random_streams_match_oracle(seed):
+    """random GSE traffic -- more FragIDs in flight than reassembly slots, FragIDs restarted, CRC failures, PDUs that
+    never end -- alone and mixed with TS frames and sync losses (a frame entered out of sync is walked one byte
+    late, :157-168), cut into calls at random places"""
+    rng = np.random.default_rng(2000 + seed)
+    kbch = [7032, 14232, 32208, 58192][seed % 4]
+    f = bbstream.random_gse_scenario(rng, kbch, nframes=30 if seed < 8 else 300, ts_every=0 if seed % 2 else 4)
+    cuts = sorted(set(int(x) for x in rng.integers(0, len(f) + 1, 5)) | {0, len(f)})
+    compare(kbch, [f[a:b] for a, b in zip(cuts[:-1], cuts[1:])], cap=65536 * 64)
+    compare(kbch, [f], cap=65536 * 64)
+
+
+def test_gse_counters_and_refused_calls():
+    rng = np.random.default_rng(77)
+    kbch = 7032   # s1/2
+    f = bbstream.random_gse_scenario(rng, kbch, nframes=40)
+    want = OrcParser(kbch).work(f, 65536 * 16)
+    g = pkg.BBFrameTSParser()
+    g.setFrameSize(kbch)
+    # too little room for the GSE output: refused as a whole (the reference would overrun the buffer)
+    with pytest.raises(pkg.DVBS2FecError) as e:
+        g.work(f, len(f), len(want) // 2)
+    assert e.value.code == pkg.ENOSPC
+    g.close()
+    g = pkg.BBFrameTSParser()
+    g.setFrameSize(kbch)
+    got = g.work(f, len(f), len(want) + 189)
+    assert np.array_equal(got, want)
+    c = g.gse_counters
+    assert c["pdus"] > 20 and c["crc_errors"] >= 1 and c["malformed"] == 0
+    # a packet whose length leads outside the input: reported, in bounds, nothing else disturbed
+    bad = f[:3].copy()
+    bad[2, 10] = 0xC0 | 0x30 | 0x0F   # complete PDU, no label, 12-bit length 0xFFF.. inside the LAST frame of the call
+    bad[2, 11] = 0xFF
+    g.work(bad)
+    assert g.gse_counters["malformed"] == 1
+    g.close()
+
+
+def test_gse_device_buffers_async_pool():
+    """dvbs2fec_ts_work_device: the GSE pass is enqueued blindly behind the TS pass with a descriptor pool sized in
+    advance; results equal the host-buffer call, a pool that is too small refuses the call"""
+    import torch
+    rng = np.random.default_rng(5150)
+    kbch = KBCH["n1/2"]
+    f = bbstream.random_gse_scenario(rng, kbch, nframes=60, ts_every=5)
+    want = OrcParser(kbch).work(f, 65536 * 64)
+    dev = torch.device("cuda", 0)
+    d_bb = torch.from_numpy(f).to(dev)
+    d_out = torch.zeros(f.size + 3 * 70000, dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+    g = pkg.BBFrameTSParser()
+    g.setFrameSize(kbch)
+    got, at = [], 0
+    for n in (1, 7, len(f) - 8):
+        g.work_device(d_bb[at:at + n].data_ptr(), n, d_out.data_ptr(), d_out.numel(), d_n.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        got.append(d_out[:int(d_n.item())].cpu().numpy().copy())
+        at += n
+    assert np.array_equal(np.concatenate(got), want)
+    g.close()
+    g = pkg.BBFrameTSParser()
+    g.setFrameSize(kbch)
+    g.set_gse(3)
+    g.work_device(d_bb.data_ptr(), len(f), d_out.data_ptr(), d_out.numel(), d_n.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    assert int(d_n.item()) == pkg.ENOSPC
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["tsparse_ts_n12", "tsparse_odd_s14", "tsparse_gse_n12", "tsparse_gsemix_s12"])
 def test_cuda_reproduces_reference_ts_parser(name):
     gold = dict(np.load(os.path.join(GOLD, name + ".npz")))
     g = pkg.BBFrameTSParser()
@@ -97,7 +183,7 @@ def test_cuda_reproduces_reference_ts_parser(name):
         n = int(gold["out_len"][k])
         assert len(out) == n and np.array_equal(out, gold["out"][at:at + n])
         at += n
-        assert [g.last_bb_cnt, g.last_bb_proc] == [int(x) for x in gold["stats"][k][11:13]]
+        assert [g.last_bb_cnt, g.last_bb_proc, g.last_gse_crc_err] == [int(x) for x in gold["stats"][k][11:14]]
         if g.have_header:
             assert gpu_header_fields(g.last_header) == [int(x) for x in gold["stats"][k][:11]]
     g.close()

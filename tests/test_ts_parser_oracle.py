@@ -169,6 +169,18 @@ def test_gse_matches_reference_parser():
 
 
 @needs_ref
+@pytest.mark.parametrize("seed", range(10))
+def test_gse_random_streams_match_reference_parser(seed):
+    """random GSE traffic (more FragIDs in flight than slots, restarts, CRC failures), alone and mixed with TS
+    frames and sync losses, cut into calls at random places"""
+    rng = np.random.default_rng(2000 + seed)
+    kbch = [7032, 14232, 32208, 58192][seed % 4]
+    f = bbstream.random_gse_scenario(rng, kbch, nframes=30, ts_every=0 if seed % 2 else 4)
+    cuts = sorted(set(int(x) for x in rng.integers(0, len(f) + 1, 5)) | {0, len(f)})
+    _compare(kbch, [f[a:b] for a, b in zip(cuts[:-1], cuts[1:])], cap=65536 * 16)
+
+
+@needs_ref
 @pytest.mark.parametrize("seed", range(12))
 def test_ts_random_streams_match_reference_parser(seed):
     rng = np.random.default_rng(1000 + seed)

@@ -98,6 +98,9 @@ def ts_parser_fixture(kind, kbch, seed):
         pk = bbstream.ts_packets(260, rng)
         frames, _ = bbstream.ts_bbframes(kbch, pk, first_byte=101)
         cuts = [0, 3, 4, len(frames)]
+    elif kind == "gse_mixed":   # random GSE traffic between TS frames and sync losses
+        frames = bbstream.random_gse_scenario(rng, kbch, nframes=24, ts_every=4)
+        cuts = [0, 5, 6, 19, len(frames)]
     else:
         frames = bbstream.gse_bbframes(kbch, bbstream.gse_scenario(rng))
         cuts = [0, 2, 3, len(frames)]
@@ -135,6 +138,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "tsparse_ts_n12.npz"), **ts_parser_fixture("ts", 32208, 11))
     np.savez_compressed(os.path.join(OUT, "tsparse_odd_s14.npz"), **ts_parser_fixture("ts_odd", 3072, 5))
     np.savez_compressed(os.path.join(OUT, "tsparse_gse_n12.npz"), **ts_parser_fixture("gse", 32208, 8))
+    np.savez_compressed(os.path.join(OUT, "tsparse_gsemix_s12.npz"), **ts_parser_fixture("gse_mixed", 7032, 21))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
