@@ -79,6 +79,25 @@ void orc_deinterleave(int constellation, int shortframe, int rate, const int8_t*
 int orc_bb_to_soft(const orc_constellation* c, int constellation, int shortframe, int rate,
                    const float* plframe, int8_t* out);
 
+/* ---- row 8(f)-3 (oracle_plsync.c): PL sync, PLHEADER demodulation, coarse frequency error ---- */
+/* complex symbols are interleaved float pairs (re, im) */
+typedef struct orc_plsync orc_plsync;
+int orc_raw_frame_size(int slot_num, int pilots);                                     /* dvbs2_pl_sync.cpp:15-30 */
+orc_plsync* orc_plsync_create(int slot_num, int pilots);                              /* S2PLSyncBlock::init */
+void orc_plsync_destroy(orc_plsync* p);
+int orc_plsync_process(orc_plsync* p, int count, const float* in, float* out);        /* ::process (:80-100) */
+void orc_plsync_stats(const orc_plsync* p, int* raw_frame_size, int* current_position, double* best_match);
+typedef struct orc_plhdr orc_plhdr;
+orc_plhdr* orc_plhdr_create(float loop_bw);                                           /* S2PLHDRDemod::init */
+void orc_plhdr_destroy(orc_plhdr* p);
+/* S2PLHDRDemod::process: one frame in, the 90 rotated header symbols out; res = {modcod, shortframes, pilots};
+ * loop = {phase, freq} of the phase loop after the call */
+int orc_plhdr_process(orc_plhdr* p, int count, const float* in, float* out90, int* res, float* loop);
+/* dvbs2_pilot_coarse_fed; rn = orc_pl_rn(codenum) */
+float orc_coarse_fed(const float* frame, int raw_frame_size, int pilots, int pls_code, const uint8_t* rn);
+void orc_plheader_symbols(int pls_code, float* out90);                                /* s2_sof + s2_plscodes symbols */
+uint64_t orc_pls_codeword(int pls_code);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,12 @@
 #include "common/dsp/demod/constellation.h"
 #include "dvbs2/bbframe_ts_parser.h"
 #include "dvbs2/codings/s2_scrambling.h"
+// row 8(f)-3: PL sync, PLHEADER demodulation, coarse frequency error -- compiled against shim/dsp/processor.h etc.
+#define private public   // the phase loop of S2PLHDRDemod is a private member; the tests compare its state
+#include "dvbs2/dvbs2_pl_sync.h"
+#include "dvbs2/dvbs2_plhdr_demod.h"
+#undef private
+#include "dvbs2/dvbs2_fed.h"
 
 using namespace dsp::dvbs2;
 
@@ -269,5 +275,57 @@ void ref_pl_descramble(int codenum, const float* in, int nsym, float* out, int s
         out[2 * i + 1] = r.im;
     }
 }
+
+// ---- S2PLSyncBlock (dvbs2/dvbs2_pl_sync.h:11-66): init(nullptr, slot_num, pilots, sof, pls), then process() ----
+namespace {
+s2_sof g_sof;
+s2_plscodes g_pls;
+}
+void* ref_plsync_create(int slot_num, int pilots) {
+    auto* b = new S2PLSyncBlock();
+    b->init(nullptr, slot_num, pilots != 0, &g_sof, &g_pls);
+    return b;
+}
+int ref_plsync_process(void* h, int count, const float* in, float* out) {
+    return static_cast<S2PLSyncBlock*>(h)->process(count, (dsp::complex_t*)in, (dsp::complex_t*)out);
+}
+void ref_plsync_stats(void* h, int* raw_frame_size, int* current_position, double* best_match) {
+    auto* b = static_cast<S2PLSyncBlock*>(h);
+    *raw_frame_size = b->raw_frame_size;
+    *current_position = b->current_position;
+    *best_match = b->best_match;
+}
+// ---- S2PLHDRDemod (dvbs2/dvbs2_plhdr_demod.h:13-49) ----
+void* ref_plhdr_create(float loop_bw) {
+    auto* b = new S2PLHDRDemod();
+    b->init(nullptr, loop_bw, &g_sof, &g_pls);
+    return b;
+}
+// count symbols of one frame in, the 90 header symbols out; res = {modcod, shortframes, pilots}; loop = {phase, freq}
+int ref_plhdr_process(void* h, int count, const float* in, float* out90, int* res, float* loop) {
+    auto* b = static_cast<S2PLHDRDemod*>(h);
+    std::vector<dsp::complex_t> out(count > 90 ? count : 90);
+    int r = b->process(count, (dsp::complex_t*)in, out.data());
+    memcpy(out90, out.data(), 90 * sizeof(dsp::complex_t));
+    res[0] = b->detect_modcod;
+    res[1] = b->detect_shortframes;
+    res[2] = b->detect_pilots;
+    loop[0] = b->pcl.phase;
+    loop[1] = b->pcl.freq;
+    return r;
+}
+// ---- dvbs2_pilot_coarse_fed (dvbs2/dvbs2_fed.h:7-48) ----
+float ref_coarse_fed(const float* frame, int raw_frame_size, int pilots, int pls_code, int codenum) {
+    static std::map<int, std::unique_ptr<dsp::dvbs2::S2Scrambling>> cache;
+    auto& sc = cache[codenum];
+    if (!sc) sc.reset(new dsp::dvbs2::S2Scrambling(codenum));
+    return dvbs2_pilot_coarse_fed((dsp::complex_t*)frame, raw_frame_size, pilots != 0, pls_code, g_sof, g_pls, sc.get());
+}
+// symbols of the PLHEADER of PLS index `pls_code` (s2_defs.h:16-31,33-86): 26 SOF + 64 code symbols
+void ref_plheader_symbols(int pls_code, float* out90) {
+    for (int i = 0; i < 26; ++i) { out90[2 * i] = g_sof.symbols[i].re; out90[2 * i + 1] = g_sof.symbols[i].im; }
+    for (int i = 0; i < 64; ++i) { out90[52 + 2 * i] = g_pls.symbols[pls_code][i].re; out90[52 + 2 * i + 1] = g_pls.symbols[pls_code][i].im; }
+}
+unsigned long long ref_pls_codeword(int pls_code) { return g_pls.codewords[pls_code]; }
 
 } // extern "C"

@@ -16,6 +16,8 @@ namespace dsp {
         }
         complex_t operator+(const complex_t& b) const { return complex_t{re + b.re, im + b.im}; }
         complex_t operator-(const complex_t& b) const { return complex_t{re - b.re, im - b.im}; }
+        complex_t& operator+=(const complex_t& b) { re += b.re; im += b.im; return *this; }   // dvbs2_pl_sync.cpp:176-190
+        complex_t& operator-=(const complex_t& b) { re -= b.re; im -= b.im; return *this; }
         complex_t conj() const { return complex_t{re, -im}; }
         float phase() const { return atan2f(im, re); }
         float amplitude() const { return sqrtf((re * re) + (im * im)); }

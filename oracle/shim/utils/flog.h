@@ -4,4 +4,6 @@
 #include <cstdio>
 namespace flog {
     inline void error(const char* msg) { fprintf(stderr, "[flog] %s\n", msg); }
+    template <typename... A>
+    inline void info(const char*, A...) {}   // dvbs2_pl_sync.cpp:29,68 log the pilot frame size
 }

@@ -25,7 +25,8 @@ _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 
 def _build_oracle():
     so = os.path.join(ORACLE_DIR, "libdvbs2_oracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_ldpc.c", "oracle_bch.c", "oracle_demap.c", "oracle_ts.c", "oracle.h")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_ldpc.c", "oracle_bch.c", "oracle_demap.c", "oracle_ts.c", "oracle_plsync.c",
+                                                   "oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
     return so
@@ -74,6 +75,21 @@ def oracle():
         lib.orc_bbheader_seal.argtypes = [_u8p]
         lib.orc_up_crc8.argtypes = [_u8p]
         lib.orc_up_crc8.restype = C.c_uint8
+        lib.orc_raw_frame_size.argtypes = [C.c_int, C.c_int]
+        lib.orc_plsync_create.argtypes = [C.c_int, C.c_int]
+        lib.orc_plsync_create.restype = C.c_void_p
+        lib.orc_plsync_destroy.argtypes = [C.c_void_p]
+        lib.orc_plsync_process.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p]
+        lib.orc_plsync_stats.argtypes = [C.c_void_p, ip, ip, C.POINTER(C.c_double)]
+        lib.orc_plhdr_create.argtypes = [C.c_float]
+        lib.orc_plhdr_create.restype = C.c_void_p
+        lib.orc_plhdr_destroy.argtypes = [C.c_void_p]
+        lib.orc_plhdr_process.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _i32p, _f32p]
+        lib.orc_coarse_fed.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _u8p]
+        lib.orc_coarse_fed.restype = C.c_float
+        lib.orc_plheader_symbols.argtypes = [C.c_int, _f32p]
+        lib.orc_pls_codeword.argtypes = [C.c_int]
+        lib.orc_pls_codeword.restype = C.c_uint64
         _oracle = lib
     return _oracle
 
@@ -104,6 +120,19 @@ def ref():
         lib.ref_mod.argtypes = [C.c_int, C.c_float, C.c_float, _u8p, C.c_int, _f32p]
         if hasattr(lib, "ref_pl_descramble"):
             lib.ref_pl_descramble.argtypes = [C.c_int, _f32p, C.c_int, _f32p, C.c_int]
+        if hasattr(lib, "ref_plsync_create"):
+            lib.ref_plsync_create.argtypes = [C.c_int, C.c_int]
+            lib.ref_plsync_create.restype = C.c_void_p
+            lib.ref_plsync_process.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p]
+            lib.ref_plsync_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+            lib.ref_plhdr_create.argtypes = [C.c_float]
+            lib.ref_plhdr_create.restype = C.c_void_p
+            lib.ref_plhdr_process.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _i32p, _f32p]
+            lib.ref_coarse_fed.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int]
+            lib.ref_coarse_fed.restype = C.c_float
+            lib.ref_plheader_symbols.argtypes = [C.c_int, _f32p]
+            lib.ref_pls_codeword.argtypes = [C.c_int]
+            lib.ref_pls_codeword.restype = C.c_uint64
         if hasattr(lib, "ref_ts_create"):
             lib.ref_ts_create.argtypes = [C.c_int]
             lib.ref_ts_create.restype = C.c_void_p
