@@ -178,6 +178,49 @@ int dvbs2fec_ts_gse_stats(dvbs2fec_ts_parser* p, int* last_gse_crc_err, int* pdu
 int dvbs2fec_ts_stats(dvbs2fec_ts_parser* p, dvbs2fec_bbheader* last_header, int* last_bb_cnt, int* last_bb_proc,
                       int* gse_frames);
 
+/* ---- upstream of the decode stage: PL frame synchronisation, PLHEADER demodulation, coarse frequency error
+ *      (SURVEY.md 8(f) rank 3), as DVBS2Demod::process drives them per block of clock-recovered symbols
+ *      (dvbs2/module_dvbs2_demod.cpp:300-316).  Complex symbols are interleaved float pairs (re, im).  One object
+ *      holds the state of S2PLSyncBlock and S2PLHDRDemod of one demodulator; it lives on the device between calls. ---- */
+typedef struct dvbs2fec_plsync dvbs2fec_plsync;
+int dvbs2fec_plsync_create(int device, dvbs2fec_plsync** out);
+void dvbs2fec_plsync_destroy(dvbs2fec_plsync* p);
+/* S2PLSyncBlock::init / setParams (dvbs2/dvbs2_pl_sync.cpp:10-35,47-76): slots of 90 payload symbols per frame and
+ * pilots -> raw_frame_size; the gathering state starts over.  reset (:37-45) only does the latter. */
+int dvbs2fec_plsync_set_params(dvbs2fec_plsync* p, int slot_num, int pilots);
+int dvbs2fec_plsync_reset(dvbs2fec_plsync* p);
+int dvbs2fec_plsync_raw_frame_size(const dvbs2fec_plsync* p);
+/* S2PLSyncBlock::process (dvbs2/dvbs2_pl_sync.cpp:80-165): count symbols in; every frame completed by them comes out,
+ * raw_frame_size symbols each, starting at the position the PLHEADER correlator chose.  Returns the number of symbols
+ * written (a multiple of raw_frame_size; out needs room for count + raw_frame_size).  Host buffers, synchronous. */
+int dvbs2fec_plsync_process(dvbs2fec_plsync* p, int count, const float* in, float* out);
+/* same on device buffers, asynchronous on `stream`: at most max_frames frames are written to d_out, their number to
+ * d_nframes (optional device int) */
+int dvbs2fec_plsync_process_device(dvbs2fec_plsync* p, int count, const float* d_in, float* d_out, int max_frames,
+                                   int* d_nframes, void* stream);
+/* public members after process (dvbs2_pl_sync.h:38-40): current_position, best_match; pending = symbols gathered
+ * but not delivered yet.  Returns the frames the last call delivered. */
+int dvbs2fec_plsync_stats(dvbs2fec_plsync* p, int* current_position, double* best_match, int* pending);
+/* S2PLHDRDemod::init (dvbs2/dvbs2_plhdr_demod.cpp:5-12): loop bandwidth; phase and frequency start at 0 */
+int dvbs2fec_plhdr_set_params(dvbs2fec_plsync* p, float loop_bw);
+/* S2PLHDRDemod::process (dvbs2/dvbs2_plhdr_demod.cpp:33-67), once per frame in order: nframes frames of raw_frame_size
+ * symbols in; headers = 90 phase-corrected header symbols per frame (what process() leaves in out[0..90));
+ * results = four ints per frame: detect_modcod, detect_shortframes, detect_pilots, PLS index; loop_state (optional)
+ * = phase and frequency of the loop after the last frame.  The sin/cos of the loop are evaluated on the device:
+ * header symbols and loop state agree with the reference to float rounding (tests: 1e-4), the PLS fields exactly
+ * wherever no header symbol lies within that distance of a decision boundary. */
+int dvbs2fec_plhdr_process(dvbs2fec_plsync* p, int nframes, const float* frames, float* headers, int32_t* results,
+                           float* loop_state);
+int dvbs2fec_plhdr_process_device(dvbs2fec_plsync* p, int nframes, const float* d_frames, float* d_headers,
+                                  int32_t* d_results, void* stream);
+/* dvbs2_pilot_coarse_fed (dvbs2/dvbs2_fed.h:7-48) for nframes frames: one float per frame (what module_dvbs2_demod.cpp
+ * :302 feeds back into the frequency shifter).  pls_code = PLS index of the configured MODCOD (S2PLLBlock::pls_code),
+ * codenum = Gold code of the PL scrambler (pilot blocks are descrambled; ignored without pilots). */
+int dvbs2fec_coarse_fed(dvbs2fec_plsync* p, int nframes, const float* frames, int pilots, int pls_code, int codenum,
+                        float* err);
+int dvbs2fec_coarse_fed_device(dvbs2fec_plsync* p, int nframes, const float* d_frames, int pilots, int pls_code,
+                               int codenum, float* d_err, void* stream);
+
 /* ---- in-tree transmitter for synthetic input (not part of the reference's decode path) ---- */
 /* bbframe: kbch/8 bytes -> code_bits: N bytes of 0/1 (BB scramble, BCH, LDPC; EN 302 307 5.2-5.3) */
 int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits);

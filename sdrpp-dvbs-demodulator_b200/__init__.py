@@ -111,6 +111,20 @@ def lib():
     L.dvbs2fec_ts_stats.argtypes = [vp, C.POINTER(BBHeader), ip, ip, ip]
     L.dvbs2fec_ts_set_gse.argtypes = [vp, C.c_int]
     L.dvbs2fec_ts_gse_stats.argtypes = [vp, ip, ip, ip, ip, ip]
+    L.dvbs2fec_plsync_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.dvbs2fec_plsync_destroy.argtypes = [vp]
+    L.dvbs2fec_plsync_destroy.restype = None
+    L.dvbs2fec_plsync_set_params.argtypes = [vp, C.c_int, C.c_int]
+    L.dvbs2fec_plsync_reset.argtypes = [vp]
+    L.dvbs2fec_plsync_raw_frame_size.argtypes = [vp]
+    L.dvbs2fec_plsync_process.argtypes = [vp, C.c_int, vp, vp]
+    L.dvbs2fec_plsync_process_device.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp]
+    L.dvbs2fec_plsync_stats.argtypes = [vp, ip, C.POINTER(C.c_double), ip]
+    L.dvbs2fec_plhdr_set_params.argtypes = [vp, C.c_float]
+    L.dvbs2fec_plhdr_process.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.dvbs2fec_plhdr_process_device.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.dvbs2fec_coarse_fed.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.dvbs2fec_coarse_fed_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]
     _lib = L
     return L
 
@@ -399,3 +413,70 @@ class BBFrameTSParser:
 
     def work_device(self, d_bb_ptr, cnt, d_out_ptr, buffer_outsize, d_produced_ptr=0, stream_ptr=0):
         _check(lib().dvbs2fec_ts_work_device(self._p, d_bb_ptr, cnt, d_out_ptr, buffer_outsize, d_produced_ptr, stream_ptr))
+
+
+class S2PLSyncBlock:
+    """dvbs2/dvbs2_pl_sync.h:11-66 on the device, together with the PLHEADER demodulator (S2PLHDRDemod,
+    dvbs2/dvbs2_plhdr_demod.h:13-49) and the coarse frequency error detector (dvbs2/dvbs2_fed.h:7-48) that
+    DVBS2Demod::process runs on its output.  Symbols are complex64 arrays."""
+
+    def __init__(self, slot_num, pilots, device=0, loop_bw=0.004):
+        self._p = C.c_void_p()
+        _check(lib().dvbs2fec_plsync_create(device, C.byref(self._p)))
+        self.setParams(slot_num, pilots)
+        _check(lib().dvbs2fec_plhdr_set_params(self._p, loop_bw))
+        self.current_position, self.best_match, self.pending = -1, 0.0, 0
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().dvbs2fec_plsync_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setParams(self, slot_num, pilots):
+        _check(lib().dvbs2fec_plsync_set_params(self._p, slot_num, int(pilots)))
+        self.raw_frame_size = _check(lib().dvbs2fec_plsync_raw_frame_size(self._p))
+
+    def reset(self):
+        _check(lib().dvbs2fec_plsync_reset(self._p))
+
+    def stats(self):
+        a, b, c = C.c_int(), C.c_double(), C.c_int()
+        n = _check(lib().dvbs2fec_plsync_stats(self._p, C.byref(a), C.byref(b), C.byref(c)))
+        self.current_position, self.best_match, self.pending = a.value, b.value, c.value
+        return n
+
+    def process(self, symbols):
+        x = np.ascontiguousarray(symbols, np.complex64)
+        out = np.zeros(len(x) + 2 * self.raw_frame_size, np.complex64)
+        n = _check(lib().dvbs2fec_plsync_process(self._p, len(x), _ptr(x), _ptr(out)))
+        self.stats()
+        return out[:n]
+
+    def process_device(self, d_in_ptr, count, d_out_ptr, max_frames, d_nframes_ptr=0, stream_ptr=0):
+        _check(lib().dvbs2fec_plsync_process_device(self._p, count, d_in_ptr, d_out_ptr, max_frames, d_nframes_ptr, stream_ptr))
+
+    def plhdr_set_params(self, loop_bw):
+        _check(lib().dvbs2fec_plhdr_set_params(self._p, loop_bw))
+
+    def plhdr_process(self, frames):
+        """frames [n][raw_frame_size] -> (headers [n][90] complex64, results [n][4] int32 = modcod, shortframes, pilots,
+        PLS index, loop state (phase, freq))"""
+        x = np.ascontiguousarray(frames, np.complex64).reshape(-1, self.raw_frame_size)
+        n = len(x)
+        hdr = np.zeros((n, 90), np.complex64)
+        res = np.zeros((n, 4), np.int32)
+        loop = np.zeros(2, np.float32)
+        _check(lib().dvbs2fec_plhdr_process(self._p, n, _ptr(x), _ptr(hdr), _ptr(res), _ptr(loop)))
+        return hdr, res, loop
+
+    def coarse_fed(self, frames, pilots, pls_code, codenum=0):
+        x = np.ascontiguousarray(frames, np.complex64).reshape(-1, self.raw_frame_size)
+        err = np.zeros(len(x), np.float32)
+        _check(lib().dvbs2fec_coarse_fed(self._p, len(x), _ptr(x), int(pilots), pls_code, codenum, _ptr(err)))
+        return err

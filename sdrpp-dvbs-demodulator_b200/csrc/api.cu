@@ -40,6 +40,15 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+}  // namespace
+namespace s2 {
+// for the C-ABI entry points that live in other translation units (pl_api.cu)
+int api_fail(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+}  // namespace s2
+namespace {
 #define CU(call)                                                                              \
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \
