@@ -189,7 +189,7 @@ int dvbs2fec_plsync_raw_frame_size(const dvbs2fec_plsync* p) { return p ? p->rfs
 
 // common part: `count` new symbols are already behind the carried ones in work[cur]
 static int plsync_run(dvbs2fec_plsync* p, int count, const float2* d_append, float2* d_out, int* d_nframes, int max_frames, cudaStream_t st) {
-    CU(p->metric.reserve((size_t)p->pend_ub + count + 1));
+    CU(p->metric.reserve((size_t)2 * p->rfs + count + 1));
     CU(p->starts.reserve((size_t)max_frames + 1));
     PlSyncArgs a{};
     a.work = p->work[p->cur].p;
@@ -244,12 +244,13 @@ int dvbs2fec_plsync_process_device(dvbs2fec_plsync* p, int count, const float* d
     if (count < 0 || (count && !d_in) || !d_out || max_frames < 0) return api_fail(DVBS2FEC_EINVAL, "bad arguments");
     CU(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t need = (size_t)p->pend_ub + count + 1;
-    if (need > p->work[p->cur].cap || std::max(need, (size_t)2 * p->rfs + 1) > p->work[p->cur ^ 1].cap) {
+    // fewer than two frames are ever carried over: sized for that, the buffers only grow with the caller's block size
+    const size_t need = (size_t)2 * p->rfs + count + 1;
+    if (need > p->work[p->cur].cap || need > p->work[p->cur ^ 1].cap) {
         // buffers grow only here, with everything enqueued so far finished
         CU(cudaStreamSynchronize(st));
         CU(p->work[p->cur].grow(need, p->pend_ub, p->stream));
-        CU(p->work[p->cur ^ 1].reserve(std::max(need, (size_t)2 * p->rfs + 1)));
+        CU(p->work[p->cur ^ 1].reserve(need));
     }
     // Without a look at the device the number of carried symbols is only bounded: fewer than two frames (a window
     // plus the realignment it asked for).  The kernels take the exact count from the device state, and the first

@@ -550,51 +550,49 @@ __device__ inline uint32_t crc32_mulmod(uint32_t x, uint32_t y) {
 }
 
 // The slot logic of :313-334 (first), :363-377 (middle) and :335-362 (last fragment) over the descriptors in stream
-// order; complete PDUs (:231-279) only advance the output offset.  One warp: the lanes fetch 32 descriptors at a
-// time, every lane replays the same sequence (the slot state is warp-uniform) and keeps the verdict of its own.
+// order.  One warp: the lanes fetch 32 descriptors at a time, every lane replays the fragments among them (complete
+// PDUs do not touch the slots and are skipped by a ballot) with warp-uniform slot state and keeps the verdict of its
+// own.  Which slot a fragment lands in, where its bytes go and which fragments form a chain does not depend on any
+// CRC (a last fragment frees its slot either way, :341), so the CRCs are left to the next kernel.
 __global__ void __launch_bounds__(32) gse_assemble_kernel(const TsArgs a) {
     if (a.state->phase != 1) return;
     GseState* G = a.gse.state;
     const int lane = threadIdx.x;
     const int nd = max(G->ndesc, 0);
-    int on[3], id[3], proto[3], ctr[3], head[3], tail[3], carry[3];
-    uint32_t crc[3];
+    int on[3], id[3], proto[3], ctr[3], head[3], tail[3], carry[3], cont[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        on[r] = G->slot[r].on; id[r] = G->slot[r].id; proto[r] = G->slot[r].proto; ctr[r] = G->slot[r].ctr; crc[r] = G->slot[r].crc;
+        on[r] = G->slot[r].on; id[r] = G->slot[r].id; proto[r] = G->slot[r].proto; ctr[r] = G->slot[r].ctr;
         head[r] = tail[r] = -1;
-        carry[r] = on[r] ? ctr[r] : 0;
+        cont[r] = on[r];                 // the chain continues one begun in an earlier call
+        carry[r] = on[r] ? ctr[r] : 0;   // with this many bytes in the reassembly buffer
     }
-    int og = 0, pdus = 0, errs = 0, dropped = 0, last_err = G->last_crc_err;
+    if (lane < 3) G->entry_crc[lane] = G->slot[lane].crc;
+    int dropped = 0;
     for (int base = 0; base < nd; base += 32) {
         const int d = base + lane;
         const bool have = d < nd;
-        uint32_t w0 = 0, w1 = 0, c0 = 0, xp = 0;
+        uint32_t w0 = 0, w1 = 0;
         if (have) {
             const GseDesc e = a.gse.desc[d];
             w0 = (uint32_t)e.kind | (uint32_t)e.fragid << 8 | (uint32_t)e.proto << 16;
             w1 = e.len;
-            if (e.kind) {
-                c0 = a.gse.crc0[d];
-                xp = a.gse.xpow[d];
-            }
             a.gse.nxt[d] = -1;
         }
         __syncwarp();
         GseOut mine{0, 0, -1, -1};
         int myaux = -1, myaux2 = 0;
-        const int lim = min(32, nd - base);
-        for (int k = 0; k < lim; ++k) {
+        if (have && (w0 & 0xFF) == 0) mine.emit = ((((w0 >> 16) == 0x0800u) || ((w0 >> 16) == 0x86DDu)) ? 4 : 2) + (int)w1;
+        unsigned frag = __ballot_sync(0xFFFFFFFFu, have && (w0 & 0xFF) != 0);
+        while (frag) {
+            const int k = __ffs(frag) - 1;
+            frag &= frag - 1;
             const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, w0, k);
             const int len = (int)__shfl_sync(0xFFFFFFFFu, w1, k);
-            const uint32_t kc0 = __shfl_sync(0xFFFFFFFFu, c0, k), kxp = __shfl_sync(0xFFFFFFFFu, xp, k);
             const int kind = v0 & 0xFF, fid = (v0 >> 8) & 0xFF, pr = (int)(v0 >> 16), me = base + k;
-            GseOut o{og, 0, -1, -1};
+            GseOut o{0, 0, -1, -1};
             int aux = -1, aux2 = 0;
-            if (kind == 0) {
-                o.emit = ((pr == 0x0800 || pr == 0x86DD) ? 4 : 2) + len;
-                ++pdus;
-            } else if (kind == 1) {
+            if (kind == 1) {
                 int r = -1;
 #pragma unroll
                 for (int rr = 2; rr >= 0; --rr)
@@ -603,9 +601,10 @@ __global__ void __launch_bounds__(32) gse_assemble_kernel(const TsArgs a) {
 #pragma unroll
                 for (int rr = 0; rr < 3; ++rr)
                     if (rr == r) {
-                        on[rr] = 1; id[rr] = fid; proto[rr] = pr; ctr[rr] = len; crc[rr] = kc0;
+                        on[rr] = 1; id[rr] = fid; proto[rr] = pr; ctr[rr] = len;
                         head[rr] = tail[rr] = me;
                         carry[rr] = 0;
+                        cont[rr] = 0;
                         o.pos = 0;
                     }
             } else {
@@ -625,28 +624,19 @@ __global__ void __launch_bounds__(32) gse_assemble_kernel(const TsArgs a) {
                             head[rr] = me;
                         }
                         tail[rr] = me;
-                        crc[rr] = crc32_mulmod(crc[rr], kxp) ^ kc0;
                         if (kind == 2) {
                             ctr[rr] += len;
                         } else {
                             on[rr] = 0;
                             ctr[rr] += len - 4;
-                            if (crc[rr] == 0) {
-                                last_err = 0;
-                                o.emit = ((proto[rr] == 0x0800 || proto[rr] == 0x86DD) ? 4 : 2) + ctr[rr];
-                                o.link = head[rr];
-                                aux = carry[rr] > 0 ? (rr | carry[rr] << 2) : -1;
-                                aux2 = proto[rr];
-                                ++pdus;
-                            } else {
-                                last_err = 1;
-                                ++errs;
-                            }
+                            o.emit = ((proto[rr] == 0x0800 || proto[rr] == 0x86DD) ? 4 : 2) + ctr[rr];   // if the CRC-32 agrees
+                            o.link = head[rr];
+                            aux = cont[rr] ? (rr | carry[rr] << 2) : -1;
+                            aux2 = proto[rr];
                         }
                     }
                 if (!taken) ++dropped;
             }
-            og += o.emit;
             if (lane == k) {
                 mine = o;
                 myaux = aux;
@@ -660,24 +650,94 @@ __global__ void __launch_bounds__(32) gse_assemble_kernel(const TsArgs a) {
         }
         __syncwarp();
     }
-    // GSE bytes in front of every frame = in front of its first descriptor
-    for (int f = lane; f <= a.cnt; f += 32) {
-        const int d0 = (f < a.cnt && G->ndesc >= 0) ? a.gse.doff[f] : nd;
-        a.gse.before[f] = d0 < nd ? a.gse.out[d0].before : og;
-    }
     if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            G->slot[r] = GseSlot{on[r], id[r], proto[r], ctr[r], crc[r]};
-            G->save[r] = GseSave{head[r], carry[r], on[r]};
+            G->slot[r] = GseSlot{on[r], id[r], proto[r], ctr[r], G->slot[r].crc};
+            G->save[r] = GseSave{head[r], carry[r], on[r], cont[r]};
         }
         G->old = G->cur;
         G->cur ^= 1;
-        G->last_crc_err = last_err;
-        G->pdus = pdus;
-        G->crc_errors = errs;
         G->dropped = dropped;
-        G->out_bytes = og;
+    }
+}
+
+// running CRC-32 of a chain of fragments from their zero-start CRCs: crc(s, B) = s x^(8|B|) + crc(0, B)
+__device__ inline uint32_t gse_chain_crc(const TsArgs& a, uint32_t crc, int x, int stop_at) {
+    for (; x >= 0; x = a.gse.nxt[x]) {
+        crc = crc32_mulmod(crc, a.gse.xpow[x]) ^ a.gse.crc0[x];
+        if (x == stop_at) break;
+    }
+    return crc;
+}
+
+// A thread per last fragment: the CRC-32 over its chain decides whether the PDU goes out (:343-361).  Three more
+// threads bring the running CRCs of the slots that stay open up to date.
+__global__ void __launch_bounds__(kGseThreads) gse_verify_kernel(const TsArgs a) {
+    if (a.state->phase != 1) return;
+    GseState* G = a.gse.state;
+    const int nd = max(G->ndesc, 0);
+    for (int d = blockIdx.x * kGseThreads + threadIdx.x; d < nd + 3; d += gridDim.x * kGseThreads) {
+        if (d >= nd) {
+            const int r = d - nd;
+            const GseSave sv = G->save[r];
+            if (!sv.active) continue;
+            if (sv.cont) G->slot[r].crc = gse_chain_crc(a, G->entry_crc[r], sv.head, -1);
+            else G->slot[r].crc = gse_chain_crc(a, a.gse.crc0[sv.head], a.gse.nxt[sv.head], -1);
+            continue;
+        }
+        if (a.gse.desc[d].kind != 3) continue;
+        const GseOut o = a.gse.out[d];
+        if (o.pos < 0) continue;   // no slot was waiting for it
+        const int aux = a.gse.aux[d];
+        const uint32_t crc = aux >= 0 ? gse_chain_crc(a, G->entry_crc[aux & 3], o.link, d)
+                                      : gse_chain_crc(a, a.gse.crc0[o.link], a.gse.nxt[o.link], d);
+        if (crc != 0) {   // (the received CRC-32 is folded into the last fragment's value)
+            a.gse.out[d].emit = 0;
+            a.gse.out[d].link = -2;   // marks the failure for the counters
+        }
+    }
+}
+
+// GSE bytes in front of every packet and every frame (a scan over what the packets put out), counters, and
+// last_gse_crc_err = the verdict of the last reassembly that ended in this call
+__global__ void __launch_bounds__(kPlanThreads) gse_offsets_kernel(const TsArgs a) {
+    __shared__ uint32_t s_w32[kPlanThreads / 32];
+    if (a.state->phase != 1) return;
+    GseState* G = a.gse.state;
+    const int nd = max(G->ndesc, 0), tid = threadIdx.x;
+    const int per = (nd + kPlanThreads - 1) / kPlanThreads;
+    const int d0 = min(nd, tid * per), d1 = min(nd, d0 + per);
+    uint32_t bytes = 0, pdus = 0, errs = 0, last_end = 0;
+    for (int d = d0; d < d1; ++d) {
+        const GseOut o = a.gse.out[d];
+        bytes += (uint32_t)o.emit;
+        pdus += o.emit > 0;
+        errs += o.link == -2;
+        if (a.gse.desc[d].kind == 3 && o.pos >= 0) last_end = (uint32_t)(2 * d + 2 + (o.link == -2));
+    }
+    auto add = [](uint32_t x, uint32_t y) { return x + y; };
+    auto umax = [](uint32_t x, uint32_t y) { return x > y ? x : y; };
+    uint32_t total, pdus_total, errs_total, last_total;
+    uint32_t at = block_scan_exclusive(bytes, 0u, add, s_w32, total);
+    block_scan_exclusive(pdus, 0u, add, s_w32, pdus_total);
+    block_scan_exclusive(errs, 0u, add, s_w32, errs_total);
+    block_scan_exclusive(last_end, 0u, umax, s_w32, last_total);
+    for (int d = d0; d < d1; ++d) {
+        a.gse.out[d].before = (int)at;
+        at += (uint32_t)a.gse.out[d].emit;
+    }
+    __syncthreads();
+    // GSE bytes in front of every frame = in front of its first descriptor
+    for (int f = tid; f <= a.cnt; f += kPlanThreads) {
+        const int first = (f < a.cnt && G->ndesc >= 0) ? a.gse.doff[f] : nd;
+        a.gse.before[f] = first < nd ? a.gse.out[first].before : (int)total;
+    }
+    if (tid == 0) {
+        if (last_total) G->last_crc_err = (int)(last_total & 1u);
+        G->pdus = (int)pdus_total;
+        G->crc_errors = (int)errs_total;
+        G->out_bytes = (int)total;
     }
 }
 
@@ -749,6 +809,8 @@ int gse_launch_rest(const TsArgs& a, cudaStream_t stream) {
     if (a.cnt > 0) gse_fill_kernel<<<per_frame, kGseThreads, 0, stream>>>(a);
     gse_crc_kernel<<<by_desc, kGseThreads, 0, stream>>>(a);
     gse_assemble_kernel<<<1, 32, 0, stream>>>(a);
+    gse_verify_kernel<<<by_desc, kGseThreads, 0, stream>>>(a);
+    gse_offsets_kernel<<<1, kPlanThreads, 0, stream>>>(a);
     TsArgs b = a;
     b.mode = 2;
     b.copy_phase = 2;

@@ -44,10 +44,12 @@ struct GseSave {         // what the copy kernel must put into the new buffer of
     int head;            // first fragment descriptor of this call's part of the chain (-1: none)
     int carry;           // bytes inherited from the previous call that stay in front of it
     int active;
+    int cont;            // the chain continues one begun in an earlier call
 };
 struct GseState {
     GseSlot slot[3];
     GseSave save[3];
+    uint32_t entry_crc[3];   // running CRC-32 of the slots when the call began
     int cur, old;        // buffer set holding the inherited heads: for the next call / of the call in flight
     int last_crc_err;    // last_gse_crc_err (bbframe_ts_parser.h:73)
     int pdus, crc_errors, malformed, dropped;   // counters of the last call
@@ -67,7 +69,7 @@ struct GseOut {          // what the sequential pass decides per packet (16 byte
     int before;          // GSE bytes of this call in front of it
     int emit;            // bytes it puts out (GRE header included), 0: none
     int pos;             // fragments: position of its data in the reassembly buffer; -1: dropped
-    int link;            // last fragment: first descriptor of the chain (-1: none) ; others: unused
+    int link;            // last fragment: first descriptor of the chain (-2 once its CRC-32 has failed); others: unused
 };
 struct GseWork {         // per-call scratch; null desc = GSE pass not available (frames are only counted)
     int* doff;           // [cnt + 1] first descriptor of every frame
@@ -78,7 +80,8 @@ struct GseWork {         // per-call scratch; null desc = GSE pass not available
     uint32_t* crc0;      // zero-start CRC-32 of the data (first fragment: the finished start value; last: xor received)
     uint32_t* xpow;      // x^(8 len) mod P
     int* nxt;            // next fragment of the chain
-    int* aux;            // last fragment: slot | inherited bytes << 2 (-1: nothing inherited) ; proto in aux2
+    int* aux;            // last fragment: slot | inherited bytes << 2 when its chain began in an earlier call, else -1;
+                         // protocol type of the PDU in aux2
     int* aux2;
     int cap;             // descriptors the pool holds
     GseState* state;

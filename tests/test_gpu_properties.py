@@ -180,6 +180,59 @@ def test_config4_apsk_normal_full_chain_from_symbols(modcod, sigma):
     dec.close()
 
 
+def test_config2_8psk_3_5_from_symbols_near_threshold():
+    """config 2 proper: 8PSK 3/5 normal PLFRAME symbols at the reference mapper's amplitude, Es/N0 around the code's
+    threshold, through demapper (LUT, reversed 3-column interleaver) + LDPC + BCH.  On its own demapper's LLRs
+    (scaled by 50, halved until they fit: SURVEY N7) the reference decoder burns all iterations on every frame --
+    that IS the high-iteration regime of config 2 -- and the GPU chain reproduces it frame by frame: LLR bytes,
+    iteration counts, BCH verdicts, BBFRAME bytes."""
+    dec = pkg.DVBS2Decoder(max_batch=16, max_trials=25)
+    dec.setDemodParams(12, False, False)
+    regime = []
+    for esn0 in (5.0, 6.0, 8.0):
+        sigma = float(np.sqrt(0.5 / 10 ** (esn0 / 10)))
+        noisy, payload = _symbols_batch(12, False, 3, sigma, 1200 + int(esn0))
+        bb, res = dec.decode_plframes(noisy)
+        want = _oracle_from_symbols(12, False, noisy, 25)
+        for i, (wbb, wit, wco) in enumerate(want):
+            assert (res["ldpc_iters"][i], res["bch_corr"][i]) == (wit, wco), esn0
+            assert np.array_equal(bb[i], wbb), esn0
+        regime += [w[1] for w in want]
+    assert sum(it == -1 or it >= 10 for it in regime) >= 3   # the frames near the threshold burn (nearly) all iterations
+    dec.close()
+
+
+def test_config4_32apsk_9_10_chain_is_exact_behind_the_float_demapper():
+    """32APSK has no LUT in the reference (constellation.cpp:294,319-321): expf/logf/sqrtf run per symbol, on the
+    device here, so LLR bytes may differ from glibc's by one LSB on a few symbols (tolerance: <= 0.5 % of the LLRs,
+    |delta| <= 1) and byte parity of the whole chain is undefined.  What is defined, and checked: the demapper within
+    that tolerance, and everything behind it -- LDPC iteration counts, BCH counts, BBFRAME bytes -- exactly equal to
+    the oracle run on the very LLRs the device demapper produced."""
+    from fec import MODCODS
+    modcod = 28
+    dec = pkg.DVBS2Decoder(max_batch=16, max_trials=25)
+    dec.setDemodParams(modcod, False, False)
+    const, ctype, rate, g1, g2 = MODCODS[modcod]
+    o = orclib.oracle()
+    c = o.orc_const_create(ctype, g1, g2)
+    for sigma, seed in ((0.012, 1), (0.035, 2), (0.05, 3)):
+        noisy, payload = _symbols_batch(modcod, False, 3, sigma, 2800 + seed)
+        llr_gpu = dec.bb_to_soft(noisy)
+        bb, res = dec.decode_plframes(noisy)
+        for i in range(len(noisy)):
+            llr_cpu = np.zeros(dec.N, np.int8)
+            o.orc_bb_to_soft(c, const, 0, rate, np.ascontiguousarray(noisy[i]), llr_cpu)
+            d = np.abs(llr_gpu[i].astype(np.int16) - llr_cpu.astype(np.int16))
+            assert d.max() <= 1 and (d != 0).mean() <= 0.005
+            want = np.zeros(dec.kbch // 8, np.uint8)
+            it, co = C.c_int(), C.c_int()
+            o.orc_decode_frame(0, rate, llr_gpu[i].copy(), 25, want, C.byref(it), C.byref(co))
+            assert (res["ldpc_iters"][i], res["bch_corr"][i]) == (it.value, co.value), (sigma, i)
+            assert np.array_equal(bb[i], want), (sigma, i)
+    o.orc_const_destroy(c)
+    dec.close()
+
+
 def test_config3_short_frame_modcod_sweep_from_symbols():
     """all ten short-frame QPSK codes (1/4 ... 8/9) with the fused demapper, against the oracle chain"""
     dec = pkg.DVBS2Decoder(max_batch=16)
