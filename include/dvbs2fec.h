@@ -99,6 +99,15 @@ int dvbs2fec_decode_batch(dvbs2fec_handle* h, const int8_t* llr, int n, uint8_t*
 /* same, starting from PLFRAME symbols (module_dvbs2_demod.cpp:334-366) */
 int dvbs2fec_decode_plframes(dvbs2fec_handle* h, const float* plframes, int n, uint8_t* bb_out,
                              dvbs2fec_result* results);
+/* Quantised symbols path for the LUT constellations (QPSK, 8PSK, 16APSK).  The reference demapper reduces every
+ * symbol to two 8-bit LUT coordinates before it looks anything up (constellation_t::demod_soft_lut,
+ * common/dsp/demod/constellation.cpp:295-310).  dvbs2fec_quantize_plframes does exactly that on the host -- pilot
+ * removal and PL descrambling (dvbs2fec_set_pl_scrambling) included, header dropped -- and writes 2 bytes per payload
+ * symbol (N / bits_per_symbol symbols per frame); dvbs2fec_decode_plframes_idx / dvbs2fec_submit_plframe_idx take
+ * those instead of 8-byte complex floats: a quarter of the PCIe traffic, bit-identical LLRs.  32APSK has no LUT in
+ * the reference (:294,319-321): DVBS2FEC_EINVAL, send symbols. */
+int dvbs2fec_quantize_plframes(const dvbs2fec_handle* h, const float* plframes, int n, uint8_t* idx_out);
+int dvbs2fec_decode_plframes_idx(dvbs2fec_handle* h, const uint8_t* idx, int n, uint8_t* bb_out, dvbs2fec_result* results);
 /* device-resident variant on the handle's first device: all pointers are device pointers, work is
  * enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) and NOT synchronised.  The call owns a
  * scratch area of its own (never shared with the synchronous entry points); calls issued on different streams
@@ -118,6 +127,16 @@ int dvbs2fec_kernel_times(dvbs2fec_handle* h, float* demap_ms, float* ldpc_ms, f
  *      module_dvbs2_demod.cpp:343-347): frames come back in submission order ---- */
 int dvbs2fec_submit_llr(dvbs2fec_handle* h, const int8_t* llr, uint64_t tag);
 int dvbs2fec_submit_plframe(dvbs2fec_handle* h, const float* plframe, int nsym, uint64_t tag);
+int dvbs2fec_submit_plframe_idx(dvbs2fec_handle* h, const uint8_t* idx, uint64_t tag);   /* see dvbs2fec_quantize_plframes */
+/* Zero-copy submit: acquire hands out the place of the next frame inside the page-locked batch being filled
+ * (nldpc bytes / plframe_symbols complex floats / 2 bytes per payload symbol), the producer -- the demapper, the
+ * PLL loop, a socket read -- writes its output there instead of into a buffer of its own, commit queues it.  One
+ * frame at a time per handle; the batch is not launched while a frame is being written.  Saves the copy of
+ * submit_* (64.8 KB per normal frame), which is what limits a multi-GPU handle fed by few host threads. */
+int dvbs2fec_acquire_llr(dvbs2fec_handle* h, int8_t** slot);
+int dvbs2fec_acquire_plframe(dvbs2fec_handle* h, float** slot);
+int dvbs2fec_acquire_plframe_idx(dvbs2fec_handle* h, uint8_t** slot);
+int dvbs2fec_commit(dvbs2fec_handle* h, uint64_t tag);
 /* up to max frames; bb_out receives kbch/8 bytes per frame.  timeout_us: 0 = poll, <0 = wait for one. */
 int dvbs2fec_collect(dvbs2fec_handle* h, uint8_t* bb_out, dvbs2fec_result* results, int max, int timeout_us);
 /* force the partial batch through (DVBS2Demod::reset / tempStop) */

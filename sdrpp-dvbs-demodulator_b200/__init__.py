@@ -87,6 +87,12 @@ def lib():
     L.dvbs2fec_decode_batch.argtypes = [vp, vp, C.c_int, vp, vp]
     L.dvbs2fec_decode_plframes.argtypes = [vp, vp, C.c_int, vp, vp]
     L.dvbs2fec_decode_batch_device.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.dvbs2fec_quantize_plframes.argtypes = [vp, vp, C.c_int, vp]
+    L.dvbs2fec_decode_plframes_idx.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.dvbs2fec_submit_plframe_idx.argtypes = [vp, vp, C.c_uint64]
+    for f in ("dvbs2fec_acquire_llr", "dvbs2fec_acquire_plframe", "dvbs2fec_acquire_plframe_idx"):
+        getattr(L, f).argtypes = [vp, C.POINTER(vp)]
+    L.dvbs2fec_commit.argtypes = [vp, C.c_uint64]
     L.dvbs2fec_set_profiling.argtypes = [vp, C.c_int]
     L.dvbs2fec_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), ip]
     L.dvbs2fec_submit_llr.argtypes = [vp, vp, C.c_uint64]
@@ -253,6 +259,35 @@ class DVBS2Decoder:
         res = np.zeros(x.shape[0], RESULT_DTYPE)
         _check(lib().dvbs2fec_decode_plframes(self._h, _ptr(x), x.shape[0], _ptr(bb), _ptr(res)))
         return bb, res
+
+    def quantize_plframes(self, plframes):
+        """PLFRAME symbols -> two LUT coordinates per payload symbol (uint8 [n][N / bits][2]), on the host"""
+        x = np.ascontiguousarray(plframes).view(np.float32).reshape(-1, self.plframe_symbols * 2)
+        nsym = self.N // modcod_info(self.modcod, self.shortframes)["bits"]
+        out = np.zeros((x.shape[0], nsym, 2), np.uint8)
+        _check(lib().dvbs2fec_quantize_plframes(self._h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def decode_plframes_idx(self, idx):
+        x = np.ascontiguousarray(idx, np.uint8)
+        n = x.shape[0]
+        bb = np.zeros((n, self.kbch // 8), np.uint8)
+        res = np.zeros(n, RESULT_DTYPE)
+        _check(lib().dvbs2fec_decode_plframes_idx(self._h, _ptr(x), n, _ptr(bb), _ptr(res)))
+        return bb, res
+
+    def acquire_llr(self):
+        """zero-copy submit: a writable int8 view of the next frame's place in the page-locked batch; commit(tag) queues it"""
+        p = C.c_void_p()
+        _check(lib().dvbs2fec_acquire_llr(self._h, C.byref(p)))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=(self.N,))
+
+    def commit(self, tag=0):
+        _check(lib().dvbs2fec_commit(self._h, tag))
+
+    def submit_plframe_idx(self, idx, tag=0):
+        x = np.ascontiguousarray(idx, np.uint8)
+        _check(lib().dvbs2fec_submit_plframe_idx(self._h, _ptr(x), tag))
 
     def decode_batch_raw(self, llr_ptr, n, bb_ptr, res_ptr):
         """Host pointers (e.g. pinned buffers); synchronous."""

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <climits>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -111,6 +112,7 @@ struct Slot {
     PinBuf<unsigned int> arrived_vals;   // the values the copy engine writes there, one per piece
     DevBuf<int8_t> llr;
     DevBuf<float> sym;
+    DevBuf<uint8_t> idx;                 // LUT coordinates per payload symbol (quantised symbols path)
     DevBuf<uint8_t> hard;
     DevBuf<int16_t> iters;
     DevBuf<int16_t> corr;
@@ -207,6 +209,7 @@ struct dvbs2fec_handle {
     std::condition_variable cv_work, cv_done;
     std::thread worker;
     bool stop = false, flush_req = false, busy = false;
+    bool acquired = false;              // a producer is writing a frame straight into the batch being filled
     // Frames wait in page-locked staging batches ("stages"): submit copies a frame straight into the stage being
     // filled, the worker hands a full (or timed-out) stage to the GPUs with asynchronous copies in both
     // directions, collect copies BBFRAMEs out of finished stages.  Stages cycle free -> fill -> ready -> inflight
@@ -219,7 +222,7 @@ struct dvbs2fec_handle {
         bool has_ts = false;
         std::vector<uint64_t> tags;
         int n = 0, taken = 0, cap = 0;
-        bool is_sym = false;
+        int kind = 0;                      // 0 LLRs, 1 PLFRAME symbols, 2 LUT coordinates
         int rc = 0;
         size_t kb = 0, in_bytes = 0;
         std::atomic<int> outstanding{0};   // device shares still running
@@ -323,11 +326,17 @@ int setup_device_tables(dvbs2fec_handle* h, DevCtx& d) {
     return 0;
 }
 
-int reserve_slot(dvbs2fec_handle* h, DevCtx& d, Slot& s, int nframes, bool with_sym, bool host_staging) {
+// kind of input: 0 = LLRs, 1 = PLFRAME symbols, 2 = LUT coordinates of the payload symbols
+size_t input_frame_bytes(const dvbs2fec_handle* h, int kind) {
+    return kind == 1 ? (size_t)h->plsyms * 8 : kind == 2 ? (size_t)(h->code->N / h->mc.bits) * 2 : (size_t)h->code->N;
+}
+
+int reserve_slot(dvbs2fec_handle* h, DevCtx& d, Slot& s, int nframes, int kind, bool host_staging) {
     const LdpcCode& c = *h->code;
     CU(cudaSetDevice(d.device));
     CU(s.llr.reserve((size_t)nframes * c.N));
-    if (with_sym) CU(s.sym.reserve((size_t)nframes * h->plsyms * 2));
+    if (kind == 1) CU(s.sym.reserve((size_t)nframes * h->plsyms * 2));
+    if (kind == 2) CU(s.idx.reserve((size_t)nframes * input_frame_bytes(h, 2)));
     CU(s.hard.reserve((size_t)nframes * h->hard_stride));
     CU(s.iters.reserve(nframes));
     CU(s.corr.reserve(nframes));
@@ -336,7 +345,7 @@ int reserve_slot(dvbs2fec_handle* h, DevCtx& d, Slot& s, int nframes, bool with_
     CU(s.workspace.reserve((size_t)d.grid * ldpc_workspace_bytes(d.ldpc)));
     CU(s.counter.reserve(1));
     if (host_staging) {
-        size_t in_bytes = with_sym ? (size_t)nframes * h->plsyms * 8 : (size_t)nframes * c.N;
+        size_t in_bytes = (size_t)nframes * input_frame_bytes(h, kind);
         CU(s.h_in.reserve(in_bytes));
         CU(s.h_bb.reserve((size_t)nframes * (c.kbch / 8)));
         CU(s.h_res.reserve(nframes));
@@ -347,7 +356,7 @@ int reserve_slot(dvbs2fec_handle* h, DevCtx& d, Slot& s, int nframes, bool with_
 // enqueue demap (optional) + LDPC + BCH/descramble for n frames already on the device
 int enqueue_chain(dvbs2fec_handle* h, DevCtx& d, Slot& s, const float* d_sym, const int8_t* d_llr, int n,
                   uint8_t* d_bb, dvbs2fec_result* d_res, cudaStream_t st, int* launches, uint64_t tag_base = 0,
-                  const unsigned int* arrived = nullptr) {
+                  const unsigned int* arrived = nullptr, const uint8_t* d_idx = nullptr) {
     const int8_t* llr = d_llr;
     // kernel-time spans for dvbs2fec_kernel_times; several threads (one per GPU, the queue worker) may add some
     dvbs2fec_handle::Span cur{0, nullptr, nullptr};
@@ -364,9 +373,9 @@ int enqueue_chain(dvbs2fec_handle* h, DevCtx& d, Slot& s, const float* d_sym, co
             h->spans.push_back(cur);
         }
     };
-    if (d_sym) {
+    if (d_sym || d_idx) {
         mark(0, true);
-        int e = demap_launch(d.demap, d_sym, n, s.llr.p, st);
+        int e = d_sym ? demap_launch(d.demap, d_sym, n, s.llr.p, st) : demap_idx_launch(d.demap, d_idx, n, s.llr.p, st);
         mark(0, false);
         if (e) return fail(DVBS2FEC_ECUDA, "demap launch: %s", cudaGetErrorString((cudaError_t)e));
         llr = s.llr.p;
@@ -462,17 +471,18 @@ int finish_slot(dvbs2fec_handle* h, Slot& s) {
 }
 
 // frames [0, n) of one device's share, host buffers in and out
-int run_device_share(dvbs2fec_handle* h, DevCtx& d, const int8_t* llr, const float* sym, int n, uint8_t* bb,
+int run_device_share(dvbs2fec_handle* h, DevCtx& d, const int8_t* llr, const float* sym, const uint8_t* idx, int n, uint8_t* bb,
                      dvbs2fec_result* res, uint64_t tag0, int* launches) {
     if (n <= 0) return 0;
     CU(cudaSetDevice(d.device));
     const LdpcCode& c = *h->code;
     const size_t kb = c.kbch / 8;
-    const size_t in_frame_bytes = sym ? (size_t)h->plsyms * 8 : (size_t)c.N;
-    const uint8_t* in = sym ? reinterpret_cast<const uint8_t*>(sym) : reinterpret_cast<const uint8_t*>(llr);
+    const int kind = sym ? 1 : idx ? 2 : 0;
+    const size_t in_frame_bytes = input_frame_bytes(h, kind);
+    const uint8_t* in = sym ? reinterpret_cast<const uint8_t*>(sym) : idx ? idx : reinterpret_cast<const uint8_t*>(llr);
     const int chunk = std::min(h->cfg.max_batch, n);
     for (int k = 0; k < kSlots; ++k) {
-        int rc = reserve_slot(h, d, d.slot[k], chunk, sym != nullptr, true);
+        int rc = reserve_slot(h, d, d.slot[k], chunk, kind, true);
         if (rc) return rc;
     }
     // caller buffers that are already page-locked are used directly; pageable ones are staged
@@ -505,7 +515,7 @@ int run_device_share(dvbs2fec_handle* h, DevCtx& d, const int8_t* llr, const flo
         const int m = std::min(chunk, n - f0);
         if ((rc = finish_slot(h, s))) return rc;
         const uint8_t* src = in + (size_t)f0 * in_frame_bytes;
-        if (!sym) {   // LLR input: the kernel starts on the first piece
+        if (kind == 0) {   // LLR input: the kernel starts on the first piece
             if ((rc = arm_streamed_input(s, m))) return rc;
             if ((rc = feed_streamed_input(s, src, m, in_frame_bytes, pin_in))) return rc;
             rc = enqueue_chain(h, d, s, nullptr, s.llr.p, m, s.bb.p, s.res.p, s.stream, launches, tag0 + f0, s.arrived.p);
@@ -515,8 +525,10 @@ int run_device_share(dvbs2fec_handle* h, DevCtx& d, const int8_t* llr, const flo
                 memcpy(s.h_in.p, src, (size_t)m * in_frame_bytes);
                 src = s.h_in.p;
             }
-            CU(cudaMemcpyAsync(s.sym.p, src, (size_t)m * in_frame_bytes, cudaMemcpyHostToDevice, s.stream));
-            rc = enqueue_chain(h, d, s, s.sym.p, nullptr, m, s.bb.p, s.res.p, s.stream, launches, tag0 + f0);
+            void* dst = kind == 1 ? (void*)s.sym.p : (void*)s.idx.p;
+            CU(cudaMemcpyAsync(dst, src, (size_t)m * in_frame_bytes, cudaMemcpyHostToDevice, s.stream));
+            rc = enqueue_chain(h, d, s, kind == 1 ? s.sym.p : nullptr, nullptr, m, s.bb.p, s.res.p, s.stream, launches, tag0 + f0, nullptr,
+                               kind == 2 ? s.idx.p : nullptr);
             if (rc) return rc;
         }
         s.user_bb = bb ? bb + (size_t)f0 * kb : nullptr;
@@ -536,17 +548,19 @@ int run_device_share(dvbs2fec_handle* h, DevCtx& d, const int8_t* llr, const flo
     return 0;
 }
 
-int decode_host(dvbs2fec_handle* h, const int8_t* llr, const float* sym, int n, uint8_t* bb, dvbs2fec_result* res) {
+int decode_host(dvbs2fec_handle* h, const int8_t* llr, const float* sym, int n, uint8_t* bb, dvbs2fec_result* res,
+                const uint8_t* idx = nullptr) {
     if (!h || !h->configured) return fail(DVBS2FEC_EINVAL, "set_modcod has not been called");
-    if (n < 0 || (!llr && !sym)) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (n < 0 || (!llr && !sym && !idx)) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (idx && h->mc.constellation == APSK32) return fail(DVBS2FEC_EINVAL, "32APSK has no LUT in the reference: send symbols");
     if (h->devs.empty()) return fail(DVBS2FEC_ENODEV, "no CUDA device");
     const int nd = (int)h->devs.size();
     const size_t kb = h->code->kbch / 8;
-    const size_t in_stride = sym ? (size_t)h->plsyms * 2 : (size_t)h->code->N;
+    const size_t in_stride = sym ? (size_t)h->plsyms * 2 : idx ? input_frame_bytes(h, 2) : (size_t)h->code->N;
     h->last_launches = 0;
     if (nd == 1) {
         int launches = 0;
-        int rc = run_device_share(h, *h->devs[0], llr, sym, n, bb, res, 0, &launches);
+        int rc = run_device_share(h, *h->devs[0], llr, sym, idx, n, bb, res, 0, &launches);
         h->last_launches = launches;
         return rc;
     }
@@ -559,7 +573,7 @@ int decode_host(dvbs2fec_handle* h, const int8_t* llr, const float* sym, int n, 
         int f0 = std::min(n, k * per), f1 = std::min(n, f0 + per);
         th.emplace_back([=, &rcs, &ln, &errs] {
             rcs[k] = run_device_share(h, *h->devs[k], llr ? llr + (size_t)f0 * in_stride : nullptr,
-                                      sym ? sym + (size_t)f0 * in_stride : nullptr, f1 - f0,
+                                      sym ? sym + (size_t)f0 * in_stride : nullptr, idx ? idx + (size_t)f0 * in_stride : nullptr, f1 - f0,
                                       bb ? bb + (size_t)f0 * kb : nullptr, res ? res + f0 : nullptr, (uint64_t)f0, &ln[k]);
             if (rcs[k]) errs[k] = g_err;
         });
@@ -597,16 +611,16 @@ void launch_stage(dvbs2fec_handle* h, int st, int which) {
         DevCtx& d = *h->devs[k];
         Slot& s = d.slot[kSlots + which];
         auto body = [&]() -> int {
-            int rc = reserve_slot(h, d, s, std::max(m, h->cfg.max_batch), S.is_sym, false);
+            int rc = reserve_slot(h, d, s, std::max(m, h->cfg.max_batch), S.kind, false);
             if (rc) return rc;
             // plain copy-in on the slot's stream: with two batches in flight per handle (and other handles' work
             // beside them) the copy of one batch already overlaps the kernels of another, and a kernel that
             // starts early and waits for streamed input would only hold SMs that a neighbour could use
             // (measured: 8 handles at max_batch 4096, 588 k frames/s plain vs 405 k streamed)
-            void* dst = S.is_sym ? (void*)s.sym.p : (void*)s.llr.p;
+            void* dst = S.kind == 1 ? (void*)s.sym.p : S.kind == 2 ? (void*)s.idx.p : (void*)s.llr.p;
             CU(cudaMemcpyAsync(dst, S.in.p + (size_t)f0 * S.in_bytes, (size_t)m * S.in_bytes, cudaMemcpyHostToDevice, s.stream));
-            rc = enqueue_chain(h, d, s, S.is_sym ? s.sym.p : nullptr, S.is_sym ? nullptr : s.llr.p, m, s.bb.p, s.res.p, s.stream,
-                               &h->last_launches, (uint64_t)f0);
+            rc = enqueue_chain(h, d, s, S.kind == 1 ? s.sym.p : nullptr, S.kind == 0 ? s.llr.p : nullptr, m, s.bb.p, s.res.p, s.stream,
+                               &h->last_launches, (uint64_t)f0, nullptr, S.kind == 2 ? s.idx.p : nullptr);
             if (rc) return rc;
             CU(cudaMemcpyAsync(S.bb.p + (size_t)f0 * S.kb, s.bb.p, (size_t)m * S.kb, cudaMemcpyDeviceToHost, s.stream));
             CU(cudaMemcpyAsync(S.res.p + f0, s.res.p, (size_t)m * sizeof(dvbs2fec_result), cudaMemcpyDeviceToHost, s.stream));
@@ -660,7 +674,7 @@ void worker_main(dvbs2fec_handle* h) {
             if (!h->st_ready.empty()) {
                 st = h->st_ready.front();
                 h->st_ready.pop_front();
-            } else if (h->st_fill >= 0 && h->stages[h->st_fill].n > 0 &&
+            } else if (h->st_fill >= 0 && h->stages[h->st_fill].n > 0 && !h->acquired &&
                        (h->flush_req || std::chrono::steady_clock::now() >= h->stages[h->st_fill].first + latency)) {
                 st = h->st_fill;
                 h->st_fill = -1;
@@ -680,7 +694,7 @@ void worker_main(dvbs2fec_handle* h) {
             h->flush_req = false;
             h->cv_done.notify_all();
         }
-        if (filling && (int)h->st_inflight.size() < kSlots)
+        if (filling && !h->acquired && (int)h->st_inflight.size() < kSlots)
             h->cv_work.wait_until(lk, h->stages[h->st_fill].first + latency);
         else
             h->cv_work.wait(lk);
@@ -767,7 +781,7 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
             Slot& s = d.slot[k];
             if (s.copy) cudaStreamSynchronize(s.copy);
             if (s.stream) cudaStreamSynchronize(s.stream);
-            s.llr.release(); s.sym.release(); s.hard.release(); s.iters.release(); s.corr.release();
+            s.llr.release(); s.sym.release(); s.idx.release(); s.hard.release(); s.iters.release(); s.corr.release();
             s.bb.release(); s.res.release(); s.workspace.release(); s.counter.release();
             s.h_in.release(); s.h_bb.release(); s.h_res.release();
             s.arrived.release(); s.arrived_vals.release();
@@ -889,7 +903,7 @@ int dvbs2fec_bb_to_soft(dvbs2fec_handle* h, const float* plframes, int n, int8_t
     if (n == 0) return 0;
     DevCtx& d = *h->devs[0];
     Slot& s = d.slot[0];
-    int rc = reserve_slot(h, d, s, n, true, false);
+    int rc = reserve_slot(h, d, s, n, 1, false);
     if (rc) return rc;
     CU(cudaMemcpyAsync(s.sym.p, plframes, (size_t)n * h->plsyms * 8, cudaMemcpyHostToDevice, s.stream));
     int e = demap_launch(d.demap, s.sym.p, n, s.llr.p, s.stream);
@@ -904,7 +918,7 @@ int dvbs2fec_ldpc_decode(dvbs2fec_handle* h, int8_t* frames, int n, int max_tria
     if (n == 0) return 0;
     DevCtx& d = *h->devs[0];
     Slot& s = d.slot[0];
-    int rc = reserve_slot(h, d, s, n, false, false);
+    int rc = reserve_slot(h, d, s, n, 0, false);
     if (rc) return rc;
     const size_t bytes = (size_t)n * h->code->N;
     CU(cudaMemcpyAsync(s.llr.p, frames, bytes, cudaMemcpyHostToDevice, s.stream));
@@ -934,7 +948,7 @@ int dvbs2fec_bch_decode(dvbs2fec_handle* h, uint8_t* frames, int n, int16_t* cor
     if (n == 0) return 0;
     DevCtx& d = *h->devs[0];
     Slot& s = d.slot[0];
-    int rc = reserve_slot(h, d, s, n, false, false);
+    int rc = reserve_slot(h, d, s, n, 0, false);
     if (rc) return rc;
     const size_t nb = h->code->K / 8;
     CU(cudaMemsetAsync(s.hard.p, 0, (size_t)n * h->hard_stride, s.stream));
@@ -976,6 +990,43 @@ int dvbs2fec_decode_plframes(dvbs2fec_handle* h, const float* plframes, int n, u
     return decode_host(h, nullptr, plframes, n, bb_out, results);
 }
 
+int dvbs2fec_quantize_plframes(const dvbs2fec_handle* h, const float* plframes, int n, uint8_t* idx_out) {
+    if (!h || !h->configured || !plframes || !idx_out || n < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (h->mc.constellation == APSK32) return fail(DVBS2FEC_EINVAL, "32APSK has no LUT in the reference: send symbols");
+    const int nsym = h->code->N / h->mc.bits;
+    std::vector<uint8_t> rn;
+    if (h->pl_codenum >= 0) rn = pl_scrambling_rn(h->pl_codenum, nsym + 36 * 22 + 8);
+    auto coord = [](float s) {   // constellation.cpp:295-302 / 304-310: int(double) truncation (cvttsd2si), then the clamp
+        const double v = ((double)s / 1.5) * 256 + 128;
+        int x = (v > -2147483649.0 && v < 2147483648.0) ? (int)v : INT_MIN;
+        return (uint8_t)(x < 0 ? 0 : x >= 256 ? 255 : x);
+    };
+    for (int f = 0; f < n; ++f) {
+        const float* in = plframes + (size_t)f * h->plsyms * 2;
+        uint8_t* out = idx_out + (size_t)f * nsym * 2;
+        for (int s = 0; s < nsym; ++s) {
+            const int raw = 90 + s + (h->mc.pilots ? 36 * (s / 1440) : 0);
+            float re = in[2 * raw], im = in[2 * raw + 1];
+            if (!rn.empty()) {   // S2Scrambling::descramble: quarter turns only swap and negate
+                const float a = re, b = im;
+                switch (rn[raw - 90]) {
+                case 1: re = b; im = -a; break;
+                case 2: re = -a; im = -b; break;
+                case 3: re = -b; im = a; break;
+                default: break;
+                }
+            }
+            out[2 * s] = coord(re);
+            out[2 * s + 1] = coord(im);
+        }
+    }
+    return 0;
+}
+
+int dvbs2fec_decode_plframes_idx(dvbs2fec_handle* h, const uint8_t* idx, int n, uint8_t* bb_out, dvbs2fec_result* results) {
+    return decode_host(h, nullptr, nullptr, n, bb_out, results, idx);
+}
+
 int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n, uint8_t* d_bb_out,
                                  dvbs2fec_result* d_results, void* cuda_stream) {
     if (!h || !h->configured || !d_llr || n < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
@@ -988,7 +1039,7 @@ int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n,
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (d.dev_used) CU(cudaStreamWaitEvent(st, s.done, 0));
     const int chunk = std::min(n, std::max(h->cfg.max_batch, 1));
-    int rc = reserve_slot(h, d, s, chunk, false, false);
+    int rc = reserve_slot(h, d, s, chunk, 0, false);
     if (rc) return rc;
     const size_t kb = h->code->kbch / 8;
     h->last_launches = 0;
@@ -1002,13 +1053,11 @@ int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n,
     return rc;
 }
 
-static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym, uint64_t tag) {
-    if (!h || !h->configured) return fail(DVBS2FEC_EINVAL, "set_modcod has not been called");
-    std::lock_guard<std::mutex> producer(h->submit_mu);
-    std::unique_lock<std::mutex> lk(h->mu);
+// The slot of the next frame in the staging batch being filled (opening a batch if need be).  Called with h->mu held
+// through `lk`, which is dropped while page-locked memory is allocated.
+static int acquire_slot(dvbs2fec_handle* h, std::unique_lock<std::mutex>& lk, int kind, uint8_t** slot) {
     if (!h->worker.joinable()) h->worker = std::thread(worker_main, h);
-    const bool is_sym = sym != nullptr;
-    if (h->st_fill >= 0 && h->stages[h->st_fill].n > 0 && h->stages[h->st_fill].is_sym != is_sym) {
+    if (h->st_fill >= 0 && h->stages[h->st_fill].n > 0 && h->stages[h->st_fill].kind != kind) {
         h->st_ready.push_back(h->st_fill);   // a batch holds one kind of input: close the pending one
         h->st_fill = -1;
         h->cv_work.notify_all();
@@ -1020,8 +1069,8 @@ static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym
         dvbs2fec_handle::Stage& S = h->stages[idx];
         S.cap = h->cfg.max_batch * (int)h->devs.size();
         S.kb = h->code->kbch / 8;
-        S.in_bytes = is_sym ? (size_t)h->plsyms * 8 : (size_t)h->code->N;
-        S.is_sym = is_sym;
+        S.in_bytes = input_frame_bytes(h, kind);
+        S.kind = kind;
         S.n = S.taken = 0;
         S.ts_taken = 0;
         S.res_taken = 0;
@@ -1044,7 +1093,12 @@ static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym
         h->st_fill = idx;
     }
     dvbs2fec_handle::Stage& S = h->stages[h->st_fill];
-    memcpy(S.in.p + (size_t)S.n * S.in_bytes, is_sym ? (const void*)sym : (const void*)llr, S.in_bytes);
+    *slot = S.in.p + (size_t)S.n * S.in_bytes;
+    return 0;
+}
+// the frame in the acquired slot is complete (h->mu held)
+static void commit_slot(dvbs2fec_handle* h, uint64_t tag) {
+    dvbs2fec_handle::Stage& S = h->stages[h->st_fill];
     S.tags.push_back(tag);
     if (++S.n == 1) {
         S.first = std::chrono::steady_clock::now();
@@ -1055,6 +1109,33 @@ static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym
         h->st_fill = -1;
         h->cv_work.notify_all();
     }
+}
+
+static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym, uint64_t tag, const uint8_t* idx = nullptr) {
+    if (!h || !h->configured) return fail(DVBS2FEC_EINVAL, "set_modcod has not been called");
+    std::lock_guard<std::mutex> producer(h->submit_mu);
+    std::unique_lock<std::mutex> lk(h->mu);
+    if (h->acquired) return fail(DVBS2FEC_EINVAL, "a frame acquired with dvbs2fec_acquire_* has not been committed");
+    uint8_t* slot = nullptr;
+    const int kind = sym ? 1 : idx ? 2 : 0;
+    int rc = acquire_slot(h, lk, kind, &slot);
+    if (rc) return rc;
+    memcpy(slot, sym ? (const void*)sym : idx ? (const void*)idx : (const void*)llr, h->stages[h->st_fill].in_bytes);
+    commit_slot(h, tag);
+    return 0;
+}
+
+static int acquire_common(dvbs2fec_handle* h, int kind, void** slot) {
+    if (!h || !h->configured || !slot) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (kind == 2 && h->mc.constellation == APSK32) return fail(DVBS2FEC_EINVAL, "32APSK has no LUT in the reference: send symbols");
+    std::lock_guard<std::mutex> producer(h->submit_mu);
+    std::unique_lock<std::mutex> lk(h->mu);
+    if (h->acquired) return fail(DVBS2FEC_EINVAL, "the previous frame has not been committed");
+    uint8_t* p = nullptr;
+    int rc = acquire_slot(h, lk, kind, &p);
+    if (rc) return rc;
+    h->acquired = true;   // the worker leaves the batch alone until the commit (see worker_main)
+    *slot = p;
     return 0;
 }
 
@@ -1066,6 +1147,26 @@ int dvbs2fec_submit_plframe(dvbs2fec_handle* h, const float* plframe, int nsym, 
     if (!plframe || !h || !h->configured || nsym != h->plsyms)
         return fail(DVBS2FEC_EINVAL, "plframe must hold dvbs2fec_plframe_symbols() complex samples");
     return submit_common(h, nullptr, plframe, tag);
+}
+
+int dvbs2fec_submit_plframe_idx(dvbs2fec_handle* h, const uint8_t* idx, uint64_t tag) {
+    if (!idx || !h || !h->configured) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (h->mc.constellation == APSK32) return fail(DVBS2FEC_EINVAL, "32APSK has no LUT in the reference: send symbols");
+    return submit_common(h, nullptr, nullptr, tag, idx);
+}
+
+int dvbs2fec_acquire_llr(dvbs2fec_handle* h, int8_t** slot) { return acquire_common(h, 0, reinterpret_cast<void**>(slot)); }
+int dvbs2fec_acquire_plframe(dvbs2fec_handle* h, float** slot) { return acquire_common(h, 1, reinterpret_cast<void**>(slot)); }
+int dvbs2fec_acquire_plframe_idx(dvbs2fec_handle* h, uint8_t** slot) { return acquire_common(h, 2, reinterpret_cast<void**>(slot)); }
+int dvbs2fec_commit(dvbs2fec_handle* h, uint64_t tag) {
+    if (!h || !h->configured) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> producer(h->submit_mu);
+    std::unique_lock<std::mutex> lk(h->mu);
+    if (!h->acquired || h->st_fill < 0) return fail(DVBS2FEC_EINVAL, "no frame has been acquired");
+    h->acquired = false;
+    commit_slot(h, tag);
+    h->cv_work.notify_all();   // the batch may be due (latency deadline, flush) and was held back for this frame
+    return 0;
 }
 
 int dvbs2fec_collect(dvbs2fec_handle* h, uint8_t* bb_out, dvbs2fec_result* results, int max, int timeout_us) {

@@ -23,6 +23,20 @@ __device__ __forceinline__ int halving_clamp(float x) {
     return (int)x;
 }
 
+// LLR bytes of symbol s to their deinterleaved places (S2Deinterleaver::deinterleave, s2_deinterleaver.cpp:72-136)
+__device__ __forceinline__ void store_llrs(const DemapDev& d, int8_t* o, int s, const int8_t (&b)[5]) {
+    if (d.constellation == 0) {           // QPSK: the pair is swapped, no column interleave
+        *reinterpret_cast<uint16_t*>(o + 2 * s) = (uint16_t)((uint8_t)b[1] | ((uint16_t)(uint8_t)b[0] << 8));
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k < d.bits) {
+            int col = (d.reversed_cols) ? (2 - k) : k;
+            o[col * d.nsym + s] = b[k];
+        }
+}
+
 __global__ void __launch_bounds__(256) demap_kernel(const __grid_constant__ DemapDev d, const float2* __restrict__ in,
                                                     int nframes, int8_t* __restrict__ out) {
     const int frame = blockIdx.y;
@@ -63,16 +77,21 @@ __global__ void __launch_bounds__(256) demap_kernel(const __grid_constant__ Dema
         for (int jb = 0; jb < 5; ++jb)
             b[4 - jb] = (int8_t)halving_clamp((logf(acc[2 * jb + 1]) - logf(acc[2 * jb])) * d.sca);
     }
-    if (d.constellation == 0) {           // QPSK: the pair is swapped, no column interleave
-        *reinterpret_cast<uint16_t*>(o + 2 * s) = (uint16_t)((uint8_t)b[1] | ((uint16_t)(uint8_t)b[0] << 8));
-        return;
-    }
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-        if (k < d.bits) {
-            int col = (d.reversed_cols) ? (2 - k) : k;
-            o[col * d.nsym + s] = b[k];
-        }
+    store_llrs(d, o, s, b);
+}
+
+// Same gather from the two 8-bit LUT coordinates per symbol that the host computed (dvbs2fec_quantize_plframes:
+// the reference's own index arithmetic, constellation.cpp:295-310, after pilot removal and PL descrambling):
+// 2 bytes per symbol over PCIe instead of 8, identical LLRs.
+__global__ void __launch_bounds__(256) demap_idx_kernel(const __grid_constant__ DemapDev d, const uchar2* __restrict__ idx,
+                                                        int nframes, int8_t* __restrict__ out) {
+    const int frame = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= d.nsym) return;
+    const uchar2 xy = __ldg(&idx[(size_t)frame * d.nsym + s]);
+    const uint32_t w = __ldg(&d.lut[(int)xy.x * 256 + (int)xy.y]);
+    int8_t b[5] = {(int8_t)(w & 0xFF), (int8_t)((w >> 8) & 0xFF), (int8_t)((w >> 16) & 0xFF), (int8_t)(w >> 24), 0};
+    store_llrs(d, out + (size_t)frame * d.N, s, b);
 }
 
 }  // namespace
@@ -81,6 +100,14 @@ int demap_launch(const DemapDev& d, const float* plframes, int nframes, int8_t* 
     if (nframes <= 0) return 0;
     dim3 grid((d.nsym + 255) / 256, nframes);
     demap_kernel<<<grid, 256, 0, stream>>>(d, reinterpret_cast<const float2*>(plframes), nframes, llr_out);
+    return (int)cudaGetLastError();
+}
+
+int demap_idx_launch(const DemapDev& d, const uint8_t* idx, int nframes, int8_t* llr_out, cudaStream_t stream) {
+    if (nframes <= 0) return 0;
+    if (!d.lut) return (int)cudaErrorInvalidValue;   // 32APSK has no LUT
+    dim3 grid((d.nsym + 255) / 256, nframes);
+    demap_idx_kernel<<<grid, 256, 0, stream>>>(d, reinterpret_cast<const uchar2*>(idx), nframes, llr_out);
     return (int)cudaGetLastError();
 }
 

@@ -33,5 +33,7 @@ struct DemapDev {
 };
 
 int demap_launch(const DemapDev& d, const float* plframes, int nframes, int8_t* llr_out, cudaStream_t stream);
+// from LUT coordinates (two bytes per payload symbol, pilots and header already removed); not for 32APSK
+int demap_idx_launch(const DemapDev& d, const uint8_t* idx, int nframes, int8_t* llr_out, cudaStream_t stream);
 
 }  // namespace s2

@@ -150,6 +150,52 @@ def test_demapper_lut_bit_exact(dec, modcod, short):
     o.orc_const_destroy(c)
 
 
+@pytest.mark.parametrize("modcod,short,pilots,codenum", [(4, 0, False, -1), (12, 0, False, -1), (13, 1, True, 5), (18, 0, False, -1), (21, 1, True, 0)])
+def test_quantised_symbols_path_gives_identical_frames(dec, modcod, short, pilots, codenum):
+    """dvbs2fec_quantize_plframes (host: the reference's LUT index arithmetic incl. NaN / out-of-range, pilot removal,
+    PL descrambling) + dvbs2fec_decode_plframes_idx == dvbs2fec_decode_plframes on the same symbols, frame by
+    frame; also through the queue"""
+    try:
+        dec.set_pl_scrambling(codenum)
+        dec.setDemodParams(modcod, bool(short), pilots)
+        rng = np.random.default_rng(500 + modcod)
+        n = 5
+        payload = rng.integers(0, 256, (n, dec.kbch // 8), dtype=np.uint8)
+        pl = np.stack([pkg.modulate(modcod, bool(short), pilots, pkg.encode_fecframe(modcod, bool(short), payload[i])) for i in range(n)])
+        x = pl.view(np.float32).reshape(n, -1) + rng.normal(0, 0.06, (n, dec.plframe_symbols * 2)).astype(np.float32)
+        if codenum >= 0:
+            o = orclib.oracle()
+            rn = np.zeros(131072, np.uint8)
+            o.orc_pl_rn(codenum, rn)
+            nsym = dec.plframe_symbols - 90
+            for i in range(n):
+                out = np.zeros(2 * nsym, np.float32)
+                o.orc_pl_scramble(rn, np.ascontiguousarray(x[i, 180:]), nsym, out)
+                x[i, 180:] = out
+        x[0, 400:480] *= 30
+        x[0, 500] = np.nan
+        x[0, 503] = 3e30
+        x[1, 600] = -np.inf
+        want_bb, want_res = dec.decode_plframes(x)
+        idx = dec.quantize_plframes(x)
+        assert idx.shape == (n, dec.N // pkg.modcod_info(modcod, bool(short))["bits"], 2)
+        bb, res = dec.decode_plframes_idx(idx)
+        assert np.array_equal(bb, want_bb)
+        for k in ("ldpc_iters", "bch_corr", "flags"):
+            assert np.array_equal(res[k], want_res[k])
+        assert np.array_equal(bb[2:], payload[2:])
+        for i in range(n):
+            dec.submit_plframe_idx(idx[i], 40 + i)
+        dec.flush()
+        qbb, qres = dec.collect(n, timeout_us=5_000_000)
+        assert np.array_equal(qbb, want_bb) and list(qres["tag"]) == list(range(40, 40 + n))
+    finally:
+        dec.set_pl_scrambling(-1)
+    dec.setDemodParams(28, False, False)
+    with pytest.raises(pkg.DVBS2FecError):
+        dec.quantize_plframes(np.zeros((1, dec.plframe_symbols * 2), np.float32))
+
+
 @pytest.mark.parametrize("modcod,short", [(24, 1), (28, 0)])
 def test_demapper_32apsk_within_one_lsb(dec, modcod, short):
     const, ctype, rate, g1, g2 = MODCODS[modcod]
@@ -397,3 +443,37 @@ def test_pl_descrambling_inside_the_demapper(dec, modcod, short, pilots, codenum
         dec.set_pl_scrambling(-1)
     with pytest.raises(pkg.DVBS2FecError):
         dec.set_pl_scrambling(262142)
+
+
+def test_zero_copy_submit_acquire_commit(dec):
+    """frames written straight into the page-locked batch (dvbs2fec_acquire_llr / dvbs2fec_commit), mixed with copying
+    submits, come back in order and equal to decode_batch; a second acquire without commit is refused"""
+    from test_gpu_properties import make_batch
+    dec.setDemodParams(4, True, False)
+    llr, payload = make_batch(4, True, 11, 3.0, 77)
+    want_bb, want_res = dec.decode_batch(llr)
+    d = pkg.DVBS2Decoder(max_batch=4, max_latency_us=300)
+    d.setDemodParams(4, True, False)
+    for i in range(11):
+        if i % 3 == 2:
+            d.submit_llr(llr[i], i)
+        else:
+            slot = d.acquire_llr()
+            if i == 0:
+                with pytest.raises(pkg.DVBS2FecError):
+                    d.acquire_llr()
+                with pytest.raises(pkg.DVBS2FecError):
+                    d.submit_llr(llr[i], 99)
+            slot[:] = llr[i]
+            if i == 5:
+                import time
+                time.sleep(0.01)   # longer than max_latency_us: the partial batch must wait for this frame
+            d.commit(i)
+    d.flush()
+    bb, res = d.collect(16, timeout_us=5_000_000)
+    while len(res) < 11:
+        b2, r2 = d.collect(16, timeout_us=5_000_000)
+        bb, res = np.concatenate([bb, b2]), np.concatenate([res, r2])
+    assert list(res["tag"]) == list(range(11))
+    assert np.array_equal(bb, want_bb) and np.array_equal(res["ldpc_iters"], want_res["ldpc_iters"])
+    d.close()

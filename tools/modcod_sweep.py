@@ -71,6 +71,10 @@ def main():
     import time
     L = pkg.lib()
     sym_rows = []
+    # two operating points per MODCOD: nearly noise-free (the demapper and PCIe are what is measured), and the code's
+    # threshold + 1 dB, where the reference's LUT-scaled LLRs make every frame burn all 25 iterations:
+    # the decode-bound end of the symbols path.  For the LUT constellations also the quantised path (2 B per symbol).
+    thresholds = {4: 1.0, 12: 5.5, 18: 8.97, 28: 16.05}
     for modcod, name in ((4, "QPSK 1/2"), (12, "8PSK 3/5"), (18, "16APSK 2/3"), (28, "32APSK 9/10")):
         info = pkg.modcod_info(modcod, False)
         n = 1024
@@ -78,36 +82,58 @@ def main():
         dec.setDemodParams(modcod, False, False, 25)
         base = np.stack([pkg.modulate(modcod, False, False, pkg.encode_fecframe(modcod, False, rng.integers(0, 256, info["kbch"] // 8, dtype=np.uint8)))
                          for _ in range(4)]).view(np.float32).reshape(4, -1)
+        es = float((base[:, 180:] ** 2).sum() / (base[:, 180:].size / 2))   # mean symbol energy at the mapper's amplitude
         sym_bytes = base.shape[1] * 4
+        nsym = info["nldpc"] // info["bits"]
         h_in, h_bb, h_res = L.dvbs2fec_alloc_pinned(n * sym_bytes), L.dvbs2fec_alloc_pinned(n * (info["kbch"] // 8)), L.dvbs2fec_alloc_pinned(n * 16)
+        h_idx = L.dvbs2fec_alloc_pinned(n * nsym * 2)
         buf = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_float)), shape=(n, base.shape[1]))
-        nrng = np.random.default_rng(modcod)
-        for i in range(n):
-            buf[i] = base[i % 4] + nrng.normal(0, 0.04, base.shape[1]).astype(np.float32)
-        dec.set_profiling(True)
-        for _ in range(2):
-            assert L.dvbs2fec_decode_plframes(dec._h, h_in, n, h_bb, h_res) == 0
-        dec.kernel_times()
-        t0 = time.perf_counter()
-        reps = 3
-        for _ in range(reps):
-            assert L.dvbs2fec_decode_plframes(dec._h, h_in, n, h_bb, h_res) == 0
-        dt = (time.perf_counter() - t0) / reps
-        demap_ms, ldpc_ms, bch_ms, _ = dec.kernel_times()
-        res = np.ctypeslib.as_array(C.cast(h_res, C.POINTER(C.c_uint8)), shape=(n * 16,)).view(pkg.RESULT_DTYPE).reshape(-1)
-        it = res["ldpc_iters"].astype(np.int32)
-        row = {"modcod": modcod, "name": name + " normal", "frames": n, "e2e_ms": round(dt * 1e3, 3),
-               "e2e_frames_per_s": round(n / dt), "e2e_gbit_s": round(n * info["kbch"] / dt / 1e9, 2),
-               "h2d_gb_s": round(n * sym_bytes / dt / 1e9, 1),
-               "demap_ms": round(demap_ms / reps, 3), "ldpc_ms": round(ldpc_ms / reps, 3), "bch_ms": round(bch_ms / reps, 3),
-               "mean_iters": round(float(np.where(it < 0, 25, it).mean()), 2), "fer": round(float((res["bch_corr"] < 0).mean()), 4)}
-        sym_rows.append(row)
-        print(row, flush=True)
+        idx = np.ctypeslib.as_array(C.cast(h_idx, C.POINTER(C.c_uint8)), shape=(n, nsym * 2))
+        for point, esn0 in (("clean", None), ("threshold+1dB", thresholds[modcod] + 1.0)):
+            sigma = 0.04 if esn0 is None else float(np.sqrt(0.5 * es / 10 ** (esn0 / 10)))
+            nrng = np.random.default_rng(modcod)
+            for i in range(n):
+                buf[i] = base[i % 4] + nrng.normal(0, sigma, base.shape[1]).astype(np.float32)
+            paths = [("symbols (8 B/symbol)", lambda: L.dvbs2fec_decode_plframes(dec._h, h_in, n, h_bb, h_res), n * sym_bytes)]
+            quant_us = None
+            if modcod != 28:
+                t0 = time.perf_counter()
+                assert L.dvbs2fec_quantize_plframes(dec._h, h_in, n, h_idx) == 0
+                quant_us = (time.perf_counter() - t0) / n * 1e6
+                paths.append(("LUT coordinates (2 B/symbol)", lambda: L.dvbs2fec_decode_plframes_idx(dec._h, h_idx, n, h_bb, h_res), n * nsym * 2))
+            ref_bb = None
+            for pname, call, in_bytes in paths:
+                dec.set_profiling(True)
+                for _ in range(2):
+                    assert call() == 0
+                dec.kernel_times()
+                t0 = time.perf_counter()
+                reps = 3
+                for _ in range(reps):
+                    assert call() == 0
+                dt = (time.perf_counter() - t0) / reps
+                demap_ms, ldpc_ms, bch_ms, _ = dec.kernel_times()
+                res = np.ctypeslib.as_array(C.cast(h_res, C.POINTER(C.c_uint8)), shape=(n * 16,)).view(pkg.RESULT_DTYPE).reshape(-1)
+                bbv = np.ctypeslib.as_array(C.cast(h_bb, C.POINTER(C.c_uint8)), shape=(n * (info["kbch"] // 8),)).copy()
+                if ref_bb is None:
+                    ref_bb = (bbv, res.copy())
+                else:   # the quantised path must give the very same frames
+                    assert np.array_equal(bbv, ref_bb[0]) and np.array_equal(res["ldpc_iters"], ref_bb[1]["ldpc_iters"])
+                it = res["ldpc_iters"].astype(np.int32)
+                row = {"modcod": modcod, "name": name + " normal", "point": point, "esn0_db": esn0, "input": pname, "frames": n,
+                       "e2e_ms": round(dt * 1e3, 3), "e2e_frames_per_s": round(n / dt), "e2e_gbit_s": round(n * info["kbch"] / dt / 1e9, 2),
+                       "h2d_gb_s": round(in_bytes / dt / 1e9, 1),
+                       "demap_ms": round(demap_ms / reps, 3), "ldpc_ms": round(ldpc_ms / reps, 3), "bch_ms": round(bch_ms / reps, 3),
+                       "mean_iters": round(float(np.where(it < 0, 25, it).mean()), 2), "fer": round(float((res["bch_corr"] < 0).mean()), 4)}
+                if pname.startswith("LUT"):
+                    row["host_quantize_us_per_frame_1_core"] = round(quant_us, 1)
+                sym_rows.append(row)
+                print(row, flush=True)
         dec.close()
-        for ptr in (h_in, h_bb, h_res):
+        for ptr in (h_in, h_bb, h_res, h_idx):
             L.dvbs2fec_free_pinned(ptr)
     json.dump({"note": "rows: device-resident LLR input, QPSK MODCOD of each rate, Es/N0 = threshold estimate + margin, fixed noise; "
-                       "plframes: symbols in pinned host memory through dvbs2fec_decode_plframes (H2D of 8 B per symbol inside the time)",
+                       "plframes: PLFRAMEs in pinned host memory through dvbs2fec_decode_plframes (8 B per symbol) and, for the LUT constellations, dvbs2fec_decode_plframes_idx (2 B per symbol, quantised on the host beforehand); H2D inside the time",
                "rows": rows, "plframes": sym_rows}, open(args.out, "w"), indent=1)
 
 
