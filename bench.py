@@ -439,6 +439,18 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     sampler.stop()
+    # ---- what the host side can deliver at all: the same input bytes from page-locked memory, copies only, every rank at
+    #      once (under torchrun the ranks share the host's memory controllers and PCIe root complexes)
+    pin = torch.from_numpy(host_copy).pin_memory()
+    pool.copy_(pin, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        pool.copy_(pin, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_s = (time.perf_counter() - t0) / 4
+    del pin
     bb_single = np.ctypeslib.as_array(C.cast(h_bb, C.POINTER(C.c_uint8)), shape=(e2e_frames, kbch // 8)).copy()
     res_single = np.ctypeslib.as_array(C.cast(h_res, C.POINTER(C.c_uint8)), shape=(e2e_frames, 16)).copy()
 
@@ -459,7 +471,7 @@ def main():
 
     # ---- reduce over ranks
     dispatch = importlib.import_module("sdrpp-dvbs-demodulator_b200.dispatch")
-    ms_max, e2e_ms_max, ldpc_ms_max = dispatch.reduce_max([ms, e2e_s * 1e3, ldpc_ms], device=dev)
+    ms_max, e2e_ms_max, ldpc_ms_max, h2d_ms_max = dispatch.reduce_max([ms, e2e_s * 1e3, ldpc_ms, h2d_s * 1e3], device=dev)
     single_e2e_fps = e2e_frames * e2e_steps / e2e_s
 
     # ---- in-process dispatcher over all N GPUs (rank 0 only, the other ranks wait on the host)
@@ -497,7 +509,11 @@ def main():
         "kernel_ms_per_step": {"ldpc_v2_kernel": ldpc_ms / args.steps, "bch_kernel": bch_ms / args.steps},
         "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": e2e_frames * N,
                 "d2h_bytes_per_step": e2e_frames * (kbch // 8 + 16), "frames_per_step": e2e_frames, "steps": e2e_steps,
-                "api": "dvbs2fec_decode_batch (pinned host buffers)"},
+                "api": "dvbs2fec_decode_batch (pinned host buffers)",
+                "host_ceiling": {"what": "the same input bytes copied host->device and nothing else, all ranks at once, max over ranks",
+                                 "h2d_gb_s_per_gpu": args.pool * N / (h2d_ms_max * 1e-3) / 1e9,
+                                 "h2d_gb_s_total": world * args.pool * N / (h2d_ms_max * 1e-3) / 1e9,
+                                 "gbit_s_if_decoding_were_free": world * args.pool * kbch / (h2d_ms_max * 1e-3) / 1e9}},
         "roofline": {"kernel": "ldpc_v2_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": (tr[0] * args.pool / 1e9) if tr else None,
                      "traffic_unit": "GB per launch (ncu dram__bytes_read+write, %s)" % (tr[1] if tr else "n/a"), "peak_source": peak_src,

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include "bch_decoder.cuh"
 #include "demapper.cuh"
@@ -752,7 +753,14 @@ int dvbs2fec_create(const dvbs2fec_config* cfg, dvbs2fec_handle** out) {
         for (int k = 0; k < 2 * kSlots + 1; ++k) {
             CU(cudaStreamCreateWithFlags(&d->slot[k].stream, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&d->slot[k].done, cudaEventDisableTiming));
-            CU(cudaStreamCreateWithFlags(&d->slot[k].copy, cudaStreamNonBlocking));
+            // The two slots of the synchronous host path share ONE input-copy stream: their chunks then cross PCIe one
+            // after the other, in the order the kernels consume them.  With a stream each, the copy engines interleave
+            // the two transfers, the first kernel is fed at half the link rate (slower than it decodes) and the call
+            // takes a third longer (measured: e2e 17.4 -> see profiles/r02_bench_line.json).
+            if (k >= 1 && k < kSlots)
+                d->slot[k].copy = d->slot[0].copy;
+            else
+                CU(cudaStreamCreateWithFlags(&d->slot[k].copy, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&d->slot[k].armed, cudaEventDisableTiming));
         }
         h->devs.push_back(std::move(d));
@@ -778,9 +786,7 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
         cudaSetDevice(d.device);
         cudaDeviceSynchronize();   // work enqueued on caller-owned streams by the device entry point
         for (int k = 0; k < 2 * kSlots + 1; ++k) {
-            Slot& s = d.slot[k];
-            if (s.copy) cudaStreamSynchronize(s.copy);
-            if (s.stream) cudaStreamSynchronize(s.stream);
+            Slot& s = d.slot[k];   // (everything on the device has finished: cudaDeviceSynchronize above)
             s.llr.release(); s.sym.release(); s.idx.release(); s.hard.release(); s.iters.release(); s.corr.release();
             s.bb.release(); s.res.release(); s.workspace.release(); s.counter.release();
             s.h_in.release(); s.h_bb.release(); s.h_res.release();
@@ -788,7 +794,7 @@ void dvbs2fec_destroy(dvbs2fec_handle* h) {
             s.ts.release(); s.ts_len.release();
             if (s.done) cudaEventDestroy(s.done);
             if (s.armed) cudaEventDestroy(s.armed);
-            if (s.copy) cudaStreamDestroy(s.copy);
+            if (s.copy && !(k >= 1 && k < kSlots)) cudaStreamDestroy(s.copy);   // (slots 1..kSlots-1 borrow slot 0's)
             if (s.stream) cudaStreamDestroy(s.stream);
         }
         for (auto& kv : d.codes) kv.second.row_level.release();
@@ -1053,6 +1059,30 @@ int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n,
     return rc;
 }
 
+// Copy into a staging batch with non-temporal stores: the CPU never reads these bytes again (the copy engine does), so
+// they need not displace the producer's working set from its caches, and the lines are written without being read
+// first.  Measured with tools/mixed_stream on the 4-GPU box: see profiles/r02_mixed_stream_*.json.
+static void stream_copy(void* dst_v, const void* src_v, size_t n) {
+    uint8_t* dst = static_cast<uint8_t*>(dst_v);
+    const uint8_t* src = static_cast<const uint8_t*>(src_v);
+    const size_t head = std::min(n, (size_t)((16 - ((uintptr_t)dst & 15)) & 15));
+    memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    const size_t body = n & ~(size_t)63;
+    for (size_t i = 0; i < body; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+    }
+    memcpy(dst + body, src + body, n - body);
+    _mm_sfence();
+}
+
 // The slot of the next frame in the staging batch being filled (opening a batch if need be).  Called with h->mu held
 // through `lk`, which is dropped while page-locked memory is allocated.
 static int acquire_slot(dvbs2fec_handle* h, std::unique_lock<std::mutex>& lk, int kind, uint8_t** slot) {
@@ -1120,7 +1150,7 @@ static int submit_common(dvbs2fec_handle* h, const int8_t* llr, const float* sym
     const int kind = sym ? 1 : idx ? 2 : 0;
     int rc = acquire_slot(h, lk, kind, &slot);
     if (rc) return rc;
-    memcpy(slot, sym ? (const void*)sym : idx ? (const void*)idx : (const void*)llr, h->stages[h->st_fill].in_bytes);
+    stream_copy(slot, sym ? (const void*)sym : idx ? (const void*)idx : (const void*)llr, h->stages[h->st_fill].in_bytes);
     commit_slot(h, tag);
     return 0;
 }
