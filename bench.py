@@ -427,7 +427,9 @@ def main():
     h_res = L.dvbs2fec_alloc_pinned(e2e_frames * 16)
     host_copy = pool.cpu().numpy()
     C.memmove(h_in, host_copy.ctypes.data, args.pool * N)
-    dec_e = pkg.DVBS2Decoder(devices=[local_rank], max_batch=max(256, min(4096, args.pool // 4)), max_trials=MAX_TRIALS)
+    # two chunks per call, one per pipeline slot (tools/e2e_sweep2.py: 8192-frame chunks give 21.2 Gbit/s, 4096 19.5, 1024 14.8:
+    # a chunk is one kernel launch, and the fewer frame pairs a launch has per CTA the more its last wave costs)
+    dec_e = pkg.DVBS2Decoder(devices=[local_rank], max_batch=max(256, min(8192, args.pool // 2)), max_trials=MAX_TRIALS)
     dec_e.setDemodParams(MODCOD, SHORT, False, MAX_TRIALS)
     for _ in range(2):
         dec_e.decode_batch_raw(h_in, e2e_frames, h_bb, h_res)
@@ -550,7 +552,7 @@ def dispatcher_leg(pkg, L, ndev, h_in, nframes, N, kbch, bb_single, res_single, 
     """One handle, all devices: dvbs2fec_decode_batch on the same pinned input the single-device run decoded, and a
     stretch of the frame queue (submit_llr / collect).  Output bytes must equal the single-device result."""
     kb = kbch // 8
-    dec = pkg.DVBS2Decoder(devices=list(range(ndev)), max_batch=max(256, min(4096, nframes // (4 * ndev))), max_trials=MAX_TRIALS)
+    dec = pkg.DVBS2Decoder(devices=list(range(ndev)), max_batch=max(256, min(8192, nframes // (2 * ndev))), max_trials=MAX_TRIALS)
     dec.setDemodParams(MODCOD, SHORT, False, MAX_TRIALS)
     h_bb = L.dvbs2fec_alloc_pinned(nframes * kb)
     h_res = L.dvbs2fec_alloc_pinned(nframes * 16)
