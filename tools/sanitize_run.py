@@ -82,3 +82,47 @@ while n_res < len(frames):
     n_ts += len(ts); n_res += len(res)
 print("fused ts bytes", n_ts, "frames", n_res)
 dec.close()
+
+# GSE extraction: interleaved reassemblies, CRC failures, more FragIDs than slots, mixed with TS frames and sync losses;
+# host-buffer calls of several sizes, a refused call (too little room), a device-buffer call with a small pool
+ts = pkg.BBFrameTSParser()
+ts.setFrameSize(7032)
+g = bbstream.random_gse_scenario(np.random.default_rng(8), 7032, nframes=40, ts_every=4)
+tot = 0
+for a, b in ((0, 1), (1, 9), (9, 10), (10, 33), (33, len(g))):
+    tot += len(ts.work(g[a:b], b - a, 65536 * 16))
+try:
+    ts.work(g, len(g), 1000)
+except pkg.DVBS2FecError as e:
+    print("refused:", e.code)
+print("gse bytes", tot, ts.gse_counters)
+ts.close()
+# PL front end: sync on a noisy stream in uneven calls, PLHEADER demodulation, coarse FED with pilots
+import plstream  # noqa: E402
+x = plstream.stream((4 << 2) | 1, 36, True, 6, np.random.default_rng(9), esn0_db=5.0, lead=500, cfo=1e-4)
+ps = pkg.S2PLSyncBlock(36, True)
+frames = []
+for a, b in ((0, 1), (1, 100), (100, 3400), (3400, 3401), (3401, 12000), (12000, len(x))):
+    frames.append(ps.process(x[a:b]))
+fr = np.concatenate(frames).reshape(-1, ps.raw_frame_size)
+hdr, res, loop = ps.plhdr_process(fr)
+err = ps.coarse_fed(fr, True, (4 << 2) | 1, 3)
+print("plsync frames", len(fr), res[:, 0].tolist(), [round(float(e), 4) for e in err])
+ps.close()
+# quantised symbols path and zero-copy submit
+dec = pkg.DVBS2Decoder(max_batch=4, max_latency_us=300, max_trials=6)
+dec.setDemodParams(13, True, False, 6)
+pay = rng.integers(0, 256, (3, dec.kbch // 8), dtype=np.uint8)
+pl = np.stack([pkg.modulate(13, True, False, pkg.encode_fecframe(13, True, pay[i])) for i in range(3)])
+noisy = pl.view(np.float32) + rng.normal(0, 0.05, (3, dec.plframe_symbols * 2)).astype(np.float32)
+idx = dec.quantize_plframes(noisy)
+bb, res = dec.decode_plframes_idx(idx)
+print("idx path", (bb == pay).all())
+dec.setDemodParams(4, True, False, 6)
+for i in range(5):
+    slot = dec.acquire_llr()
+    slot[:] = np.where(pkg.encode_fecframe(4, True, rng.integers(0, 256, dec.kbch // 8, dtype=np.uint8)) > 0, -20, 20)
+    dec.commit(i)
+dec.flush()
+print("zero-copy", len(dec.collect(8, timeout_us=2_000_000)[1]))
+dec.close()
