@@ -223,7 +223,7 @@ int ldpc_prepare(LdpcDev& c) {
     if (c.v2) {
         pl->fn2[0] = pick_fn2(c, false);
         pl->fn2[1] = pick_fn2(c, true);
-        pl->threads = c.lanes2 ? 736 : kLdpcThreads;
+        pl->threads = c.lanes2 ? 720 : 360;   // v2::kLdpcThreads2 / v2::kThreads
         if (!pl->fn2[0] || !pl->fn2[1] || ldpc_slot_groups_for(c.max_cnt, c.lanes2) != c.sg) {
             delete pl;
             return (int)cudaErrorInvalidValue;

@@ -34,6 +34,10 @@
 namespace s2 {
 namespace v2 {
 
+// One thread per row and none to spare: 360 threads = eleven warps and a quarter.  (With 384 threads the 24 extra
+// ones either need a "row exists" predicate everywhere or shadow row 359, which racecheck rightly flags.)
+constexpr int kThreads = 360;
+
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
@@ -252,6 +256,7 @@ __device__ __noinline__ int full_test(const LdpcParams2& p, bool after_pass, con
         const int wid = tid >> 5, lane = tid & 31;
         if (wid < 12) {
             const bool row = tid < 360;
+            const unsigned wl = __activemask();     // (the CTA's last warp is a partial one)
             const int8_t* ca = inA + K + (size_t)q * (row ? tid : 0);
             const int8_t* cb = inB + K + (size_t)q * (row ? tid : 0);
             for (int i = 0; i < q; ++i) {
@@ -261,8 +266,8 @@ __device__ __noinline__ int full_test(const LdpcParams2& p, bool after_pass, con
                     const uint32_t b = STREAMED ? (uint8_t)__ldcg(cb + i) : (uint8_t)__ldg(cb + i);
                     w = (a | (b << 8)) ^ 0x8080u;
                 }
-                const unsigned ba = __ballot_sync(0xFFFFFFFFu, !(w & 0x80u));
-                const unsigned bb = __ballot_sync(0xFFFFFFFFu, !(w & 0x8000u));
+                const unsigned ba = __ballot_sync(wl, !(w & 0x80u));
+                const unsigned bb = __ballot_sync(wl, !(w & 0x8000u));
                 if (lane == 0) {
                     __stcg(&HP[i * kBitWords + wid], ba);
                     __stcg(&HP[(q + i) * kBitWords + wid], bb);
@@ -357,7 +362,7 @@ static __device__ __noinline__ bool wait_arrived(const unsigned int* arrived_ptr
 }
 
 template <int CNT, bool RAGGED, bool STREAMED, int OCC>
-__global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid_constant__ LdpcParams2 p) {
+__global__ void __launch_bounds__(kThreads, OCC) ldpc_v2_kernel(const __grid_constant__ LdpcParams2 p) {
     constexpr int SLOTS = CNT + 2;
     constexpr int MW = (SLOTS + 1) / 2;     // message words per row in registers
     constexpr int SG = (SLOTS + 7) / 8;     // uint4 groups per row in the workspace
@@ -375,10 +380,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
     __shared__ int s_bad[2];
 
     const int tid = threadIdx.x;
-    const bool active = tid < 360;
-    // Threads 360..383 shadow row 359: they read and write exactly what thread 359 (same warp) does, so the pass
-    // needs no "row exists" predicate anywhere.  Everything that must count rows once uses `active`.
-    const int j = active ? tid : 359;
+    const int j = tid;     // this thread's row in every layer
     const uint32_t vbase = (uint32_t)__cvta_generic_to_shared(vdata);
     uint32_t dbase = (uint32_t)__cvta_generic_to_shared(desc);
     uint32_t j2 = 2u * (uint32_t)j;
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
         opq->x = j2; opq->y = xaddr; opq->z = dbase; opq->w = m1;
         j2 = opq->x; xaddr = opq->y; dbase = opq->z; m1 = opq->w;
     }
-    for (int x = tid; x < q * DW; x += kLdpcThreads) {
+    for (int x = tid; x < q * DW; x += kThreads) {
         const int i = x / DW, w = x - i * DW;
         const int loff = p.layer_off[i], cnt = (int)p.layer_off[i + 1] - loff;
         uint32_t v = 0;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
     const int npairs = (p.nframes + 1) >> 1;
 
     // zero the bit planes once: bytes 45..51 of every 360-bit group are never written and must read as 0
-    for (int x = tid; x < 2 * (p.ngroups + q) * kBitWords; x += kLdpcThreads) __stcg(&HD[x], 0u);
+    for (int x = tid; x < 2 * (p.ngroups + q) * kBitWords; x += kThreads) __stcg(&HD[x], 0u);
 
     for (;;) {
         __syncthreads();
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
         };
 
         // ---- load: systematic LLRs -> shared (A in even bytes, B in odd), offset binary
-        for (int x = tid; x < K / 8; x += kLdpcThreads) {
+        for (int x = tid; x < K / 8; x += kThreads) {
             // streamed: the copy engine is still writing other frames of this buffer -> L2-coherent loads
             uint2 a = STREAMED ? __ldcg(reinterpret_cast<const uint2*>(inA) + x) : __ldg(reinterpret_cast<const uint2*>(inA) + x);
             uint2 b = STREAMED ? __ldcg(reinterpret_cast<const uint2*>(inB) + x) : __ldg(reinterpret_cast<const uint2*>(inB) + x);
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
             int bad = 0;
             if ((sx & 0x80u) || (mn & 0xFFFFu) == 0) bad |= 1;
             if ((sx & 0x800000u) || (mn >> 16) == 0) bad |= 2;
-            return bad;       // (threads 360..383 repeat row 359's verdict)
+            return bad;
         };
 
         __syncthreads();
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
             //      screen found nothing for a frame that is still iterating
             int bad = (__syncthreads_or(scr & 1) ? 1 : 0) | (__syncthreads_or(scr & 2) ? 2 : 0);
             if (live & ~bad)
-                bad = full_test<STREAMED, kLdpcThreads>(p, n > 0, wpty, HP, HD, reinterpret_cast<const uint4*>(vdata), inA, inB, s_bad);
+                bad = full_test<STREAMED, kThreads>(p, n > 0, wpty, HP, HD, reinterpret_cast<const uint4*>(vdata), inA, inB, s_bad);
             // ---- while (bad() && --trials >= 0) update();  (layered_decoder.hh:127-128), per frame
             int fin = 0;
             for (int f = 0; f < 2; ++f) {
@@ -532,8 +534,11 @@ __global__ void __launch_bounds__(kLdpcThreads, OCC) ldpc_v2_kernel(const __grid
                 }
             }
             if (fin) {
-                emit_results<kLdpcThreads>(p, fin, res, fa, fb, n > 0, wpty, reinterpret_cast<const uint4*>(vdata), inA, inB);
+                emit_results<kThreads>(p, fin, res, fa, fb, n > 0, wpty, reinterpret_cast<const uint4*>(vdata), inA, inB);
                 live &= ~fin;
+                // the other frame goes on: nobody may start the next pass (it overwrites the LLRs and the parity
+                // words in the workspace) while a slower warp is still reading them out
+                if (live) __syncthreads();
             }
             if (!live) break;
 

@@ -21,7 +21,7 @@
 namespace s2 {
 namespace v2 {
 
-constexpr int kLdpcThreads2 = 736;   // 23 warps: 720 half rows + 16 shadows of row 359 in the same warp as the real ones
+constexpr int kLdpcThreads2 = 720;   // one thread per half row: 22 warps and a half
 
 // One half of a check row for both frames of the pair.
 //   off[]  : shared-memory addresses of this half's data links (slot s = link 2 s + h)
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(kLdpcThreads2, 1) ldpc_v2l_kernel(const __grid
 
     const int tid = threadIdx.x;
     const int h = tid & 1;
-    // threads 720..735 shadow row 359 (same warp as the real ones: same values, same addresses, same instruction)
-    const int j = min(tid >> 1, 359);
+    const int j = tid >> 1;
+    const unsigned wl = __activemask();      // this warp's lanes (the CTA's last warp is half a warp)
     const int slot_t = 2 * j + h;            // index of this half row in the workspace records
     const uint32_t vbase = (uint32_t)__cvta_generic_to_shared(vdata);
     uint32_t dbase = (uint32_t)__cvta_generic_to_shared(desc) + 16u + (uint32_t)h * HW * 4u;
@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(kLdpcThreads2, 1) ldpc_v2l_kernel(const __grid
                 }
             }
             if (nl & 1) sx ^= kC128;
-            sx ^= __shfl_xor_sync(0xFFFFFFFFu, sx, 1);
-            mn = minu2(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, 1));
+            sx ^= __shfl_xor_sync(wl, sx, 1);
+            mn = minu2(mn, __shfl_xor_sync(wl, mn, 1));
             int bad = 0;
             if ((sx & 0x80u) || (mn & 0xFFFFu) == 0) bad |= 1;
             if ((sx & 0x800000u) || (mn >> 16) == 0) bad |= 2;
@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(kLdpcThreads2, 1) ldpc_v2l_kernel(const __grid
             if (fin) {
                 emit_results<T>(p, fin, res, fa, fb, n > 0, wpty, reinterpret_cast<const uint4*>(vdata), inA, inB);
                 live &= ~fin;
+                // the other frame goes on: nobody may start the next pass (it overwrites the LLRs and the parity
+                // words in the workspace) while a slower warp is still reading them out
+                if (live) __syncthreads();
             }
             if (!live) break;
 
@@ -319,12 +322,12 @@ __global__ void __launch_bounds__(kLdpcThreads2, 1) ldpc_v2l_kernel(const __grid
                     if (FIRST) lev_next = (i + 1 < q && p.layer_nlev[i + 1] > 1) ? (uint32_t)p.row_level[(i + 1) * 360 + j] << 24 : 0u;
                     constexpr bool kPartial = RAGGED || (CNT & 1);   // some half has fewer links than NL
                     if (nlev == 1) {
-                        row_update2<NL, FIRST, kPartial>(off, cntl, mw, preg, keep, m1, 0xFFFFFFFFu);
+                        row_update2<NL, FIRST, kPartial>(off, cntl, mw, preg, keep, m1, wl);
                         if (lw0 & 0x100u) __syncthreads();
                     } else {
                         const int mylev = (int)(keep >> 24);
                         for (int lvl = 0; lvl < nlev; ++lvl) {
-                            const unsigned lanes = __ballot_sync(0xFFFFFFFFu, mylev == lvl);
+                            const unsigned lanes = __ballot_sync(wl, mylev == lvl);
                             if (mylev == lvl) row_update2<NL, FIRST, kPartial>(off, cntl, mw, preg, keep, m1, lanes);
                             __syncthreads();
                         }
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(kLdpcThreads2, 1) ldpc_v2l_kernel(const __grid
                         else
                             __stcg(pp - 360, (uint16_t)pack_pair(preg));
                     }
-                    const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, preg, 1);
+                    const uint32_t other = __shfl_xor_sync(wl, preg, 1);
                     if (h == 1 && i + 1 < q) preg = other;
                     rp += 2 * SG * 360;
                     pp += 360;
