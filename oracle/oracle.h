@@ -73,6 +73,10 @@ void orc_const_points(const orc_constellation* c, float* re_im); /* constellatio
 void orc_demod_soft_calc(const orc_constellation* c, float re, float im, int8_t* bits);
 void orc_demod_soft_lut(const orc_constellation* c, float re, float im, int8_t* bits);
 void orc_mod(const orc_constellation* c, int symbol, float* re_im);
+/* phase_error of demod_soft_calc / demod_soft_lut (constellation.cpp:258-260,317-318) and the 256x256 table */
+float orc_demod_phase_error_calc(const orc_constellation* c, float re, float im);
+float orc_demod_phase_error(const orc_constellation* c, float re, float im);
+const float* orc_const_phase_lut(const orc_constellation* c);
 /* S2Deinterleaver::deinterleave (s2_deinterleaver.cpp:72-136); constellation 0=QPSK 1=8PSK 2=16APSK 3=32APSK */
 void orc_deinterleave(int constellation, int shortframe, int rate, const int8_t* in, int8_t* out);
 /* S2BBToSoft::process (dvbs2_bb_to_soft.cpp:7-33), pilots off: plframe = 90 header symbols + payload */
@@ -97,6 +101,17 @@ int orc_plhdr_process(orc_plhdr* p, int count, const float* in, float* out90, in
 float orc_coarse_fed(const float* frame, int raw_frame_size, int pilots, int pls_code, const uint8_t* rn);
 void orc_plheader_symbols(int pls_code, float* out90);                                /* s2_sof + s2_plscodes symbols */
 uint64_t orc_pls_codeword(int pls_code);
+
+/* ---- row 8(f)-2 (oracle_pll.c): S2PLLBlock, the payload phase loop (dvbs2/dvbs2_pll.cpp:5-86, dvbs2_pll.h:47-59) ---- */
+typedef struct orc_pll orc_pll;
+/* init + the members DVBS2Demod::init sets (module_dvbs2_demod.cpp:59-65) + update(); const_type as orc_const_create */
+orc_pll* orc_pll_create(float loop_bw, int const_type, float g1, float g2, int frame_slot_count, int pilots, int pls_code,
+                        int codenum);
+void orc_pll_destroy(orc_pll* p);
+int orc_pll_pilot_cnt(const orc_pll* p);
+/* process(): one frame in, (frame_slot_count + 1) * 90 + pilot_cnt * 36 symbols out (returned);
+ * state = {pcl.phase, pcl.freq, error} after the call */
+int orc_pll_process(orc_pll* p, const float* in, float* out, float* state);
 
 #ifdef __cplusplus
 }

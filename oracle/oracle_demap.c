@@ -25,6 +25,7 @@ struct orc_constellation {
     float amp, sca, prescale;
     float re[32], im[32];
     int8_t* lut; /* [256][256][bits] */
+    float* perr; /* [256][256]: SoftResult::phase_error of the cell (constellation.cpp:284-288) */
 };
 
 /* constellation_t::polar: float a = i*2*M_PI/n (double product rounded to float) */
@@ -78,6 +79,47 @@ void orc_demod_soft_calc(const orc_constellation* c, float re, float im, int8_t*
     for (int i = 0; i < c->bits; ++i)
         bits[c->bits - 1 - i] = clamp8((logf(tmp[2 * i + 1]) - logf(tmp[2 * i + 0])) * c->sca);
 }
+
+/* the phase_error output of demod_soft_calc (constellation.cpp:209-231,258-260): the sample, scaled like the LLR
+ * part, against the nearest point (the first one among equals: "dist < min_dist") */
+float orc_demod_phase_error_calc(const orc_constellation* c, float re, float im)
+{
+    if (c->amp != 1) {
+        re = re * c->amp;
+        im = im * c->amp;
+    }
+    if (c->prescale != 1) {
+        re = re * c->prescale;
+        im = im * c->prescale;
+    }
+    float min_dist = FLT_MAX, cr = 0, ci = 0;
+    for (int i = 0; i < c->states; ++i) {
+        float dr = re - c->re[i], di = im - c->im[i];
+        float dist = sqrtf((dr * dr) + (di * di));
+        if (dist < min_dist) {
+            min_dist = dist;
+            cr = c->re[i];
+            ci = c->im[i];
+        }
+    }
+    /* (sample * closest.conj()).phase(), complex_t::operator* of oracle/shim/dsp/types.h */
+    float bi = -ci;
+    float pr = (re * cr) - (im * bi), pi = (im * cr) + (re * bi);
+    return atan2f(pi, pr);
+}
+/* demod_soft_lut(sample, nullptr, &phase_error) (constellation.cpp:293-322) */
+float orc_demod_phase_error(const orc_constellation* c, float re, float im)
+{
+    if (c->bits == 5) return orc_demod_phase_error_calc(c, re, im);
+    int x = (int)((re / 1.5) * 256 + 256 / 2);
+    if (x < 0) x = 0;
+    if (x >= 256) x = 255;
+    int y = (int)((im / 1.5) * 256 + 256 / 2);
+    if (y < 0) y = 0;
+    if (y >= 256) y = 255;
+    return c->perr[(size_t)x * 256 + y];
+}
+const float* orc_const_phase_lut(const orc_constellation* c) { return c->perr; }
 
 orc_constellation* orc_const_create(int type, float g1, float g2)
 {
@@ -154,11 +196,13 @@ orc_constellation* orc_const_create(int type, float g1, float g2)
     }
     /* make_lut(256): sample grid (x - 128)/256 * 1.5 on both axes, x outer */
     c->lut = (int8_t*)malloc((size_t)256 * 256 * c->bits);
+    c->perr = (float*)malloc((size_t)256 * 256 * sizeof(float));
     for (int x = 0; x < 256; ++x)
         for (int y = 0; y < 256; ++y) {
             float xv = ((float)(x - 256 / 2) / (float)256) * 1.5f;
             float yv = ((float)(y - 256 / 2) / (float)256) * 1.5f;
             orc_demod_soft_calc(c, xv, yv, &c->lut[((size_t)x * 256 + y) * c->bits]);
+            c->perr[(size_t)x * 256 + y] = orc_demod_phase_error_calc(c, xv, yv);
         }
     return c;
 }
@@ -167,6 +211,7 @@ void orc_const_destroy(orc_constellation* c)
 {
     if (c) {
         free(c->lut);
+        free(c->perr);
         free(c);
     }
 }

@@ -26,6 +26,7 @@
 #define private public   // the phase loop of S2PLHDRDemod is a private member; the tests compare its state
 #include "dvbs2/dvbs2_pl_sync.h"
 #include "dvbs2/dvbs2_plhdr_demod.h"
+#include "dvbs2/dvbs2_pll.h"          // row 8(f)-2: the payload phase loop (its pcl is private too)
 #undef private
 #include "dvbs2/dvbs2_fed.h"
 
@@ -327,5 +328,35 @@ void ref_plheader_symbols(int pls_code, float* out90) {
     for (int i = 0; i < 64; ++i) { out90[52 + 2 * i] = g_pls.symbols[pls_code][i].re; out90[52 + 2 * i + 1] = g_pls.symbols[pls_code][i].im; }
 }
 unsigned long long ref_pls_codeword(int pls_code) { return g_pls.codewords[pls_code]; }
+
+// ---- S2PLLBlock (dvbs2/dvbs2_pll.h:17-78, dvbs2_pll.cpp:5-86) as DVBS2Demod::init sets it up
+//      (module_dvbs2_demod.cpp:59-65): init, pilots, constellation + make_lut(256), frame_slot_count, pls_code, update ----
+struct RefPll {
+    S2PLLBlock blk;
+    std::unique_ptr<dsp::dvbs2::S2Scrambling> sc;
+};
+void* ref_pll_create(float loop_bw, int const_type, float g1, float g2, int frame_slot_count, int pilots, int pls_code, int codenum) {
+    auto* r = new RefPll();
+    r->sc.reset(new dsp::dvbs2::S2Scrambling(codenum));
+    r->blk.init(nullptr, loop_bw, &g_sof, &g_pls, r->sc.get());
+    r->blk.pilots = pilots != 0;
+    r->blk.constellation = std::make_shared<dsp::constellation_t>((dsp::constellation_type_t)const_type, g1, g2);
+    r->blk.constellation->make_lut(256);
+    r->blk.frame_slot_count = frame_slot_count;
+    r->blk.pls_code = pls_code;
+    r->blk.update();
+    return r;
+}
+// one frame in (at least (frame_slot_count + 1) * 90 + pilot_cnt * 36 symbols), as many symbols out; returns that number.
+// state = {pcl.phase, pcl.freq, error (the block's public average)}
+int ref_pll_process(void* h, int count, const float* in, float* out, float* state) {
+    auto* r = static_cast<RefPll*>(h);
+    int n = r->blk.process(count, (dsp::complex_t*)in, (dsp::complex_t*)out);
+    state[0] = r->blk.pcl.phase;
+    state[1] = r->blk.pcl.freq;
+    state[2] = r->blk.error;
+    return n;
+}
+int ref_pll_pilot_cnt(void* h) { return static_cast<RefPll*>(h)->blk.pilot_cnt; }
 
 } // extern "C"

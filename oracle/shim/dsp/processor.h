@@ -7,6 +7,7 @@
 #pragma once
 #include <cassert>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include "types.h"
 #include <volk/volk.h>

@@ -90,6 +90,17 @@ def oracle():
         lib.orc_plheader_symbols.argtypes = [C.c_int, _f32p]
         lib.orc_pls_codeword.argtypes = [C.c_int]
         lib.orc_pls_codeword.restype = C.c_uint64
+        lib.orc_demod_phase_error.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        lib.orc_demod_phase_error.restype = C.c_float
+        lib.orc_demod_phase_error_calc.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        lib.orc_demod_phase_error_calc.restype = C.c_float
+        lib.orc_const_phase_lut.argtypes = [C.c_void_p]
+        lib.orc_const_phase_lut.restype = C.POINTER(C.c_float)
+        lib.orc_pll_create.argtypes = [C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.orc_pll_create.restype = C.c_void_p
+        lib.orc_pll_destroy.argtypes = [C.c_void_p]
+        lib.orc_pll_pilot_cnt.argtypes = [C.c_void_p]
+        lib.orc_pll_process.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
         _oracle = lib
     return _oracle
 
@@ -133,6 +144,11 @@ def ref():
             lib.ref_plheader_symbols.argtypes = [C.c_int, _f32p]
             lib.ref_pls_codeword.argtypes = [C.c_int]
             lib.ref_pls_codeword.restype = C.c_uint64
+        if hasattr(lib, "ref_pll_create"):
+            lib.ref_pll_create.argtypes = [C.c_float, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+            lib.ref_pll_create.restype = C.c_void_p
+            lib.ref_pll_process.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p]
+            lib.ref_pll_pilot_cnt.argtypes = [C.c_void_p]
         if hasattr(lib, "ref_ts_create"):
             lib.ref_ts_create.argtypes = [C.c_int]
             lib.ref_ts_create.restype = C.c_void_p
