@@ -240,6 +240,40 @@ int dvbs2fec_coarse_fed(dvbs2fec_plsync* p, int nframes, const float* frames, in
 int dvbs2fec_coarse_fed_device(dvbs2fec_plsync* p, int nframes, const float* d_frames, int pilots, int pls_code,
                                int codenum, float* d_err, void* stream);
 
+/* ---- the payload phase loop: S2PLLBlock, between PL sync and the demapper
+ *      (dvbs2/module_dvbs2_demod.cpp:332).  Part of the same object: it shares the PLHEADER tables and the PL
+ *      scrambling sequence, and its state (pcl.phase, pcl.freq) lives on the device between calls. ---- */
+/* S2PLLBlock::init + the members DVBS2Demod::init / setDemodParams set (dvbs2_pll.cpp:5-14, module_dvbs2_demod.cpp:59-65,
+ * 146-151): loop bandwidth -> criticallyDamped coefficients, constellation of the MODCOD (with its phase-error table),
+ * frame_slot_count, pls_code = modcod << 2 | shortframes << 1 | pilots, update() (pilot_cnt counted as the reference
+ * counts it, dvbs2_pll.h:47-59); codenum = Gold code of the PL scrambler.  The loop state is kept (the reference
+ * only re-creates the constellation); dvbs2fec_pll_reset zeroes phase and frequency (dvbs2_pll.cpp:16-23). */
+int dvbs2fec_pll_set_params(dvbs2fec_plsync* p, float loop_bw, int modcod, int shortframes, int pilots, int codenum);
+int dvbs2fec_pll_reset(dvbs2fec_plsync* p);
+/* hand the loop a state (a host-side loop that ran so far, or a test): pcl.phase, pcl.freq */
+int dvbs2fec_pll_set_state(dvbs2fec_plsync* p, float phase, float freq);
+/* 1: walk the loop one symbol at a time in one thread, as the reference does (the yardstick: the default kernel, which
+ * speculates 32 symbols at a time, produces the same bits -- tests/test_gpu_pll.py -- and is several times faster) */
+int dvbs2fec_pll_set_sequential(dvbs2fec_plsync* p, int on);
+/* symbols process() handles per frame: (frame_slot_count + 1) * 90 + pilot_cnt * 36 */
+int dvbs2fec_pll_frame_symbols(const dvbs2fec_plsync* p);
+/* S2PLLBlock::process (dvbs2_pll.cpp:34-86) for nframes consecutive frames of the stream, frame_stride symbols apart
+ * (raw_frame_size as PL sync delivers them; at least dvbs2fec_pll_frame_symbols): derotated header symbols and
+ * derotated, PL-descrambled payload symbols out, same stride; state (optional) = pcl.phase, pcl.freq and the block's
+ * public `error` after every frame (3 floats each).  Returns nframes.  sin / cos / atan2 are the device's: symbols and
+ * state agree with the reference to float rounding (tests: 2e-4), everything else is the reference's arithmetic. */
+int dvbs2fec_pll_process(dvbs2fec_plsync* p, int nframes, int frame_stride, const float* frames, float* out, float* state);
+/* same on device buffers, asynchronous on `stream`; d_state optional (3 floats per frame) */
+int dvbs2fec_pll_process_device(dvbs2fec_plsync* p, int nframes, int frame_stride, const float* d_frames, float* d_out,
+                                float* d_state, void* stream);
+/* Several independent streams (transponders) in one launch, a warp each: objs[k] processes nframes frames from
+ * d_frames[k] into d_out[k] (device buffers, same frame_stride; all objects on the same device and configured).
+ * Frames of one stream are a recurrence and cannot overlap; streams can. */
+int dvbs2fec_pll_process_multi_device(int nstreams, dvbs2fec_plsync* const* objs, int nframes, int frame_stride,
+                                      const float* const* d_frames, float* const* d_out, void* stream);
+/* diagnostic: evaluation rounds the last call needed (two per block of 32 symbols is the minimum) */
+int dvbs2fec_pll_rounds(dvbs2fec_plsync* p);
+
 /* ---- in-tree transmitter for synthetic input (not part of the reference's decode path) ---- */
 /* bbframe: kbch/8 bytes -> code_bits: N bytes of 0/1 (BB scramble, BCH, LDPC; EN 302 307 5.2-5.3) */
 int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits);

@@ -131,6 +131,15 @@ def lib():
     L.dvbs2fec_plhdr_process_device.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.dvbs2fec_coarse_fed.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]
     L.dvbs2fec_coarse_fed_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.dvbs2fec_pll_set_params.argtypes = [vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.dvbs2fec_pll_reset.argtypes = [vp]
+    L.dvbs2fec_pll_frame_symbols.argtypes = [vp]
+    L.dvbs2fec_pll_process.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.dvbs2fec_pll_process_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.dvbs2fec_pll_rounds.argtypes = [vp]
+    L.dvbs2fec_pll_set_state.argtypes = [vp, C.c_float, C.c_float]
+    L.dvbs2fec_pll_set_sequential.argtypes = [vp, C.c_int]
+    L.dvbs2fec_pll_process_multi_device.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]
     _lib = L
     return L
 
@@ -515,3 +524,42 @@ class S2PLSyncBlock:
         err = np.zeros(len(x), np.float32)
         _check(lib().dvbs2fec_coarse_fed(self._p, len(x), _ptr(x), int(pilots), pls_code, codenum, _ptr(err)))
         return err
+
+    # ---- S2PLLBlock (dvbs2/dvbs2_pll.h:17-78): the payload phase loop, same device object ----
+    def pll_set_params(self, loop_bw, modcod, shortframes=False, pilots=False, codenum=0):
+        _check(lib().dvbs2fec_pll_set_params(self._p, loop_bw, modcod, int(shortframes), int(pilots), codenum))
+        self.pll_frame_symbols = _check(lib().dvbs2fec_pll_frame_symbols(self._p))
+
+    def pll_reset(self):
+        _check(lib().dvbs2fec_pll_reset(self._p))
+
+    def pll_set_state(self, phase, freq):
+        _check(lib().dvbs2fec_pll_set_state(self._p, phase, freq))
+
+    def pll_set_sequential(self, on):
+        _check(lib().dvbs2fec_pll_set_sequential(self._p, int(on)))
+
+    def pll_process(self, frames, frame_stride=None):
+        """frames [n][frame_stride] complex64 (consecutive frames of the stream) -> (out [n][frame_stride], of which the
+        first pll_frame_symbols of every frame are written; state [n][3] = pcl.phase, pcl.freq, error after each frame)"""
+        stride = frame_stride or self.raw_frame_size
+        x = np.ascontiguousarray(frames, np.complex64).reshape(-1, stride)
+        out = np.zeros_like(x)
+        st = np.zeros((len(x), 3), np.float32)
+        _check(lib().dvbs2fec_pll_process(self._p, len(x), stride, _ptr(x), _ptr(out), _ptr(st)))
+        return out, st
+
+    def pll_process_device(self, d_frames_ptr, nframes, frame_stride, d_out_ptr, d_state_ptr=0, stream_ptr=0):
+        _check(lib().dvbs2fec_pll_process_device(self._p, nframes, frame_stride, d_frames_ptr, d_out_ptr, d_state_ptr, stream_ptr))
+
+    def pll_rounds(self):
+        return _check(lib().dvbs2fec_pll_rounds(self._p))
+
+
+def pll_process_multi_device(blocks, d_frames_ptrs, nframes, frame_stride, d_out_ptrs, stream_ptr=0):
+    """dvbs2fec_pll_process_multi_device: one launch for several S2PLSyncBlock objects (independent streams)"""
+    n = len(blocks)
+    objs = (C.c_void_p * n)(*[b._p for b in blocks])
+    fin = (C.c_void_p * n)(*d_frames_ptrs)
+    fout = (C.c_void_p * n)(*d_out_ptrs)
+    _check(lib().dvbs2fec_pll_process_multi_device(n, objs, nframes, frame_stride, fin, fout, stream_ptr))

@@ -2,6 +2,7 @@
 #include "host_tables.h"
 
 #include <cmath>
+#include <limits>
 #include <cstring>
 #include <mutex>
 
@@ -259,6 +260,35 @@ std::vector<uint32_t> demap_lut(const ConstellationHost& c) {
             uint32_t w = 0;
             for (int k = 0; k < c.bits && k < 4; ++k) w |= (uint32_t)(uint8_t)b[k] << (8 * k);
             lut[x * 256 + y] = w;
+        }
+    return lut;
+}
+
+float demap_phase_error(const ConstellationHost& c, float re, float im) {
+    if (c.amp != 1) { re = re * c.amp; im = im * c.amp; }
+    if (c.prescale != 1) { re = re * c.prescale; im = im * c.prescale; }
+    float best = std::numeric_limits<float>::max(), cr = 0, ci = 0;
+    for (int i = 0; i < c.states; ++i) {
+        float dr = re - c.re[i], di = im - c.im[i];
+        float dist = sqrtf((dr * dr) + (di * di));
+        if (dist < best) {       // the first point among equally near ones
+            best = dist;
+            cr = c.re[i];
+            ci = c.im[i];
+        }
+    }
+    // (sample * closest.conj()).phase()
+    const float bi = -ci;
+    const float pr = (re * cr) - (im * bi), pi = (im * cr) + (re * bi);
+    return atan2f(pi, pr);
+}
+
+std::vector<float> demap_phase_lut(const ConstellationHost& c) {
+    std::vector<float> lut(256 * 256);
+    for (int x = 0; x < 256; ++x)
+        for (int y = 0; y < 256; ++y) {
+            float xv = ((float)(x - 128) / 256.0f) * 1.5f, yv = ((float)(y - 128) / 256.0f) * 1.5f;
+            lut[x * 256 + y] = demap_phase_error(c, xv, yv);
         }
     return lut;
 }

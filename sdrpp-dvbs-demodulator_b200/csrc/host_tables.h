@@ -57,6 +57,10 @@ ConstellationHost make_constellation(Constellation type, float g1, float g2);
 void demap_calc(const ConstellationHost& c, float re, float im, int8_t* bits);
 // 256x256 LUT of constellation_t::make_lut (:272-291), one uint32 per cell (byte k = soft bit k)
 std::vector<uint32_t> demap_lut(const ConstellationHost& c);
+// phase_error of constellation_t::demod_soft_calc (:209-231,258-260) for one sample, and the 256x256 table of it that
+// make_lut stores per cell (:284-288): what S2PLLBlock::process reads through demod_soft_lut (dvbs2_pll.cpp:45,49)
+float demap_phase_error(const ConstellationHost& c, float re, float im);
+std::vector<float> demap_phase_lut(const ConstellationHost& c);
 // transmit point for a group of `bits` code bits (first bit = MSB of the label), unit-energy scale the
 // reference's own modulator uses (constellation_t::mod, :156-158)
 void map_symbol(const ConstellationHost& c, const uint8_t* code_bits, float* re_im);

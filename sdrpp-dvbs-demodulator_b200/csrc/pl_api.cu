@@ -124,6 +124,14 @@ struct dvbs2fec_plsync {
     Buf<uint8_t> rn;
     int rn_codenum = -2;
     PlSyncState h_st{};
+    // S2PLLBlock (K8)
+    Buf<PllState> pst;
+    Buf<float> perr, pll_state;
+    Buf<float2> pll_in, pll_out;
+    Buf<uint8_t> pll_jobs;
+    PllArgs pll{};            // configuration part; buffers are filled in per call
+    bool pll_ready = false;
+    bool pll_sequential = false;
 };
 
 extern "C" {
@@ -146,6 +154,8 @@ int dvbs2fec_plsync_create(int device, dvbs2fec_plsync** out) {
     build_tables(*t);
     CU(cudaMemcpy(p->tab.p, t.get(), sizeof(PlTables), cudaMemcpyHostToDevice));
     CU(cudaMemset(p->hst.p, 0, sizeof(PlHdrState)));
+    CU(p->pst.reserve(1));
+    CU(cudaMemset(p->pst.p, 0, sizeof(PllState)));
     *out = p.release();
     return 0;
 }
@@ -160,6 +170,7 @@ void dvbs2fec_plsync_destroy(dvbs2fec_plsync* p) {
     p->work[0].release(); p->work[1].release(); p->out.release(); p->frames_in.release(); p->hdr_out.release();
     p->metric.release(); p->fed_out.release(); p->starts.release(); p->st.release(); p->hst.release(); p->hres.release();
     p->tab.release(); p->rn.release();
+    p->pst.release(); p->perr.release(); p->pll_state.release(); p->pll_in.release(); p->pll_out.release(); p->pll_jobs.release();
     delete p;
 }
 
@@ -357,6 +368,164 @@ int dvbs2fec_coarse_fed(dvbs2fec_plsync* p, int nframes, const float* frames, in
     CU(cudaMemcpyAsync(err, p->fed_out.p, (size_t)nframes * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     return nframes;
+}
+
+// ---------------------------------------------------------------------------------------------- S2PLLBlock (K8)
+int dvbs2fec_pll_set_params(dvbs2fec_plsync* p, float loop_bw, int modcod, int shortframes, int pilots, int codenum) {
+    if (!p) return api_fail(DVBS2FEC_EINVAL, "handle is NULL");
+    ModcodCfg cfg;
+    if (!modcod_config(modcod, shortframes != 0, pilots != 0, &cfg)) return api_fail(DVBS2FEC_EINVAL, "modcod outside 1..28");
+    CU(cudaSetDevice(p->device));
+    int rc = fed_tables(p, 1, codenum);   // the loop descrambles every payload symbol, pilots or not
+    if (rc) return rc;
+    // PhaseControlLoop<float>::criticallyDamped(loop_bw, alpha, beta) (dvbs2_pll.cpp:10)
+    PllState s{};
+    CU(cudaMemcpy(&s, p->pst.p, sizeof s, cudaMemcpyDeviceToHost));
+    const float bw = loop_bw;
+    const float damp = (float)(sqrt(2.0) / 2.0);
+    const float den = (float)(1.0 + 2.0 * damp * bw + bw * bw);
+    s.alpha = (4 * damp * bw) / den;
+    s.beta = (4 * bw * bw) / den;
+    CU(cudaMemcpy(p->pst.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    PllArgs& a = p->pll;
+    a = PllArgs{};
+    a.pilot_cnt = 0;
+    if (pilots) {   // S2PLLBlock::update (dvbs2_pll.h:47-59): counted from the slot number (SURVEY.md note N2)
+        int raw_size = (cfg.slots - 90) / 90;
+        a.pilot_cnt = 1;
+        raw_size -= 16;
+        while (raw_size > 16) {
+            raw_size -= 16;
+            a.pilot_cnt++;
+        }
+    }
+    a.total = (cfg.slots + 1) * 90 + a.pilot_cnt * 36;
+    a.divisor = (float)(cfg.slots + 1) * 90 + a.pilot_cnt * 36;
+    a.pls_code = (modcod << 2 | (shortframes ? 2 : 0) | (pilots ? 1 : 0)) & 127;
+    const ConstellationHost c = make_constellation(cfg.constellation, cfg.g1, cfg.g2);
+    a.amp = c.amp;
+    a.prescale = c.prescale;
+    a.states = c.states;
+    for (int i = 0; i < c.states; ++i) {
+        a.pts[2 * i] = c.re[i];
+        a.pts[2 * i + 1] = c.im[i];
+    }
+    if (cfg.constellation != APSK32) {   // the reference has no table for 32APSK (constellation.cpp:294,319-321)
+        const std::vector<float> lut = demap_phase_lut(c);
+        CU(p->perr.reserve(lut.size()));
+        CU(cudaMemcpy(p->perr.p, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice));
+        a.perr_lut = p->perr.p;
+    }
+    a.rn = p->rn.p;
+    a.tab = p->tab.p;
+    a.st = p->pst.p;
+    p->pll_ready = true;
+    return 0;
+}
+
+int dvbs2fec_pll_reset(dvbs2fec_plsync* p) {
+    if (!p) return api_fail(DVBS2FEC_EINVAL, "handle is NULL");
+    CU(cudaSetDevice(p->device));
+    PllState s{};
+    CU(cudaMemcpy(&s, p->pst.p, sizeof s, cudaMemcpyDeviceToHost));
+    s.phase = 0;
+    s.freq = 0;
+    CU(cudaMemcpy(p->pst.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int dvbs2fec_pll_set_state(dvbs2fec_plsync* p, float phase, float freq) {
+    if (!p) return api_fail(DVBS2FEC_EINVAL, "handle is NULL");
+    CU(cudaSetDevice(p->device));
+    PllState s{};
+    CU(cudaMemcpy(&s, p->pst.p, sizeof s, cudaMemcpyDeviceToHost));
+    s.phase = phase;
+    s.freq = freq;
+    CU(cudaMemcpy(p->pst.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int dvbs2fec_pll_set_sequential(dvbs2fec_plsync* p, int on) {
+    if (!p) return api_fail(DVBS2FEC_EINVAL, "handle is NULL");
+    p->pll_sequential = on != 0;
+    return 0;
+}
+
+int dvbs2fec_pll_frame_symbols(const dvbs2fec_plsync* p) { return (p && p->pll_ready) ? p->pll.total : DVBS2FEC_EINVAL; }
+
+int dvbs2fec_pll_process_device(dvbs2fec_plsync* p, int nframes, int frame_stride, const float* d_frames, float* d_out, float* d_state,
+                                void* stream) {
+    if (!p || !p->pll_ready) return api_fail(DVBS2FEC_EINVAL, "dvbs2fec_pll_set_params has not been called");
+    if (nframes < 0 || frame_stride < p->pll.total || (nframes && (!d_frames || !d_out))) return api_fail(DVBS2FEC_EINVAL, "bad arguments");
+    CU(cudaSetDevice(p->device));
+    PllArgs a = p->pll;
+    a.frames = reinterpret_cast<const float2*>(d_frames);
+    a.out = reinterpret_cast<float2*>(d_out);
+    a.nframes = nframes;
+    a.rfs = frame_stride;
+    a.state_out = d_state;
+    int e = pll_launch(a, p->pll_sequential, (cudaStream_t)stream);
+    if (e) return api_fail(DVBS2FEC_ECUDA, cudaGetErrorString((cudaError_t)e));
+    return 0;
+}
+
+int dvbs2fec_pll_process(dvbs2fec_plsync* p, int nframes, int frame_stride, const float* frames, float* out, float* state) {
+    if (!p || !p->pll_ready) return api_fail(DVBS2FEC_EINVAL, "dvbs2fec_pll_set_params has not been called");
+    if (nframes < 0 || frame_stride < p->pll.total || (nframes && (!frames || !out))) return api_fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (!nframes) return 0;
+    CU(cudaSetDevice(p->device));
+    const size_t n = (size_t)nframes * frame_stride;
+    CU(p->pll_in.reserve(n));
+    CU(p->pll_out.reserve(n));
+    CU(p->pll_state.reserve((size_t)3 * nframes));
+    CU(cudaMemcpyAsync(p->pll_in.p, frames, n * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+    // (symbols behind the ones process() handles are not touched by the reference either: hand back the caller's own)
+    CU(cudaMemcpyAsync(p->pll_out.p, out, n * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+    int rc = dvbs2fec_pll_process_device(p, nframes, frame_stride, reinterpret_cast<const float*>(p->pll_in.p),
+                                         reinterpret_cast<float*>(p->pll_out.p), p->pll_state.p, p->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, p->pll_out.p, n * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
+    if (state) CU(cudaMemcpyAsync(state, p->pll_state.p, (size_t)3 * nframes * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return nframes;
+}
+
+int dvbs2fec_pll_process_multi_device(int nstreams, dvbs2fec_plsync* const* objs, int nframes, int frame_stride,
+                                      const float* const* d_frames, float* const* d_out, void* stream) {
+    if (nstreams < 1 || nstreams > 4096 || !objs || !d_frames || !d_out || nframes < 0) return api_fail(DVBS2FEC_EINVAL, "bad arguments");
+    std::vector<PllArgs> jobs((size_t)nstreams);
+    for (int k = 0; k < nstreams; ++k) {
+        dvbs2fec_plsync* p = objs[k];
+        if (!p || !p->pll_ready || p->device != objs[0]->device || frame_stride < p->pll.total || !d_frames[k] || !d_out[k])
+            return api_fail(DVBS2FEC_EINVAL, "stream not configured, on another device, or stride shorter than its frame");
+        PllArgs a = p->pll;
+        a.frames = reinterpret_cast<const float2*>(d_frames[k]);
+        a.out = reinterpret_cast<float2*>(d_out[k]);
+        a.nframes = nframes;
+        a.rfs = frame_stride;
+        a.state_out = nullptr;
+        jobs[(size_t)k] = a;
+    }
+    if (!nframes) return 0;
+    dvbs2fec_plsync* p0 = objs[0];
+    CU(cudaSetDevice(p0->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // the job records travel through the first object's scratch (stream-ordered: the copy is enqueued before the kernel)
+    CU(cudaStreamSynchronize(st));   // a previous multi call on this stream may still read the scratch
+    CU(p0->pll_jobs.reserve((size_t)nstreams * sizeof(PllArgs)));
+    CU(cudaMemcpyAsync(p0->pll_jobs.p, jobs.data(), jobs.size() * sizeof(PllArgs), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // `jobs` is pageable host memory
+    int e = pll_launch_multi(reinterpret_cast<const PllArgs*>(p0->pll_jobs.p), nstreams, st);
+    if (e) return api_fail(DVBS2FEC_ECUDA, cudaGetErrorString((cudaError_t)e));
+    return 0;
+}
+
+int dvbs2fec_pll_rounds(dvbs2fec_plsync* p) {
+    if (!p) return api_fail(DVBS2FEC_EINVAL, "handle is NULL");
+    CU(cudaSetDevice(p->device));
+    PllState s{};
+    CU(cudaMemcpy(&s, p->pst.p, sizeof s, cudaMemcpyDeviceToHost));
+    return (int)s.rounds;
 }
 
 }  // extern "C"

@@ -61,4 +61,31 @@ int plhdr_launch(const float2* frames, int nframes, int rfs, float2* headers_out
 int fed_launch(const float2* frames, int nframes, int rfs, int pilots, int pls_code, const uint8_t* rn, const PlTables* tab,
                float* err_out, cudaStream_t stream);
 
+// K8 (pl_pll.cu): S2PLLBlock::process for consecutive frames of one stream, one warp, speculative in blocks of 32 symbols
+struct PllState {
+    float alpha, beta, phase, freq, error;   // loop coefficients, pcl.phase, pcl.freq, S2PLLBlock::error
+    unsigned rounds;                          // evaluation rounds of the last call (diagnostic: 2 per 32 symbols is the floor)
+};
+struct PllArgs {
+    const float2* frames;   // nframes frames at stride rfs
+    float2* out;            // same stride; the first `total` symbols of each are written
+    int nframes, rfs;
+    int total;              // (frame_slot_count + 1) * 90 + pilot_cnt * 36 (dvbs2_pll.cpp:38)
+    int pilot_cnt;          // S2PLLBlock::update (dvbs2_pll.h:47-59)
+    float divisor;          // (float)(frame_slot_count + 1) * 90 + pilot_cnt * 36 (:82)
+    int pls_code;
+    const uint8_t* rn;      // PL scrambling sequence
+    const float* perr_lut;  // 256 x 256 phase errors of the demapper's cells, null for 32APSK
+    const PlTables* tab;
+    PllState* st;
+    float* state_out;       // optional: phase, freq, error after every frame
+    float amp, prescale;    // 32APSK only: demapper scale and points
+    int states;
+    float pts[64];
+};
+// sequential: one thread, one symbol at a time (the yardstick the tests hold the speculative kernel against)
+int pll_launch(const PllArgs& a, bool sequential, cudaStream_t stream);
+// njobs independent streams, one warp each; d_jobs in device memory
+int pll_launch_multi(const PllArgs* d_jobs, int njobs, cudaStream_t stream);
+
 }  // namespace s2

@@ -1,0 +1,170 @@
+"""Row 8(f)-2 on the GPU: dvbs2fec_pll_* (S2PLLBlock, the payload phase loop) against the CPU oracle, which
+tests/test_pll_oracle.py pins bit for bit to the reference's own dvbs2_pll.cpp.
+
+Tolerance (floating point stage): the device evaluates sinf / cosf / atan2f with CUDA's libm instead of glibc's; every
+other operation is the reference's own, in the reference's order.  An ulp in a sine moves an output symbol by an ulp and
+-- through the loop -- every later symbol by about as much; a symbol that lands within an ulp of a table-cell border may
+pick the neighbouring cell's error (the cells of one decision region differ by a few 1e-3 rad, times alpha < 0.02).
+A flipped cell inside a decision region changes one error by a few 1e-3 rad and, through alpha (0.0056 here), the
+phase of the following symbols by a few 1e-5 rad.  Nothing pulls such a difference back deterministically: the detector is
+a table, so two loops a few 1e-5 rad apart read the same cells almost always and stay apart until further flips walk them
+together again; and a symbol that noise has put next to a DECISION boundary flips the error by up to pi/2 (a kick of
+alpha pi/2 = 9e-3 rad, about once in several hundred thousand symbols at 8 dB).  Two free-running loops are therefore equal
+only statistically, whatever the arithmetic; what can be pinned is
+  (1) the kernel against the same arithmetic walked sequentially on the device: bit for bit
+      (test_speculative_kernel_equals_the_sequential_walk);
+  (2) one frame from the oracle's own loop state: the first 64 symbols (no flip yet) within 5e-6, the median deviation of
+      the frame within 1e-4, at most 2 % of its symbols further than 1e-3 off, loop phase within 2e-2 rad, loop frequency
+      and mean error within 1e-4 (test_pll_matches_oracle);
+  (3) the chain: symbols through the device loop and the device demapper decode (test_pll_feeds_the_demapper)."""
+import numpy as np
+import pytest
+
+import orclib
+import plstream
+from fec import pkg
+from test_pll_oracle import CONST, OrcPll, frames_for
+
+pytestmark = pytest.mark.gpu
+
+TOL_SYM = 1e-3
+MEDIAN_SYM = 1e-4
+
+MODCOD = {"qpsk": 4, "8psk": 12, "16apsk": 18, "32apsk": 28}   # 1/2, 3/5, 2/3 (gamma 3.15), 9/10 (gamma 2.53 / 4.30)
+SLOTS = {("qpsk", False): 360, ("8psk", False): 240, ("16apsk", False): 180, ("32apsk", False): 144,
+         ("qpsk", True): 90, ("8psk", True): 60, ("16apsk", True): 45, ("32apsk", True): 36}
+
+
+@pytest.mark.parametrize("case", [("qpsk", True, False, 8.0, 3e-5, 0, 0), ("qpsk", True, True, 5.0, -2e-5, 1, 1),
+                                  ("8psk", True, False, 12.0, 1e-5, 0, 2), ("16apsk", True, True, 16.0, 2e-5, 7, 3),
+                                  ("32apsk", True, False, 20.0, 1e-5, 0, 4), ("qpsk", False, True, 3.0, 4e-5, 0, 5),
+                                  ("8psk", False, False, 9.0, -3e-5, 3, 6)])
+def test_pll_matches_oracle(case):
+    """every frame starts from the oracle's loop state (dvbs2fec_pll_set_state), so the comparison measures what one
+    frame of device arithmetic does, not how two free-running decision-directed loops drift apart"""
+    name, short, pilots, esn0, cfo, codenum, seed = case
+    slots, modcod = SLOTS[(name, short)], MODCOD[name]
+    rng = np.random.default_rng(200 + seed)
+    nframes = 4
+    pls, fr = frames_for(name, slots, pilots, nframes, rng, esn0, cfo, codenum, modcod=modcod, short=short)
+    o = OrcPll(0.004, name, slots, pilots, pls, codenum)
+    g = pkg.S2PLSyncBlock(slots, pilots)
+    g.pll_set_params(0.004, modcod, short, pilots, codenum)
+    assert g.pll_frame_symbols == o.total
+    ws = np.zeros(3, np.float32)
+    rounds = 0
+    for f in range(nframes):
+        g.pll_set_state(float(ws[0]), float(ws[1]))
+        got, st = g.pll_process(fr[f:f + 1])
+        rounds += g.pll_rounds()
+        want, ws = o.process(fr[f])
+        dev = np.abs(got[0, :o.total] - want)
+        head = dev[:64].max()                                     # before any cell can have flipped: float rounding only
+        assert head < 5e-6, (f, head)
+        assert np.median(dev) < MEDIAN_SYM and np.mean(dev > TOL_SYM) < 0.02, (f, np.median(dev), dev.max(), np.mean(dev > TOL_SYM))
+        assert np.all(got[0, o.total:] == 0)                      # symbols behind the ones process() handles: untouched
+        dphi = abs((st[0, 0] - ws[0] + np.pi) % (2 * np.pi) - np.pi)
+        assert dphi < 2e-2 and abs(st[0, 1] - ws[1]) < 1e-4 and abs(st[0, 2] - ws[2]) < 1e-4, (f, st[0], ws)
+    # the speculation settles fast: within sight of the two rounds per 32 symbols that are the minimum
+    blocks = nframes * ((o.total + 31) // 32)
+    assert rounds <= (8 if name == "32apsk" else 5.5) * blocks, (rounds, blocks)
+    g.close()
+
+
+@pytest.mark.parametrize("case", [("qpsk", True, False, 8.0, 3e-5, 0), ("qpsk", True, True, 1.0, -2e-5, 1), ("8psk", False, False, 6.0, 4e-3, 2),
+                                  ("16apsk", True, True, 16.0, 6e-3, 3), ("32apsk", True, False, 14.0, -1e-3, 4),
+                                  ("qpsk", False, True, -1.0, 2e-2, 5)])
+def test_speculative_kernel_equals_the_sequential_walk(case):
+    """the 32-symbols-at-a-time kernel against one device thread walking the loop symbol by symbol with the same device
+    functions: the same bits -- in lock, out of lock (noise, cycle slips), with the phase wrapping every few hundred
+    symbols and the frequency riding on its clamp (carrier offsets beyond 0.01 pi per symbol)"""
+    name, short, pilots, esn0, cfo, seed = case
+    slots, modcod = SLOTS[(name, short)], MODCOD[name]
+    rng = np.random.default_rng(300 + seed)
+    pls, fr = frames_for(name, slots, pilots, 3, rng, esn0, cfo, seed, modcod=modcod, short=short)
+    res = []
+    for seq in (1, 0):
+        g = pkg.S2PLSyncBlock(slots, pilots)
+        g.pll_set_params(0.01, modcod, short, pilots, seed)
+        g.pll_set_sequential(seq)
+        a, sa = g.pll_process(fr[:2])
+        b, sb = g.pll_process(fr[2:])
+        res.append((np.concatenate([a, b]), np.concatenate([sa, sb])))
+        g.close()
+    assert np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32))
+    assert np.array_equal(res[0][1].view(np.uint32), res[1][1].view(np.uint32))
+
+
+def test_pll_reset_and_reconfiguration():
+    rng = np.random.default_rng(77)
+    pls, fr = frames_for("qpsk", 90, False, 2, rng, 10.0, 2e-5, 0, short=True)
+    g = pkg.S2PLSyncBlock(90, False)
+    g.pll_set_params(0.004, 4, True, False, 0)
+    a, sa = g.pll_process(fr[:1])
+    g.pll_reset()                                   # S2PLLBlock::reset: phase and frequency back to zero
+    b, sb = g.pll_process(fr[:1])
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(sa.view(np.uint32), sb.view(np.uint32))
+    c, sc = g.pll_process(fr[1:])                   # continues from the state after frame 0
+    o = OrcPll(0.004, "qpsk", 90, False, pls, 0)
+    o.process(fr[0])
+    want, ws = o.process(fr[1])
+    assert np.median(np.abs(c[0, :o.total] - want)) < MEDIAN_SYM
+    with pytest.raises(pkg.DVBS2FecError):
+        g.pll_set_params(0.004, 29, True, False, 0)
+    with pytest.raises(pkg.DVBS2FecError):
+        g.pll_process(fr[:1, :100], frame_stride=100)   # stride shorter than a frame
+    g.close()
+
+
+def test_pll_feeds_the_demapper():
+    """PL sync -> phase loop -> demapper, all three on the device objects: the LLRs decode (QPSK 1/2 short, 9 dB,
+    14 dB, carrier offset and Gold code 3; on the reference demapper's hot QPSK LLRs the LDPC stage rarely reports
+    convergence below 10 dB -- SURVEY.md note N7 -- so the check is on the BBFRAME bytes)"""
+    rng = np.random.default_rng(31)
+    dec = pkg.DVBS2Decoder(max_batch=16)
+    dec.setDemodParams(4, True, False, 25)
+    n = 4
+    pay = rng.integers(0, 256, (n, dec.kbch // 8), dtype=np.uint8)
+    pls = 4 << 2 | 2
+    rn = plstream.pl_rn(3)
+    frames = []
+    for i in range(n):
+        sym = pkg.modulate(4, True, False, pkg.encode_fecframe(4, True, pay[i])).view(np.complex64)
+        pl = sym[90:] * np.array([1, 1j, -1, -1j])[rn[:len(sym) - 90]]
+        frames.append(np.concatenate([plstream.plheader(pls), pl]))
+    x = np.concatenate(frames).astype(np.complex64)
+    k = np.arange(len(x))
+    x = x * np.exp(1j * (0.4 + 2 * np.pi * 1.5e-5 * k))
+    sigma = 0.667 * np.sqrt(0.5 / 10 ** 1.4)     # Es/N0 14 dB (the mapper's symbols have amplitude 2/3)
+    x = (x + sigma * (rng.normal(size=len(x)) + 1j * rng.normal(size=len(x)))).astype(np.complex64)
+    g = pkg.S2PLSyncBlock(90, False)
+    g.pll_set_params(0.004, 4, True, False, 3)
+    out, st = g.pll_process(x.reshape(n, -1))
+    bb, res = dec.decode_plframes(out.view(np.float32).reshape(n, -1))
+    assert np.array_equal(bb[1:], pay[1:]) and (res["bch_corr"][1:] >= 0).all()   # (frame 0: the loop is still pulling in)
+    g.close()
+    dec.close()
+
+
+def test_pll_multi_stream_equals_single_stream_calls():
+    import torch
+    rng = np.random.default_rng(55)
+    blocks, ins, outs, want = [], [], [], []
+    for k, (name, modcod, slots, esn0) in enumerate((("qpsk", 4, 90, 8.0), ("8psk", 12, 60, 12.0), ("qpsk", 4, 90, 10.0))):
+        pls, fr = frames_for(name, slots, False, 3, rng, esn0, 1e-5 * (k + 1), k, modcod=modcod, short=True)
+        fr = np.pad(fr, ((0, 0), (0, 8190 - fr.shape[1])))          # common stride: the longest frame
+        g = pkg.S2PLSyncBlock(slots, False)
+        g.pll_set_params(0.004, modcod, True, False, k)
+        w, _ = g.pll_process(fr, frame_stride=8190)
+        g.pll_reset()
+        blocks.append(g)
+        want.append(w)
+        ins.append(torch.from_numpy(fr.view(np.float32).copy()).cuda())
+        outs.append(torch.zeros_like(ins[-1]))
+    pkg.pll_process_multi_device(blocks, [t.data_ptr() for t in ins], 3, 8190, [t.data_ptr() for t in outs],
+                                 torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for g, w, o in zip(blocks, want, outs):
+        got = o.cpu().numpy().view(np.complex64).reshape(3, 8190)
+        assert np.array_equal(got.view(np.uint32), w.view(np.uint32))   # same kernel body, same arithmetic: bit for bit
+        g.close()

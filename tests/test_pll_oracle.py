@@ -14,10 +14,10 @@ needs_ref = pytest.mark.skipif(not orclib.have_ref() or not hasattr(orclib.ref()
 CONST = {"qpsk": (1, 2, 0.0, 0.0), "8psk": (3, 3, 0.0, 0.0), "16apsk": (4, 4, 3.15, 0.0), "32apsk": (5, 5, 2.53, 4.30)}
 
 
-def frames_for(name, slots, pilots, nframes, rng, esn0_db, cfo, codenum, modcod=4):
+def frames_for(name, slots, pilots, nframes, rng, esn0_db, cfo, codenum, modcod=4, short=False):
     """nframes aligned PLFRAMEs (as S2PLSyncBlock delivers them) with a residual carrier offset and noise"""
     ctype, bits, g1, g2 = CONST[name]
-    pls = (modcod << 2) | int(pilots)
+    pls = (modcod << 2) | int(short) << 1 | int(pilots)
     rfs = orclib.oracle().orc_raw_frame_size(slots, int(pilots))
     x = plstream.stream(pls, slots, pilots, nframes, rng, esn0_db=esn0_db, lead=0, cfo=cfo, phase=0.2, codenum=codenum,
                         bits=min(bits, 3))
