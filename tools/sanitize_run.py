@@ -108,6 +108,19 @@ fr = np.concatenate(frames).reshape(-1, ps.raw_frame_size)
 hdr, res, loop = ps.plhdr_process(fr)
 err = ps.coarse_fed(fr, True, (4 << 2) | 1, 3)
 print("plsync frames", len(fr), res[:, 0].tolist(), [round(float(e), 4) for e in err])
+# payload phase loop on the delivered frames (pilots on: table cells and the pilot stretches), and a 32APSK stream
+ps.close()
+x = plstream.stream((4 << 2) | 3, 90, True, 2, np.random.default_rng(11), esn0_db=6.0, lead=0, cfo=2e-5, codenum=3)
+ps = pkg.S2PLSyncBlock(90, True)
+ps.pll_set_params(0.004, 4, True, True, 3)
+po, pst = ps.pll_process(x.reshape(2, -1))
+print("pll", po.shape, [round(float(v), 4) for v in pst[-1]], ps.pll_rounds())
+ps.close()
+x = plstream.stream(28 << 2, 36, False, 2, np.random.default_rng(10), esn0_db=18.0, lead=0, cfo=1e-5, bits=3)
+ps = pkg.S2PLSyncBlock(36, False)
+ps.pll_set_params(0.004, 28, True, False, 0)
+po, pst = ps.pll_process(x.reshape(2, -1))
+print("pll 32apsk", po.shape, ps.pll_rounds())
 ps.close()
 # quantised symbols path and zero-copy submit
 dec = pkg.DVBS2Decoder(max_batch=4, max_latency_us=300, max_trials=6)
