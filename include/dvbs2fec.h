@@ -274,6 +274,30 @@ int dvbs2fec_pll_process_multi_device(int nstreams, dvbs2fec_plsync* const* objs
 /* diagnostic: evaluation rounds the last call needed (two per block of 32 symbols is the minimum) */
 int dvbs2fec_pll_rounds(dvbs2fec_plsync* p);
 
+/* ---- DVB-S legacy chain, the byte-domain half: the body of the frame loop of
+ *      DVBSDemod::process (dvbs/module_dvbs_demod.cpp:91-106) -- convolutional deinterleaver
+ *      (DVBSInterleaving::deinterleave, dvbs/dvbs_interleaving.h:57-70), eight RS(204,188) decodes (DVBSReedSolomon::decode,
+ *      dvbs/dvbs_reedsolomon.h:27-47, over the vendored libcorrect), energy-dispersal descrambler
+ *      (DVBSScrambling::descramble, dvbs/dvbs_scrambling.h:30-43), 8 x 188 bytes out -- for a batch of frames.
+ *      One object holds what the three reference objects hold between frames (FIFO contents, the decoder's output
+ *      buffer, the descrambler register); it lives on the device.  Bit-identical to the reference, its observable
+ *      quirks included: a packet libcorrect gives up on comes out as the previous decoded packet, and errors[] is what
+ *      DVBSReedSolomon::decode returns (bytes in which the received message differs from what comes out; never -1). ---- */
+typedef struct dvbs2fec_dvbs_outer dvbs2fec_dvbs_outer;
+int dvbs2fec_dvbs_outer_create(int device, dvbs2fec_dvbs_outer** out);
+void dvbs2fec_dvbs_outer_destroy(dvbs2fec_dvbs_outer* p);
+/* back to the state of freshly constructed objects */
+int dvbs2fec_dvbs_outer_reset(dvbs2fec_dvbs_outer* p);
+/* nframes frames of 8 x 204 bytes as the TS deframer delivers them; frame k starts at frames + k * frame_stride
+ * (1632 for back-to-back frames; the reference module itself steps by 204, module_dvbs_demod.cpp:91 -- give it that
+ * to reproduce it), so frames must hold (nframes - 1) * frame_stride + 1632 bytes.  out: nframes * 8 * 188 bytes of TS
+ * packets; errors (optional): nframes * 8 ints.  Returns the bytes written.  Host buffers, synchronous. */
+int dvbs2fec_dvbs_outer_process(dvbs2fec_dvbs_outer* p, int nframes, int frame_stride, const uint8_t* frames, uint8_t* out,
+                                int32_t* errors);
+/* same on device buffers, asynchronous on `stream` */
+int dvbs2fec_dvbs_outer_process_device(dvbs2fec_dvbs_outer* p, int nframes, int frame_stride, const uint8_t* d_frames,
+                                       uint8_t* d_out, int32_t* d_errors, void* stream);
+
 /* ---- in-tree transmitter for synthetic input (not part of the reference's decode path) ---- */
 /* bbframe: kbch/8 bytes -> code_bits: N bytes of 0/1 (BB scramble, BCH, LDPC; EN 302 307 5.2-5.3) */
 int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits);

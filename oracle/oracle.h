@@ -113,6 +113,18 @@ int orc_pll_pilot_cnt(const orc_pll* p);
  * state = {pcl.phase, pcl.freq, error} after the call */
 int orc_pll_process(orc_pll* p, const float* in, float* out, float* state);
 
+/* ---- row 8(f)-4, byte-domain half (oracle_dvbs.c): the frame loop body of DVBSDemod::process
+ *      (dvbs/module_dvbs_demod.cpp:91-106): deinterleave, 8 x RS(204,188), descramble, 8 x 188 bytes out ---- */
+typedef struct orc_dvbs_outer orc_dvbs_outer;
+orc_dvbs_outer* orc_dvbs_outer_create(void);
+void orc_dvbs_outer_destroy(orc_dvbs_outer* p);
+/* one frame of 1632 bytes in, 1504 bytes and the eight DVBSReedSolomon::decode return values out */
+void orc_dvbs_outer_frame(orc_dvbs_outer* p, const uint8_t* frame, uint8_t* out, int* errors);
+/* nframes frames, frame k at frames + k * stride */
+void orc_dvbs_outer_process(orc_dvbs_outer* p, const uint8_t* frames, int nframes, int stride, uint8_t* out, int* errors);
+/* transmit side for the tests: RS(204,188) parity of one packet */
+void orc_rs204_parity(const uint8_t* msg188, uint8_t* parity16);
+
 #ifdef __cplusplus
 }
 #endif

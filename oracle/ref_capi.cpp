@@ -29,6 +29,10 @@
 #include "dvbs2/dvbs2_pll.h"          // row 8(f)-2: the payload phase loop (its pcl is private too)
 #undef private
 #include "dvbs2/dvbs2_fed.h"
+// row 8(f)-4, byte-domain half: the DVB-S outer decoder (header-only classes + the vendored libcorrect)
+#include "dvbs/dvbs_interleaving.h"
+#include "dvbs/dvbs_reedsolomon.h"
+#include "dvbs/dvbs_scrambling.h"
 
 using namespace dsp::dvbs2;
 
@@ -358,5 +362,36 @@ int ref_pll_process(void* h, int count, const float* in, float* out, float* stat
     return n;
 }
 int ref_pll_pilot_cnt(void* h) { return static_cast<RefPll*>(h)->blk.pilot_cnt; }
+
+// ---- DVB-S outer decoder: the objects and the frame loop body of DVBSDemod::process (dvbs/module_dvbs_demod.cpp:91-106) ----
+struct RefDvbsOuter {
+    dsp::dvbs::DVBSInterleaving dvb_interleaving;
+    dsp::dvbs::DVBSReedSolomon reed_solomon;
+    dsp::dvbs::DVBSScrambling scrambler;
+    uint8_t tmp_deinterleaved_frame[204 * 8];
+};
+void* ref_dvbs_outer_create() { return new RefDvbsOuter(); }
+void ref_dvbs_outer_process(void* h, const uint8_t* frames, int nframes, int stride, uint8_t* out, int* errors) {
+    auto* r = static_cast<RefDvbsOuter*>(h);
+    int outidx = 0;
+    for (int k = 0; k < nframes; k++) {
+        uint8_t* current_frame = const_cast<uint8_t*>(&frames[(size_t)k * stride]);
+        r->dvb_interleaving.deinterleave(current_frame, r->tmp_deinterleaved_frame);
+        for (int i = 0; i < 8; i++) errors[8 * k + i] = r->reed_solomon.decode(&r->tmp_deinterleaved_frame[204 * i]);
+        r->scrambler.descramble(r->tmp_deinterleaved_frame);
+        for (int i = 0; i < 8; i++) {
+            memcpy(&out[outidx], &r->tmp_deinterleaved_frame[204 * i], 188);
+            outidx += 188;
+        }
+    }
+}
+// correct_reed_solomon_encode through the same 255-byte layout the decoder wrapper uses: parity of one 188-byte packet
+void ref_rs204_parity(const uint8_t* msg188, uint8_t* parity16) {
+    static correct_reed_solomon* rs = correct_reed_solomon_create(correct_rs_primitive_polynomial_8_4_3_2_0, 0, 1, 16);
+    uint8_t in[239] = {0}, enc[255];
+    memcpy(in + 51, msg188, 188);
+    correct_reed_solomon_encode(rs, in, 239, enc);
+    memcpy(parity16, enc + 239, 16);
+}
 
 } // extern "C"

@@ -137,6 +137,12 @@ def lib():
     L.dvbs2fec_pll_process.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.dvbs2fec_pll_process_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
     L.dvbs2fec_pll_rounds.argtypes = [vp]
+    L.dvbs2fec_dvbs_outer_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.dvbs2fec_dvbs_outer_destroy.argtypes = [vp]
+    L.dvbs2fec_dvbs_outer_destroy.restype = None
+    L.dvbs2fec_dvbs_outer_reset.argtypes = [vp]
+    L.dvbs2fec_dvbs_outer_process.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.dvbs2fec_dvbs_outer_process_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
     L.dvbs2fec_pll_set_state.argtypes = [vp, C.c_float, C.c_float]
     L.dvbs2fec_pll_set_sequential.argtypes = [vp, C.c_int]
     L.dvbs2fec_pll_process_multi_device.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]
@@ -563,3 +569,39 @@ def pll_process_multi_device(blocks, d_frames_ptrs, nframes, frame_stride, d_out
     fin = (C.c_void_p * n)(*d_frames_ptrs)
     fout = (C.c_void_p * n)(*d_out_ptrs)
     _check(lib().dvbs2fec_pll_process_multi_device(n, objs, nframes, frame_stride, fin, fout, stream_ptr))
+
+
+class DVBSOuterDecoder:
+    """The frame loop body of DVBSDemod::process (dvbs/module_dvbs_demod.cpp:91-106) on the device: DVBSInterleaving
+    .deinterleave, 8 x DVBSReedSolomon.decode, DVBSScrambling.descramble, 8 x 188 bytes out, for a batch of frames."""
+
+    def __init__(self, device=0):
+        self._p = C.c_void_p()
+        _check(lib().dvbs2fec_dvbs_outer_create(device, C.byref(self._p)))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().dvbs2fec_dvbs_outer_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(lib().dvbs2fec_dvbs_outer_reset(self._p))
+
+    def process(self, frames, nframes, frame_stride=1632):
+        """-> (TS packets [nframes * 8][188], errors [nframes * 8])"""
+        x = np.ascontiguousarray(frames, np.uint8).reshape(-1)
+        if nframes and len(x) < (nframes - 1) * frame_stride + 1632:
+            raise ValueError("input shorter than (nframes - 1) * frame_stride + 1632 bytes")
+        out = np.zeros((nframes * 8, 188), np.uint8)
+        err = np.zeros(nframes * 8, np.int32)
+        _check(lib().dvbs2fec_dvbs_outer_process(self._p, nframes, frame_stride, _ptr(x), _ptr(out), _ptr(err)))
+        return out, err
+
+    def process_device(self, d_frames_ptr, nframes, frame_stride, d_out_ptr, d_errors_ptr=0, stream_ptr=0):
+        _check(lib().dvbs2fec_dvbs_outer_process_device(self._p, nframes, frame_stride, d_frames_ptr, d_out_ptr, d_errors_ptr, stream_ptr))

@@ -101,6 +101,12 @@ def oracle():
         lib.orc_pll_destroy.argtypes = [C.c_void_p]
         lib.orc_pll_pilot_cnt.argtypes = [C.c_void_p]
         lib.orc_pll_process.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
+        lib.orc_dvbs_outer_create.restype = C.c_void_p
+        lib.orc_dvbs_outer_destroy.argtypes = [C.c_void_p]
+        lib.orc_dvbs_outer_process.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, _u8p, _i32p]
+        lib.orc_dvbs_outer_process.restype = None
+        lib.orc_rs204_parity.argtypes = [_u8p, _u8p]
+        lib.orc_rs204_parity.restype = None
         _oracle = lib
     return _oracle
 
@@ -149,6 +155,12 @@ def ref():
             lib.ref_pll_create.restype = C.c_void_p
             lib.ref_pll_process.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p]
             lib.ref_pll_pilot_cnt.argtypes = [C.c_void_p]
+        if hasattr(lib, "ref_dvbs_outer_create"):
+            lib.ref_dvbs_outer_create.restype = C.c_void_p
+            lib.ref_dvbs_outer_process.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_int, _u8p, _i32p]
+            lib.ref_dvbs_outer_process.restype = None
+            lib.ref_rs204_parity.argtypes = [_u8p, _u8p]
+            lib.ref_rs204_parity.restype = None
         if hasattr(lib, "ref_ts_create"):
             lib.ref_ts_create.argtypes = [C.c_int]
             lib.ref_ts_create.restype = C.c_void_p

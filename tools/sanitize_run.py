@@ -139,3 +139,13 @@ for i in range(5):
 dec.flush()
 print("zero-copy", len(dec.collect(8, timeout_us=2_000_000)[1]))
 dec.close()
+# DVB-S outer decoder: clean, correctable and hopeless packets, state over calls, the module's 204-byte frame stride
+import dvbs_stream  # noqa: E402
+ts_, ch = dvbs_stream.outer_stream(6, np.random.default_rng(12))
+bad = dvbs_stream.add_errors(ch, np.random.default_rng(13), per_packet=(0, 14))
+od = pkg.DVBSOuterDecoder()
+o1, e1 = od.process(bad, 2)
+o2, e2 = od.process(bad[2 * 1632:], 4)
+o3, e3 = od.process(bad, 9, 204)
+print("dvbs outer", o1.shape, o2.shape, o3.shape, int(e1.sum() + e2.sum()), int(e3.sum()))
+od.close()
