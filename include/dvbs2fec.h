@@ -298,6 +298,26 @@ int dvbs2fec_dvbs_outer_process(dvbs2fec_dvbs_outer* p, int nframes, int frame_s
 int dvbs2fec_dvbs_outer_process_device(dvbs2fec_dvbs_outer* p, int nframes, int frame_stride, const uint8_t* d_frames,
                                        uint8_t* d_out, int32_t* d_errors, void* stream);
 
+/* ---- K10: DVBS_TS_Deframer::work (dvbs/dvbs_ts_deframer.cpp:44-101, dvbs_ts_deframer.h:17-70; the module calls it
+ *      through DVBSDefra::process, dvbs/dvbs_defra.cpp:5-9).  Input: the Viterbi decoder's output, one bit per byte;
+ *      output: every window of 8 x 204 x 8 bits whose eight sync bytes differ from B8 47 47 47 47 47 47 47 in at most 8
+ *      bits, as a frame of 1632 bytes (inverted where the inverted pattern matched), in stream order.  The window persists
+ *      over calls (it starts from zeros; the reference's is allocated uninitialised).  Every window position is tested
+ *      at once on the device; bit-identical to the reference. ---- */
+typedef struct dvbs2fec_dvbs_deframer dvbs2fec_dvbs_deframer;
+int dvbs2fec_dvbs_deframer_create(int device, dvbs2fec_dvbs_deframer** out);
+void dvbs2fec_dvbs_deframer_destroy(dvbs2fec_dvbs_deframer* p);
+int dvbs2fec_dvbs_deframer_reset(dvbs2fec_dvbs_deframer* p);
+/* size bits (< 2^24) -> at most max_frames frames of 1632 bytes; returns the number of frames written (the reference
+ * writes all it finds: give max_frames >= the frames the call can hold to reproduce it).  Host buffers, synchronous. */
+int dvbs2fec_dvbs_deframer_work(dvbs2fec_dvbs_deframer* p, const uint8_t* bits, int size, uint8_t* frames, int max_frames);
+/* same on device buffers (d_frames 4-byte aligned), asynchronous on `stream`; the count goes to *d_nframes (optional) */
+int dvbs2fec_dvbs_deframer_work_device(dvbs2fec_dvbs_deframer* p, const uint8_t* d_bits, int size, uint8_t* d_frames,
+                                       int max_frames, int32_t* d_nframes, void* stream);
+/* the public members errors_nor / errors_inv (dvbs_ts_deframer.h:24-25) after the last call, the frames it found
+ * (before max_frames); returns the frames it wrote.  Synchronises the device. */
+int dvbs2fec_dvbs_deframer_stats(dvbs2fec_dvbs_deframer* p, int* errors_nor, int* errors_inv, int* found);
+
 /* ---- in-tree transmitter for synthetic input (not part of the reference's decode path) ---- */
 /* bbframe: kbch/8 bytes -> code_bits: N bytes of 0/1 (BB scramble, BCH, LDPC; EN 302 307 5.2-5.3) */
 int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits);

@@ -122,6 +122,13 @@ void orc_dvbs_outer_destroy(orc_dvbs_outer* p);
 void orc_dvbs_outer_frame(orc_dvbs_outer* p, const uint8_t* frame, uint8_t* out, int* errors);
 /* nframes frames, frame k at frames + k * stride */
 void orc_dvbs_outer_process(orc_dvbs_outer* p, const uint8_t* frames, int nframes, int stride, uint8_t* out, int* errors);
+/* DVBS_TS_Deframer::work (dvbs/dvbs_ts_deframer.cpp:44-101): unpacked bits (0/1 bytes; other values are ORed in as the
+ * reference's pack_8 does) -> frames of 1632 bytes; returns the frame count */
+typedef struct orc_dvbs_deframer orc_dvbs_deframer;
+orc_dvbs_deframer* orc_dvbs_deframer_create(void);
+void orc_dvbs_deframer_destroy(orc_dvbs_deframer* p);
+int orc_dvbs_deframer_work(orc_dvbs_deframer* p, const uint8_t* input, int size, uint8_t* output);
+void orc_dvbs_deframer_stats(const orc_dvbs_deframer* p, int* errors_nor, int* errors_inv);
 /* transmit side for the tests: RS(204,188) parity of one packet */
 void orc_rs204_parity(const uint8_t* msg188, uint8_t* parity16);
 

@@ -228,3 +228,56 @@ void orc_rs204_parity(const uint8_t* msg188, uint8_t* parity16)
     }
     for (int i = 0; i < 16; ++i) parity16[i] = rem[15 - i];
 }
+
+/* ---- DVBS_TS_Deframer::work (dvbs/dvbs_ts_deframer.cpp:44-101): a window of 8 x 204 x 8 bits slides over the unpacked
+ * bit stream (one bit per byte, as the Viterbi decoder delivers it); wherever its eight sync bytes differ from
+ * B8 47 47 47 47 47 47 47 in at most 8 bits the window goes out as a frame of 1632 bytes, wherever they differ from the
+ * inverted pattern in at most 8 bits it goes out inverted.  The reference shifts an array by memmove for every bit;
+ * here the last 13056 bits sit in a ring.  (The reference leaves its array uninitialised; the harness and this
+ * restatement start from zeros.) ---- */
+#define DEF_BITS 13056
+struct orc_dvbs_deframer {
+    uint8_t ring[DEF_BITS];
+    int pos;                 /* where the next bit goes = the oldest bit */
+    int errors_nor, errors_inv;
+};
+orc_dvbs_deframer* orc_dvbs_deframer_create(void) { return (orc_dvbs_deframer*)calloc(1, sizeof(orc_dvbs_deframer)); }
+void orc_dvbs_deframer_destroy(orc_dvbs_deframer* p) { free(p); }
+void orc_dvbs_deframer_stats(const orc_dvbs_deframer* p, int* errors_nor, int* errors_inv)
+{
+    *errors_nor = p->errors_nor;
+    *errors_inv = p->errors_inv;
+}
+int orc_dvbs_deframer_work(orc_dvbs_deframer* p, const uint8_t* input, int size, uint8_t* output)
+{
+    int frame_count = 0;
+    for (int ibit = 0; ibit < size; ++ibit) {
+        p->ring[p->pos] = input[ibit];
+        p->pos = (p->pos + 1) % DEF_BITS;          /* window bit i = ring[(pos + i) % DEF_BITS] */
+        int t_nor = 0, t_inv = 0;
+        for (int i = 0; i < 8; ++i) {
+            unsigned b = 0;
+            for (int k = 0; k < 8; ++k) b |= (unsigned)p->ring[(p->pos + 204 * 8 * i + k) % DEF_BITS] << (7 - k);   /* pack_8: plain ORs of shifted bytes */
+            b &= 0xFF;
+            t_nor += __builtin_popcount(b ^ (i == 0 ? 0xB8u : 0x47u));
+            t_inv += __builtin_popcount(b ^ (i == 0 ? 0x47u : 0xB8u));
+        }
+        if (t_nor <= 8) {
+            uint8_t* f = output + (size_t)frame_count * 1632;
+            memset(f, 0, 1632);
+            for (int i = 0; i < DEF_BITS; ++i) f[i / 8] = (uint8_t)(f[i / 8] << 1 | p->ring[(p->pos + i) % DEF_BITS]);
+            frame_count++;
+            p->errors_nor = t_nor;
+            p->errors_inv = 0;
+        }
+        if (t_inv <= 8) {
+            uint8_t* f = output + (size_t)frame_count * 1632;
+            memset(f, 0, 1632);
+            for (int i = 0; i < DEF_BITS; ++i) f[i / 8] = (uint8_t)(f[i / 8] << 1 | !p->ring[(p->pos + i) % DEF_BITS]);
+            frame_count++;
+            p->errors_nor = 0;
+            p->errors_inv = t_inv;
+        }
+    }
+    return frame_count;
+}

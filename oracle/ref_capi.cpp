@@ -33,6 +33,12 @@
 #include "dvbs/dvbs_interleaving.h"
 #include "dvbs/dvbs_reedsolomon.h"
 #include "dvbs/dvbs_scrambling.h"
+#pragma push_macro("TS_SIZE")
+#undef TS_SIZE             // (bbframe_ts_parser.h defines a macro of the name of a member of the deframer)
+#define private public   // the deframer's bit window is allocated uninitialised; the harness zeroes it
+#include "dvbs/dvbs_ts_deframer.h"
+#undef private
+#pragma pop_macro("TS_SIZE")
 
 using namespace dsp::dvbs2;
 
@@ -384,6 +390,20 @@ void ref_dvbs_outer_process(void* h, const uint8_t* frames, int nframes, int str
             outidx += 188;
         }
     }
+}
+// ---- DVBS_TS_Deframer (dvbs/dvbs_ts_deframer.h:17-70) ----
+void* ref_dvbs_deframer_create() {
+    auto* d = new deframing::DVBS_TS_Deframer();
+    memset(d->full_frame_shifter, 0, 1632 * 8);   // (new uint8_t[TS_SIZE] in the reference: indeterminate)
+    return d;
+}
+int ref_dvbs_deframer_work(void* h, const uint8_t* input, int size, uint8_t* output) {
+    return static_cast<deframing::DVBS_TS_Deframer*>(h)->work(const_cast<uint8_t*>(input), size, output);
+}
+void ref_dvbs_deframer_stats(void* h, int* errors_nor, int* errors_inv) {
+    auto* d = static_cast<deframing::DVBS_TS_Deframer*>(h);
+    *errors_nor = d->errors_nor;
+    *errors_inv = d->errors_inv;
 }
 // correct_reed_solomon_encode through the same 255-byte layout the decoder wrapper uses: parity of one 188-byte packet
 void ref_rs204_parity(const uint8_t* msg188, uint8_t* parity16) {

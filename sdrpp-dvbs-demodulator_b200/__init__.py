@@ -143,6 +143,13 @@ def lib():
     L.dvbs2fec_dvbs_outer_reset.argtypes = [vp]
     L.dvbs2fec_dvbs_outer_process.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     L.dvbs2fec_dvbs_outer_process_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.dvbs2fec_dvbs_deframer_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.dvbs2fec_dvbs_deframer_destroy.argtypes = [vp]
+    L.dvbs2fec_dvbs_deframer_destroy.restype = None
+    L.dvbs2fec_dvbs_deframer_reset.argtypes = [vp]
+    L.dvbs2fec_dvbs_deframer_work.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.dvbs2fec_dvbs_deframer_work_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]
+    L.dvbs2fec_dvbs_deframer_stats.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.dvbs2fec_pll_set_state.argtypes = [vp, C.c_float, C.c_float]
     L.dvbs2fec_pll_set_sequential.argtypes = [vp, C.c_int]
     L.dvbs2fec_pll_process_multi_device.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]
@@ -605,3 +612,44 @@ class DVBSOuterDecoder:
 
     def process_device(self, d_frames_ptr, nframes, frame_stride, d_out_ptr, d_errors_ptr=0, stream_ptr=0):
         _check(lib().dvbs2fec_dvbs_outer_process_device(self._p, nframes, frame_stride, d_frames_ptr, d_out_ptr, d_errors_ptr, stream_ptr))
+
+
+class DVBSTSDeframer:
+    """deframing::DVBS_TS_Deframer (dvbs/dvbs_ts_deframer.h:17-70) on the device: work() takes the Viterbi decoder's
+    unpacked bits and returns the frames of 8 x 204 bytes it finds; errors_nor / errors_inv as the reference's members."""
+
+    def __init__(self, device=0):
+        self._p = C.c_void_p()
+        _check(lib().dvbs2fec_dvbs_deframer_create(device, C.byref(self._p)))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().dvbs2fec_dvbs_deframer_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(lib().dvbs2fec_dvbs_deframer_reset(self._p))
+
+    def work(self, bits, max_frames=None):
+        """-> frames [n][1632]"""
+        x = np.ascontiguousarray(bits, np.uint8).reshape(-1)
+        if max_frames is None:
+            max_frames = len(x) // 64 + 2
+        out = np.zeros((max_frames, 1632), np.uint8)
+        n = _check(lib().dvbs2fec_dvbs_deframer_work(self._p, _ptr(x), len(x), _ptr(out), max_frames))
+        return out[:n].copy()
+
+    def work_device(self, d_bits_ptr, size, d_frames_ptr, max_frames, d_nframes_ptr=0, stream_ptr=0):
+        _check(lib().dvbs2fec_dvbs_deframer_work_device(self._p, d_bits_ptr, size, d_frames_ptr, max_frames, d_nframes_ptr, stream_ptr))
+
+    def stats(self):
+        """-> (errors_nor, errors_inv, frames found by the last call)"""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _check(lib().dvbs2fec_dvbs_deframer_stats(self._p, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value

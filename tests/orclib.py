@@ -107,6 +107,10 @@ def oracle():
         lib.orc_dvbs_outer_process.restype = None
         lib.orc_rs204_parity.argtypes = [_u8p, _u8p]
         lib.orc_rs204_parity.restype = None
+        lib.orc_dvbs_deframer_create.restype = C.c_void_p
+        lib.orc_dvbs_deframer_destroy.argtypes = [C.c_void_p]
+        lib.orc_dvbs_deframer_work.argtypes = [C.c_void_p, _u8p, C.c_int, _u8p]
+        lib.orc_dvbs_deframer_stats.argtypes = [C.c_void_p, ip, ip]
         _oracle = lib
     return _oracle
 
@@ -161,6 +165,10 @@ def ref():
             lib.ref_dvbs_outer_process.restype = None
             lib.ref_rs204_parity.argtypes = [_u8p, _u8p]
             lib.ref_rs204_parity.restype = None
+        if hasattr(lib, "ref_dvbs_deframer_create"):
+            lib.ref_dvbs_deframer_create.restype = C.c_void_p
+            lib.ref_dvbs_deframer_work.argtypes = [C.c_void_p, _u8p, C.c_int, _u8p]
+            lib.ref_dvbs_deframer_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         if hasattr(lib, "ref_ts_create"):
             lib.ref_ts_create.argtypes = [C.c_int]
             lib.ref_ts_create.restype = C.c_void_p

@@ -91,3 +91,69 @@ def test_outer_decoder_matches_reference(case):
         ob, eb = b.process(seg, hi - lo, stride)
         assert np.array_equal(ea, eb)
         assert np.array_equal(oa, ob)
+
+
+# ---- TS deframer ----------------------------------------------------------------------------------------------------
+class OrcDeframer:
+    def __init__(self):
+        self.o = orclib.oracle()
+        self.h = self.o.orc_dvbs_deframer_create()
+        self.work_fn, self.stats_fn = self.o.orc_dvbs_deframer_work, self.o.orc_dvbs_deframer_stats
+
+    def work(self, bits):
+        import ctypes as C
+        bits = np.ascontiguousarray(bits, np.uint8)
+        out = np.zeros((len(bits) // 100 + 4) * 1632, np.uint8)      # room for the frames a test stream can hold
+        n = self.work_fn(self.h, bits, len(bits), out)
+        a, b = C.c_int(), C.c_int()
+        self.stats_fn(self.h, C.byref(a), C.byref(b))
+        return out[:n * 1632].reshape(n, 1632).copy(), (a.value, b.value)
+
+
+class RefDeframer(OrcDeframer):
+    def __init__(self):
+        self.o = orclib.ref()
+        self.h = self.o.ref_dvbs_deframer_create()
+        self.work_fn, self.stats_fn = self.o.ref_dvbs_deframer_work, self.o.ref_dvbs_deframer_stats
+
+
+def deframer_bits(nframes, rng, lead=777, flip=0.0, invert=False):
+    """the unpacked bit stream behind the Viterbi decoder: junk, then frames of 8 x 204 bytes with their sync bytes"""
+    ts, ch = dvbs_stream.outer_stream(nframes, rng)
+    bits = np.unpackbits(ch)
+    bits = np.concatenate([rng.integers(0, 2, lead, dtype=np.uint8), bits, rng.integers(0, 2, 300, dtype=np.uint8)])
+    if flip:
+        bits ^= (rng.random(len(bits)) < flip).astype(np.uint8)
+    if invert:
+        bits ^= 1
+    return ch.reshape(nframes, 1632), bits
+
+
+def test_deframer_finds_the_frames():
+    rng = np.random.default_rng(4)
+    frames, bits = deframer_bits(3, rng)
+    got, st = OrcDeframer().work(bits)
+    assert len(got) == 3 and np.array_equal(got, frames) and st == (0, 0)
+    frames, bits = deframer_bits(2, rng, invert=True)
+    got, st = OrcDeframer().work(bits)
+    assert len(got) == 2 and np.array_equal(got, frames)
+
+
+needs_ref_def = pytest.mark.skipif(not orclib.have_ref() or not hasattr(orclib.ref(), "ref_dvbs_deframer_create"),
+                                   reason="oracle/_ref/libdvbs2_ref.so (with the TS deframer) not built")
+
+
+@needs_ref_def
+@pytest.mark.parametrize("case", [(0.0, False, 0), (0.02, False, 1), (0.02, True, 2), (0.5, False, 3)])
+def test_deframer_matches_reference(case):
+    """clean, 2 % bit errors (sync bytes with a few wrong bits still lock, some frames are missed), inverted stream, noise
+    only; the stream cut into calls at odd places (the window crosses calls)"""
+    flip, invert, seed = case
+    rng = np.random.default_rng(20 + seed)
+    frames, bits = deframer_bits(3, rng, lead=int(rng.integers(1, 2000)), flip=flip, invert=invert)
+    a, b = OrcDeframer(), RefDeframer()
+    cuts = sorted(set(int(c) for c in rng.integers(0, len(bits), 5)) | {0, len(bits)})
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        ga, sa = a.work(bits[lo:hi])
+        gb, sb = b.work(bits[lo:hi])
+        assert ga.shape == gb.shape and np.array_equal(ga, gb) and sa == sb

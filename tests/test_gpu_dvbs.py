@@ -63,3 +63,48 @@ def test_outer_decoder_argument_errors():
     with pytest.raises(pkg.DVBS2FecError):
         pkg.DVBSOuterDecoder(device=99)
     g.close()
+
+
+# ---- K10: TS deframer ------------------------------------------------------------------------------------------------
+from test_dvbs_oracle import OrcDeframer, deframer_bits
+
+
+@pytest.mark.parametrize("case", [(0.0, False, 0), (0.02, False, 1), (0.02, True, 2), (0.5, False, 3), (0.004, False, 4)])
+def test_deframer_matches_oracle(case):
+    """clean, bit errors (sync bytes with a few wrong bits still lock), inverted stream, noise only; the stream cut into
+    calls at odd places (the window crosses calls, down to calls of one bit)"""
+    flip, invert, seed = case
+    rng = np.random.default_rng(30 + seed)
+    frames, bits = deframer_bits(5, rng, lead=int(rng.integers(1, 3000)), flip=flip, invert=invert)
+    o, g = OrcDeframer(), pkg.DVBSTSDeframer()
+    cuts = sorted(set(int(c) for c in rng.integers(0, len(bits), 6)) | {0, 1, 2, len(bits)})
+    total = 0
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        want, ws = o.work(bits[lo:hi])
+        got = g.work(bits[lo:hi])
+        assert got.shape == want.shape and np.array_equal(got, want)
+        st = g.stats()
+        assert st[:2] == ws and st[2] == len(want)
+        total += len(got)
+    if flip == 0.0:
+        assert total == 5
+    g.reset()
+    want, _ = OrcDeframer().work(bits[:20000])
+    assert np.array_equal(g.work(bits[:20000]), want)
+    g.close()
+
+
+def test_deframer_large_call_and_frame_limit():
+    """300 frames (3.9 Mbit) in one call: all found, in order; max_frames bounds what is written, stats tell what was found"""
+    rng = np.random.default_rng(5)
+    frames, bits = deframer_bits(300, rng, lead=12345)
+    g = pkg.DVBSTSDeframer()
+    got = g.work(bits, max_frames=400)
+    assert np.array_equal(got, frames)
+    g.reset()
+    got = g.work(bits, max_frames=7)
+    assert np.array_equal(got, frames[:7]) and g.stats()[2] == 300
+    assert g.work(np.zeros(0, np.uint8)).shape == (0, 1632)
+    with pytest.raises(pkg.DVBS2FecError):
+        pkg.DVBSTSDeframer(device=99)
+    g.close()
