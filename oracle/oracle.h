@@ -129,6 +129,21 @@ orc_dvbs_deframer* orc_dvbs_deframer_create(void);
 void orc_dvbs_deframer_destroy(orc_dvbs_deframer* p);
 int orc_dvbs_deframer_work(orc_dvbs_deframer* p, const uint8_t* input, int size, uint8_t* output);
 void orc_dvbs_deframer_stats(const orc_dvbs_deframer* p, int* errors_nor, int* errors_inv);
+/* ---- inner half of the DVB-S chain (oracle_vit.c) ----
+ * Viterbi_DVBS as the module constructs it (module_dvbs_demod.cpp:23: phases 0 and 90 degrees, 8192 soft bits per call)
+ * behind DVBSVitBlock::process (dvbs_vit.cpp:6-13): count (a multiple of 8192) signed soft bits -> decoded bits, one per
+ * byte; returns how many.  out needs room for count bytes; bytes the reference does not write are not written. */
+typedef struct orc_vit orc_vit;
+orc_vit* orc_vit_create(float ber_threshold, int max_outsync);
+void orc_vit_destroy(orc_vit* v);
+int orc_vit_process(orc_vit* v, int count, const int8_t* in, uint8_t* out);
+/* ber(), getState(), rate() and the lock the decoder holds; rate 0..4 = 1/2, 2/3, 3/4, 5/6, 7/8 */
+void orc_vit_stats(const orc_vit* v, float* ber, int* state, int* rate, int* phase, int* shift, int* invalid);
+/* DVBSymToSoftBlock::process (dvbs_syms_to_soft.cpp:26-42): count symbols (re, im floats) -> soft bits in chunks of 8192 */
+typedef struct orc_sts orc_sts;
+orc_sts* orc_sts_create(void);
+void orc_sts_destroy(orc_sts* s);
+int orc_sts_process(orc_sts* s, int count, const float* syms, int8_t* out);
 /* transmit side for the tests: RS(204,188) parity of one packet */
 void orc_rs204_parity(const uint8_t* msg188, uint8_t* parity16);
 

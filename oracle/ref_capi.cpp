@@ -33,6 +33,14 @@
 #include "dvbs/dvbs_interleaving.h"
 #include "dvbs/dvbs_reedsolomon.h"
 #include "dvbs/dvbs_scrambling.h"
+// row 8(f)-4, inner half: soft symbols, the self-locking punctured Viterbi decoder
+#include <sstream>
+#include <string>
+#include <functional>
+#include "dvbs/dvbs_syms_to_soft.h"
+#define private public   // Viterbi_DVBS keeps its BER test buffers as uninitialised members that it reads before writing
+#include "dvbs/viterbi_all.h"
+#undef private
 #pragma push_macro("TS_SIZE")
 #undef TS_SIZE             // (bbframe_ts_parser.h defines a macro of the name of a member of the deframer)
 #define private public   // the deframer's bit window is allocated uninitialised; the harness zeroes it
@@ -404,6 +412,47 @@ void ref_dvbs_deframer_stats(void* h, int* errors_nor, int* errors_inv) {
     auto* d = static_cast<deframing::DVBS_TS_Deframer*>(h);
     *errors_nor = d->errors_nor;
     *errors_inv = d->errors_inv;
+}
+// ---- viterbi::Viterbi_DVBS (dvbs/viterbi_all.h:33-163) as the module constructs it (module_dvbs_demod.cpp:23: BER threshold
+// 0.15, 20 calls out of sync, VIT_BUF_SIZE = 8192 soft bits per call, phases 0 and 90 degrees) ----
+void* ref_vit_create(float ber_threshold, int max_outsync) {
+    auto* v = new viterbi::Viterbi_DVBS(ber_threshold, max_outsync, 8192, {PHASE_0, PHASE_90});
+    // members the search reads before anything has written them (viterbi_all.cpp:89,107,127,147,167: the decoders read
+    // past what the depuncturers wrote; get_ber reads one re-encoded bit rate 5/6 never writes): zeros here and in the oracle
+    memset(v->ber_test_buffer, 0, sizeof v->ber_test_buffer);
+    memset(v->ber_soft_buffer, 0, sizeof v->ber_soft_buffer);
+    memset(v->ber_depunc_buffer, 0, sizeof v->ber_depunc_buffer);
+    memset(v->ber_decoded_buffer, 0, sizeof v->ber_decoded_buffer);
+    memset(v->ber_encoded_buffer, 0, sizeof v->ber_encoded_buffer);
+    v->d_rate = viterbi::RATE_1_2; v->d_phase = PHASE_0; v->d_shift = 0; v->d_ber = 10;
+    return v;
+}
+void ref_vit_destroy(void* h) { delete static_cast<viterbi::Viterbi_DVBS*>(h); }
+// layout the restatement relies on: the 1/2 search decoder reads up to 13 bytes past ber_soft_buffer, into the member behind it
+int ref_vit_layout_ok(void* h) {
+    auto* v = static_cast<viterbi::Viterbi_DVBS*>(h);
+    return v->ber_soft_buffer + sizeof v->ber_soft_buffer == v->ber_depunc_buffer;
+}
+// DVBSVitBlock::process (dvbs/dvbs_vit.cpp:6-13): one work() per 8192 soft bits; input is rotated in place as the reference does
+int ref_vit_process(void* h, int count, int8_t* in, uint8_t* out) {
+    auto* v = static_cast<viterbi::Viterbi_DVBS*>(h);
+    int oidx = 0;
+    for (int i = 0; i < count; i += 8192) oidx += v->work(&in[i], 8192, &out[oidx]);
+    return oidx;
+}
+void ref_vit_stats(void* h, float* ber, int* state, int* rate, int* phase, int* shift, int* invalid) {
+    auto* v = static_cast<viterbi::Viterbi_DVBS*>(h);
+    *ber = v->ber(); *state = v->getState(); *rate = (int)v->d_rate; *phase = (int)v->d_phase; *shift = v->d_shift; *invalid = v->d_invalid;
+}
+// ---- DVBSymToSoftBlock::process (dvbs/dvbs_syms_to_soft.cpp:26-42) ----
+void* ref_sts_create() {
+    auto* s = new dsp::dvbs::DVBSymToSoftBlock();
+    s->init(nullptr, STREAM_BUFFER_SIZE);
+    s->syms_callback = [](dsp::complex_t*, int) {};
+    return s;
+}
+int ref_sts_process(void* h, int count, const float* syms, int8_t* out) {
+    return static_cast<dsp::dvbs::DVBSymToSoftBlock*>(h)->process(count, (dsp::complex_t*)syms, out);
 }
 // correct_reed_solomon_encode through the same 255-byte layout the decoder wrapper uses: parity of one 188-byte packet
 void ref_rs204_parity(const uint8_t* msg188, uint8_t* parity16) {

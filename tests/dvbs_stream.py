@@ -80,3 +80,56 @@ def add_errors(stream, rng, per_packet=(0, 9), burst_every=0):
         pos = rng.choice(204, k, replace=False) + 204 * p
         s[pos] ^= rng.integers(1, 256, k, dtype=np.uint8)
     return s
+
+
+# ---- inner code (EN 300 421 4.4.3): K = 7 convolutional code, punctured, as soft bits -----------------------------------
+RATES = ["1/2", "2/3", "3/4", "5/6", "7/8"]
+# which of X (first polynomial) and Y (second) survive, per information bit of the puncturing period (EN 300 421 table 2)
+_PUNCT = {0: ([1], [1]), 1: ([1, 0], [1, 1]), 2: ([1, 0, 1], [1, 1, 0]), 3: ([1, 0, 1, 0, 1], [1, 1, 0, 1, 0]),
+          4: ([1, 0, 0, 0, 1, 0, 1], [1, 1, 1, 1, 0, 1, 0])}
+
+
+def _parity(v):
+    v = v.astype(np.uint8)
+    v ^= v >> 4
+    v ^= v >> 2
+    v ^= v >> 1
+    return v & 1
+
+
+def conv_encode(bits, state=0):
+    """the reference's CCEncoder (cc_encoder.cpp:92-104): register << 1 | bit, outputs parity(reg & 79), parity(reg & 109)"""
+    b = np.asarray(bits, np.uint8) & 1
+    hist = np.concatenate([[(state >> k) & 1 for k in range(5, -1, -1)], b]).astype(np.int64)   # oldest first
+    reg = np.zeros(len(b), np.int64)
+    for k in range(7):
+        reg |= hist[6 - k:len(hist) - k] << k
+    return _parity(reg & 79), _parity(reg & 109)
+
+
+def puncture(x, y, rate):
+    """-> the transmitted bit sequence of one rate (index into RATES)"""
+    px, py = _PUNCT[rate]
+    n = len(x)
+    keep = np.zeros((n, 2), bool)
+    keep[:, 0] = np.resize(np.array(px, bool), n)
+    keep[:, 1] = np.resize(np.array(py, bool), n)
+    return np.stack([x, y], 1)[keep]
+
+
+def inner_softs(bits, rate, rng, amp=60.0, sigma=0.0, phase=0, lead=0):
+    """decoded-domain bits -> the signed soft bits DVBSymToSoftBlock hands to the Viterbi decoder: bit 1 = +amp; `lead`
+    soft bits of noise first (moves the puncturing / pairing phase); phase 1: the constellation turned so that the decoder
+    has to lock on its 90 degree branch (it maps (a, b) -> (b, -a), rotation.cpp:33-42)"""
+    x, y = conv_encode(bits)
+    tx = puncture(x, y, rate).astype(np.float64) * 2 - 1
+    s = np.concatenate([rng.normal(0, 20, lead), tx * amp])
+    if len(s) % 2:
+        s = s[:-1]
+    if sigma:
+        s = s + rng.normal(0, sigma, len(s))
+    s = np.clip(np.rint(s), -127, 127)
+    if phase == 1:
+        a, b = s[0::2].copy(), s[1::2].copy()
+        s[0::2], s[1::2] = -b, a
+    return s.astype(np.int8)

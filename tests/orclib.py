@@ -111,6 +111,14 @@ def oracle():
         lib.orc_dvbs_deframer_destroy.argtypes = [C.c_void_p]
         lib.orc_dvbs_deframer_work.argtypes = [C.c_void_p, _u8p, C.c_int, _u8p]
         lib.orc_dvbs_deframer_stats.argtypes = [C.c_void_p, ip, ip]
+        lib.orc_vit_create.argtypes = [C.c_float, C.c_int]
+        lib.orc_vit_create.restype = C.c_void_p
+        lib.orc_vit_destroy.argtypes = [C.c_void_p]
+        lib.orc_vit_process.argtypes = [C.c_void_p, C.c_int, _i8p, _u8p]
+        lib.orc_vit_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float)] + [ip] * 5
+        lib.orc_sts_create.restype = C.c_void_p
+        lib.orc_sts_destroy.argtypes = [C.c_void_p]
+        lib.orc_sts_process.argtypes = [C.c_void_p, C.c_int, _f32p, _i8p]
         _oracle = lib
     return _oracle
 
@@ -169,6 +177,15 @@ def ref():
             lib.ref_dvbs_deframer_create.restype = C.c_void_p
             lib.ref_dvbs_deframer_work.argtypes = [C.c_void_p, _u8p, C.c_int, _u8p]
             lib.ref_dvbs_deframer_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        if hasattr(lib, "ref_vit_create"):
+            lib.ref_vit_create.argtypes = [C.c_float, C.c_int]
+            lib.ref_vit_create.restype = C.c_void_p
+            lib.ref_vit_destroy.argtypes = [C.c_void_p]
+            lib.ref_vit_layout_ok.argtypes = [C.c_void_p]
+            lib.ref_vit_process.argtypes = [C.c_void_p, C.c_int, _i8p, _u8p]
+            lib.ref_vit_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float)] + [C.POINTER(C.c_int)] * 5
+            lib.ref_sts_create.restype = C.c_void_p
+            lib.ref_sts_process.argtypes = [C.c_void_p, C.c_int, _f32p, _i8p]
         if hasattr(lib, "ref_ts_create"):
             lib.ref_ts_create.argtypes = [C.c_int]
             lib.ref_ts_create.restype = C.c_void_p
