@@ -318,6 +318,35 @@ int dvbs2fec_dvbs_deframer_work_device(dvbs2fec_dvbs_deframer* p, const uint8_t*
  * (before max_frames); returns the frames it wrote.  Synchronises the device. */
 int dvbs2fec_dvbs_deframer_stats(dvbs2fec_dvbs_deframer* p, int* errors_nor, int* errors_inv, int* found);
 
+/* ---- K11: the inner decoder of the DVB-S chain -- DVBSVitBlock::process (dvbs/dvbs_vit.cpp:6-13) over
+ *      viterbi::Viterbi_DVBS (dvbs/viterbi_all.h:33-163, viterbi_all.cpp:75-318) as the module constructs it
+ *      (module_dvbs_demod.cpp:23: phases 0 and 90 degrees, 8192 soft bits per work() call; ber_threshold 0.15 and
+ *      max_outsync 20 there), and DVBSymToSoftBlock::process (dvbs/dvbs_syms_to_soft.cpp:26-42) in front of it.
+ *      Self-locking punctured K = 7 decoder: searches rate (1/2, 2/3, 3/4, 5/6, 7/8), constellation phase and puncturing
+ *      shift by decoding + re-encoding 2048 soft bits on every candidate, then decodes block after block until max_outsync
+ *      blocks in a row fail the BER test.  All blocks of a call are decoded at once on the device; decoded bits, BER and
+ *      lock parameters are bit-identical to the reference running its bundled generic butterfly kernel
+ *      (dvbs/viterbi/volk_k7_r2_generic_fixed.h), its quirks included (see csrc/dvbs_viterbi.cu).  The members the
+ *      reference reads before writing them start from zeros. ---- */
+typedef struct dvbs2fec_dvbs_viterbi dvbs2fec_dvbs_viterbi;
+int dvbs2fec_dvbs_viterbi_create(int device, float ber_threshold, int max_outsync, dvbs2fec_dvbs_viterbi** out);
+void dvbs2fec_dvbs_viterbi_destroy(dvbs2fec_dvbs_viterbi* v);
+int dvbs2fec_dvbs_viterbi_reset(dvbs2fec_dvbs_viterbi* v);
+/* count signed soft bits (a multiple of 8192; the reference reads past its input otherwise) -> decoded bits, one per
+ * byte; returns how many (0 while searching).  out must hold count bytes; bytes the reference leaves unwritten (27 of
+ * every 6826 at rate 5/6) keep the caller's content.  Unlike the reference the input is not rotated in place.  Host
+ * buffers, synchronous. */
+int dvbs2fec_dvbs_viterbi_process(dvbs2fec_dvbs_viterbi* v, int count, const int8_t* in, uint8_t* out);
+/* same on device buffers (no PCIe traffic but the per-block BER counts); synchronous: the lock state machine runs on the host */
+int dvbs2fec_dvbs_viterbi_process_device(dvbs2fec_dvbs_viterbi* v, int count, const int8_t* d_in, uint8_t* d_out);
+/* Viterbi_DVBS::ber(), getState() (0 searching, 1 locked), rate() (0..4 = 1/2, 2/3, 3/4, 5/6, 7/8) and the lock's phase
+ * (0 / 1 = 0 / 90 degrees), puncturing shift and count of bad blocks; any pointer may be NULL */
+int dvbs2fec_dvbs_viterbi_stats(dvbs2fec_dvbs_viterbi* v, float* ber, int* state, int* rate, int* phase, int* shift, int* invalid);
+/* DVBSymToSoftBlock::process: count symbols (re, im) -> clamp(re * 100), clamp(im * 100) in chunks of 8192 soft bits; what
+ * does not fill a chunk waits in the handle; returns the soft bits written (out: 2 * count + 8192 bytes) */
+int dvbs2fec_dvbs_sts_process(dvbs2fec_dvbs_viterbi* v, int count, const float* syms, int8_t* out);
+int dvbs2fec_dvbs_sts_process_device(dvbs2fec_dvbs_viterbi* v, int count, const float* d_syms, int8_t* d_out);
+
 /* ---- in-tree transmitter for synthetic input (not part of the reference's decode path) ---- */
 /* bbframe: kbch/8 bytes -> code_bits: N bytes of 0/1 (BB scramble, BCH, LDPC; EN 302 307 5.2-5.3) */
 int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits);

@@ -150,6 +150,15 @@ def lib():
     L.dvbs2fec_dvbs_deframer_work.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     L.dvbs2fec_dvbs_deframer_work_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]
     L.dvbs2fec_dvbs_deframer_stats.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.dvbs2fec_dvbs_viterbi_create.argtypes = [C.c_int, C.c_float, C.c_int, C.POINTER(vp)]
+    L.dvbs2fec_dvbs_viterbi_destroy.argtypes = [vp]
+    L.dvbs2fec_dvbs_viterbi_destroy.restype = None
+    L.dvbs2fec_dvbs_viterbi_reset.argtypes = [vp]
+    L.dvbs2fec_dvbs_viterbi_process.argtypes = [vp, C.c_int, vp, vp]
+    L.dvbs2fec_dvbs_viterbi_process_device.argtypes = [vp, C.c_int, vp, vp]
+    L.dvbs2fec_dvbs_viterbi_stats.argtypes = [vp, C.POINTER(C.c_float)] + [C.POINTER(C.c_int)] * 5
+    L.dvbs2fec_dvbs_sts_process.argtypes = [vp, C.c_int, vp, vp]
+    L.dvbs2fec_dvbs_sts_process_device.argtypes = [vp, C.c_int, vp, vp]
     L.dvbs2fec_pll_set_state.argtypes = [vp, C.c_float, C.c_float]
     L.dvbs2fec_pll_set_sequential.argtypes = [vp, C.c_int]
     L.dvbs2fec_pll_process_multi_device.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]
@@ -653,3 +662,54 @@ class DVBSTSDeframer:
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         _check(lib().dvbs2fec_dvbs_deframer_stats(self._p, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+
+class DVBSViterbi:
+    """DVBSVitBlock over viterbi::Viterbi_DVBS (dvbs/dvbs_vit.cpp:6-13, dvbs/viterbi_all.h:33-163) on the device, plus
+    DVBSymToSoftBlock (dvbs/dvbs_syms_to_soft.cpp:26-42) in front of it."""
+    RATES = ("1/2", "2/3", "3/4", "5/6", "7/8")
+
+    def __init__(self, ber_threshold=0.15, max_outsync=20, device=0):
+        self._p = C.c_void_p()
+        _check(lib().dvbs2fec_dvbs_viterbi_create(device, ber_threshold, max_outsync, C.byref(self._p)))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().dvbs2fec_dvbs_viterbi_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(lib().dvbs2fec_dvbs_viterbi_reset(self._p))
+
+    def process(self, softs, out=None):
+        """signed soft bits (a multiple of 8192) -> decoded bits, one per byte.  `out` (len(softs) bytes) is the buffer the
+        bits are written into: what the reference leaves unwritten at rate 5/6 keeps its content"""
+        x = np.ascontiguousarray(softs, np.int8).reshape(-1)
+        if out is None:
+            out = np.zeros(len(x), np.uint8)
+        n = _check(lib().dvbs2fec_dvbs_viterbi_process(self._p, len(x), _ptr(x), _ptr(out)))
+        return out[:n]
+
+    def process_device(self, d_in_ptr, count, d_out_ptr):
+        return _check(lib().dvbs2fec_dvbs_viterbi_process_device(self._p, count, d_in_ptr, d_out_ptr))
+
+    def stats(self):
+        """-> (ber, state, rate, phase, shift, invalid)"""
+        b = C.c_float()
+        v = [C.c_int() for _ in range(5)]
+        _check(lib().dvbs2fec_dvbs_viterbi_stats(self._p, C.byref(b), *[C.byref(i) for i in v]))
+        return (b.value,) + tuple(i.value for i in v)
+
+    def syms_to_soft(self, syms):
+        """complex symbols -> soft bits, in chunks of 8192 (the rest waits for the next call)"""
+        x = np.ascontiguousarray(syms).view(np.float32).reshape(-1) if np.iscomplexobj(syms) else np.ascontiguousarray(syms, np.float32).reshape(-1)
+        n = len(x) // 2
+        out = np.zeros(2 * n + 8192, np.int8)
+        k = _check(lib().dvbs2fec_dvbs_sts_process(self._p, n, _ptr(x), _ptr(out)))
+        return out[:k]

@@ -1,0 +1,102 @@
+"""Row 8(f)-4, inner half, on the GPU: dvbs2fec_dvbs_viterbi_* / dvbs2fec_dvbs_sts_* against the CPU oracle, which
+tests/test_vit_oracle.py pins to the reference's own sources.  Bit-exact: decoded bits, BER, lock state after every call."""
+import numpy as np
+import pytest
+
+import dvbs_stream
+from fec import pkg
+from test_vit_oracle import CASES, OrcViterbi, same_stats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_viterbi_matches_oracle(case):
+    """search, lock, decode at every rate, both phases, odd puncturing offsets; calls of one to five blocks"""
+    rate, sigma, phase, lead, seed = case
+    rng = np.random.default_rng(100 + seed)
+    bits = rng.integers(0, 2, 130000, dtype=np.uint8)
+    s = dvbs_stream.inner_softs(bits, rate, rng, sigma=sigma, phase=phase, lead=lead)
+    nb = min(len(s) // 8192, 14)
+    o, g = OrcViterbi(), pkg.DVBSViterbi()
+    k = 0
+    while k < nb:
+        n = min(int(rng.integers(1, 6)), nb - k)
+        seg = s[k * 8192:(k + n) * 8192]
+        want = o.process(seg, fill=k & 1)
+        got = g.process(seg, out=np.full(len(seg), k & 1, np.uint8))
+        assert got.shape == want.shape and np.array_equal(got, want), (k, n)
+        assert same_stats(g.stats(), o.stats()), (k, g.stats(), o.stats())
+        k += n
+    assert g.stats()[1] == 1 and g.stats()[2] == rate
+    g.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_viterbi_lock_lost_and_found_matches_oracle(seed):
+    """noise, signal, noise until the lock is given up, another rate, degenerate input -- in ONE call (the batch is cut
+    where the state changes) and again block by block"""
+    rng = np.random.default_rng(200 + seed)
+    r1, r2 = [(1, 3), (4, 0), (2, 1)][seed]
+    noise = lambda n: np.clip(np.rint(rng.normal(0, 40, n * 8192)), -128, 127).astype(np.int8)
+    sig = lambda r, n, lead: dvbs_stream.inner_softs(rng.integers(0, 2, 8192 * n, dtype=np.uint8), r, rng, sigma=[12.0, 10.0, 9.0, 7.0, 5.0][r],
+                                                     lead=lead)[:n * 8192]
+    s = np.concatenate([noise(2), sig(r1, 4, 2), noise(5), sig(r2, 4, 0), np.zeros(8192, np.int8), np.full(8192, -128, np.int8), noise(7)])
+    o, g = OrcViterbi(0.15, 3), pkg.DVBSViterbi(0.15, 3)
+    want = o.process(s, fill=7)
+    got = g.process(s, out=np.full(len(s), 7, np.uint8))
+    assert np.array_equal(got, want) and same_stats(g.stats(), o.stats())
+    g.reset()
+    o = OrcViterbi(0.15, 3)
+    for k in range(len(s) // 8192):
+        seg = s[k * 8192:(k + 1) * 8192]
+        want = o.process(seg, fill=7)
+        got = g.process(seg, out=np.full(8192, 7, np.uint8))
+        assert np.array_equal(got, want), k
+        assert same_stats(g.stats(), o.stats()), (k, g.stats(), o.stats())
+    g.close()
+
+
+@pytest.mark.parametrize("rate", [0, 1, 2, 3, 4])
+def test_viterbi_large_batch(rate):
+    """200 blocks in one call: equal to the oracle; the transmitted bits come back (rate 5/6: where the reference decodes)"""
+    rng = np.random.default_rng(300 + rate)
+    nbits = [4096, 5462, 6144, 6827, 7168][rate] * 200
+    bits = rng.integers(0, 2, nbits, dtype=np.uint8)
+    s = dvbs_stream.inner_softs(bits, rate, rng, sigma=[14.0, 11.0, 10.0, 8.0, 6.0][rate])
+    s = s[:len(s) // 8192 * 8192]
+    g = pkg.DVBSViterbi()
+    got = g.process(s)
+    want = OrcViterbi().process(s)
+    assert np.array_equal(got, want)
+    assert g.stats()[1:3] == (1, rate)
+    if rate != 3:
+        assert np.mean(got[200:-200] == bits[200:len(got) - 200]) > 0.999
+    g.close()
+
+
+def test_syms_to_soft_matches_oracle():
+    import orclib
+    rng = np.random.default_rng(5)
+    o = orclib.oracle()
+    ho = o.orc_sts_create()
+    g = pkg.DVBSViterbi()
+    for n in [1, 4095, 1, 5000, 0, 12289, 3, 100000]:
+        syms = (rng.normal(0, 0.9, (n, 2))).astype(np.float32)
+        if n > 10:
+            syms[3:7] = [[1.27, -1.27], [1.2701, -1.2799], [5.0, -7.0], [0.0049, -0.0099]]
+        want = np.zeros(2 * n + 8192, np.int8)
+        k = o.orc_sts_process(ho, n, np.ascontiguousarray(syms.reshape(-1)), want)
+        got = g.syms_to_soft(syms)
+        assert len(got) == k and np.array_equal(got, want[:k])
+    g.close()
+
+
+def test_viterbi_argument_errors():
+    g = pkg.DVBSViterbi()
+    with pytest.raises(pkg.DVBS2FecError):
+        g.process(np.zeros(1000, np.int8))
+    assert len(g.process(np.zeros(0, np.int8))) == 0
+    with pytest.raises(pkg.DVBS2FecError):
+        pkg.DVBSViterbi(device=99)
+    g.close()
