@@ -347,6 +347,23 @@ int dvbs2fec_dvbs_viterbi_stats(dvbs2fec_dvbs_viterbi* v, float* ber, int* state
 int dvbs2fec_dvbs_sts_process(dvbs2fec_dvbs_viterbi* v, int count, const float* syms, int8_t* out);
 int dvbs2fec_dvbs_sts_process_device(dvbs2fec_dvbs_viterbi* v, int count, const float* d_syms, int8_t* d_out);
 
+/* ---- the decode stage of the DVB-S module in one call: DVBSDemod::process (dvbs/module_dvbs_demod.cpp:78-119) behind its
+ *      sample-domain front end (demod.process, SDR++ DSP: not part of this library).  count complex symbols (re, im) ->
+ *      soft bits -> Viterbi (K11) -> TS deframer (K10) -> deinterleaver / RS(204,188) / descrambler (K9) -> TS packets of
+ *      188 bytes; every intermediate buffer stays on the device.  frame_stride: 204 walks the deframer's frames the way
+ *      the module does (module_dvbs_demod.cpp:87 steps by 204 bytes instead of 1632), 1632 takes them back to back.
+ *      Returns the TS bytes written (a multiple of 1504) or DVBS2FEC_ENOSPC.  At most nbits / 1632 + 8 frames per call are
+ *      taken from the deframer (it finds one per 13056 bits in a stream that is not built to fool it); frames_found tells. ---- */
+typedef struct dvbs2fec_dvbs_demod dvbs2fec_dvbs_demod;
+int dvbs2fec_dvbs_demod_create(int device, float ber_threshold, int max_outsync, int frame_stride, dvbs2fec_dvbs_demod** out);
+void dvbs2fec_dvbs_demod_destroy(dvbs2fec_dvbs_demod* p);
+int dvbs2fec_dvbs_demod_reset(dvbs2fec_dvbs_demod* p);
+int dvbs2fec_dvbs_demod_process(dvbs2fec_dvbs_demod* p, int count, const float* syms, uint8_t* out, int out_cap);
+/* stats_viterbi_ber / _lock / _rate (0..4), stats_rs_avg, stats_deframer_err (module_dvbs_demod.cpp:101-115) and the frames
+ * the deframer found / the call decoded; any pointer may be NULL */
+int dvbs2fec_dvbs_demod_stats(dvbs2fec_dvbs_demod* p, float* viterbi_ber, int* viterbi_lock, int* viterbi_rate, float* rs_avg,
+                              int* deframer_err, int* frames_found, int* frames_done);
+
 /* ---- in-tree transmitter for synthetic input (not part of the reference's decode path) ---- */
 /* bbframe: kbch/8 bytes -> code_bits: N bytes of 0/1 (BB scramble, BCH, LDPC; EN 302 307 5.2-5.3) */
 int dvbs2fec_encode_fecframe(int modcod, int shortframes, const uint8_t* bbframe, uint8_t* code_bits);

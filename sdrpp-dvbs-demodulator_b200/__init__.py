@@ -159,6 +159,13 @@ def lib():
     L.dvbs2fec_dvbs_viterbi_stats.argtypes = [vp, C.POINTER(C.c_float)] + [C.POINTER(C.c_int)] * 5
     L.dvbs2fec_dvbs_sts_process.argtypes = [vp, C.c_int, vp, vp]
     L.dvbs2fec_dvbs_sts_process_device.argtypes = [vp, C.c_int, vp, vp]
+    L.dvbs2fec_dvbs_demod_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(vp)]
+    L.dvbs2fec_dvbs_demod_destroy.argtypes = [vp]
+    L.dvbs2fec_dvbs_demod_destroy.restype = None
+    L.dvbs2fec_dvbs_demod_reset.argtypes = [vp]
+    L.dvbs2fec_dvbs_demod_process.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+    L.dvbs2fec_dvbs_demod_stats.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                            C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.dvbs2fec_pll_set_state.argtypes = [vp, C.c_float, C.c_float]
     L.dvbs2fec_pll_set_sequential.argtypes = [vp, C.c_int]
     L.dvbs2fec_pll_process_multi_device.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]
@@ -713,3 +720,42 @@ class DVBSViterbi:
         out = np.zeros(2 * n + 8192, np.int8)
         k = _check(lib().dvbs2fec_dvbs_sts_process(self._p, n, _ptr(x), _ptr(out)))
         return out[:k]
+
+
+class DVBSDemod:
+    """The decode stage of dsp::dvbs::DVBSDemod::process (dvbs/module_dvbs_demod.cpp:78-119) behind demod.process: symbols
+    -> TS packets, on the device.  frame_stride=204 is the module's own walk over the deframer's frames, 1632 back to back."""
+
+    def __init__(self, ber_threshold=0.15, max_outsync=20, frame_stride=204, device=0):
+        self._p = C.c_void_p()
+        _check(lib().dvbs2fec_dvbs_demod_create(device, ber_threshold, max_outsync, frame_stride, C.byref(self._p)))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().dvbs2fec_dvbs_demod_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(lib().dvbs2fec_dvbs_demod_reset(self._p))
+
+    def process(self, syms):
+        """complex symbols -> TS packets [n][188]"""
+        x = np.ascontiguousarray(syms).view(np.float32).reshape(-1) if np.iscomplexobj(syms) else np.ascontiguousarray(syms, np.float32).reshape(-1)
+        n = len(x) // 2
+        out = np.zeros(((2 * n + 8192) // 1632 + 8) * 1504, np.uint8)
+        k = _check(lib().dvbs2fec_dvbs_demod_process(self._p, n, _ptr(x), _ptr(out), len(out)))
+        return out[:k].reshape(-1, 188).copy()
+
+    def stats(self):
+        """-> dict(viterbi_ber, viterbi_lock, viterbi_rate, rs_avg, deframer_err, frames_found, frames_done)"""
+        b, r = C.c_float(), C.c_float()
+        i = [C.c_int() for _ in range(5)]
+        _check(lib().dvbs2fec_dvbs_demod_stats(self._p, C.byref(b), C.byref(i[0]), C.byref(i[1]), C.byref(r), C.byref(i[2]), C.byref(i[3]), C.byref(i[4])))
+        return dict(viterbi_ber=b.value, viterbi_lock=i[0].value, viterbi_rate=i[1].value, rs_avg=r.value, deframer_err=i[2].value,
+                    frames_found=i[3].value, frames_done=i[4].value)

@@ -100,3 +100,71 @@ def test_viterbi_argument_errors():
     with pytest.raises(pkg.DVBS2FecError):
         pkg.DVBSViterbi(device=99)
     g.close()
+
+
+# ---- the whole decode stage of the module: symbols -> TS packets ------------------------------------------------------------
+class OracleChain:
+    """DVBSDemod::process (module_dvbs_demod.cpp:78-100) behind demod.process, out of the oracle's pieces (each pinned to the
+    reference's class); the bit buffer persists from call to call like the handle's"""
+
+    def __init__(self, stride):
+        import orclib
+        from test_dvbs_oracle import OrcDeframer, OrcOuter
+        self.o = orclib.oracle()
+        self.sts = self.o.orc_sts_create()
+        self.vit, self.defr, self.outer, self.stride = OrcViterbi(), OrcDeframer(), OrcOuter(), stride
+        self.bits = np.zeros(0, np.uint8)
+
+    def process(self, syms):
+        x = np.ascontiguousarray(syms, np.complex64).view(np.float32).reshape(-1)
+        n = len(x) // 2
+        soft = np.zeros(2 * n + 8192, np.int8)
+        k = self.o.orc_sts_process(self.sts, n, x, soft)
+        if not k:
+            return np.zeros((0, 188), np.uint8)
+        if len(self.bits) < 2 * n + 8192 + 8192:
+            self.bits = np.concatenate([self.bits, np.zeros(2 * n + 8192 + 8192 - len(self.bits), np.uint8)])
+        nb = self.vit.proc(self.vit.h, k, soft[:k].copy(), self.bits)
+        frames, _ = self.defr.work(self.bits[:nb])
+        nfr = min(len(frames), nb // 1632 + 8)
+        if not nfr:
+            return np.zeros((0, 188), np.uint8)
+        ts, err = self.outer.process(frames.reshape(-1), nfr, self.stride)
+        return ts
+
+
+def dvbs_symbols(nframes, rate, rng, sigma=0.08, lead=0):
+    """TS packets -> outer code -> inner code -> QPSK symbols (bit 1 = +0.6) with noise"""
+    ts, ch = dvbs_stream.outer_stream(nframes, rng)
+    bits = np.unpackbits(ch)
+    x, y = dvbs_stream.conv_encode(bits)
+    tx = dvbs_stream.puncture(x, y, rate).astype(np.float32) * 2 - 1
+    tx = np.concatenate([rng.normal(0, 0.3, lead).astype(np.float32), tx])
+    tx = tx[:len(tx) // 2 * 2] * 0.6 + rng.normal(0, sigma, len(tx) // 2 * 2).astype(np.float32)
+    return ts, (tx[0::2] + 1j * tx[1::2]).astype(np.complex64)
+
+
+@pytest.mark.parametrize("case", [(0, 1632, 0), (1, 1632, 1), (2, 204, 2), (4, 1632, 3), (3, 1632, 4)])
+def test_demod_chain_matches_oracle_and_recovers_the_packets(case):
+    """symbols in, TS packets out, in calls of uneven sizes: equal to the chain of oracle pieces; with back-to-back frames
+    (stride 1632) and a rate the reference decodes properly the transmitted packets come back"""
+    rate, stride, seed = case
+    rng = np.random.default_rng(400 + seed)
+    ts, syms = dvbs_symbols(40, rate, rng, lead=2 * int(rng.integers(0, 50)))
+    o, g = OracleChain(stride), pkg.DVBSDemod(frame_stride=stride)
+    cuts = sorted(set(int(c) for c in rng.integers(0, len(syms), 4)) | {0, len(syms)})
+    got_all = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        want = o.process(syms[lo:hi])
+        got = g.process(syms[lo:hi])
+        assert got.shape == want.shape and np.array_equal(got, want), (lo, hi)
+        got_all.append(got)
+    st = g.stats()
+    assert st["viterbi_lock"] == 1 and st["viterbi_rate"] == rate
+    got_all = np.concatenate(got_all)
+    if stride == 1632 and rate != 3:
+        assert len(got_all) >= 8 * 20
+        sent = {p.tobytes() for p in ts}
+        good = sum(p.tobytes() in sent for p in got_all[24:])
+        assert good >= len(got_all) - 24 - 8
+    g.close()
