@@ -39,6 +39,7 @@ cudaError_t reserve(T*& p, size_t& cap, size_t n, bool zero = false) {
     if (zero) {
         cudaMemset(q, 0, n * sizeof(T));
         if (p) cudaMemcpy(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);      // grows without forgetting
+        cudaDeviceSynchronize();      // both are asynchronous, and the decoder's stream does not wait for the default stream
     }
     if (p) cudaFree(p);
     p = q;
@@ -97,6 +98,7 @@ int dvbs2fec_dvbs_demod_reset(dvbs2fec_dvbs_demod* p) {
     if (rc) return rc;
     CU(cudaSetDevice(p->device));
     if (p->d_bits) CU(cudaMemset(p->d_bits, 0, p->bits_cap));
+    CU(cudaDeviceSynchronize());
     std::fill(p->errors, p->errors + 8, 0);
     p->frames_found = p->frames_done = 0;
     return 0;
@@ -105,7 +107,7 @@ int dvbs2fec_dvbs_demod_reset(dvbs2fec_dvbs_demod* p) {
 int dvbs2fec_dvbs_demod_process(dvbs2fec_dvbs_demod* p, int count, const float* syms, uint8_t* out, int out_cap) {
     if (!p || count < 0 || out_cap < 0 || (count && !syms) || (out_cap && !out)) return api_fail(DVBS2FEC_EINVAL, "bad arguments");
     if (!count) return 0;
-    if (count > (1 << 22)) return api_fail(DVBS2FEC_EINVAL, "more than 2^22 symbols in one call");
+    if (count > (1 << 23)) return api_fail(DVBS2FEC_EINVAL, "more than 2^23 symbols in one call");
     CU(cudaSetDevice(p->device));
     const size_t nsoft_max = (size_t)2 * count + 8192;
     CU(reserve(p->d_syms, p->syms_cap, (size_t)2 * count));

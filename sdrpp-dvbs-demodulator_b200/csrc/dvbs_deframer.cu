@@ -194,6 +194,7 @@ int dvbs2fec_dvbs_deframer_reset(dvbs2fec_dvbs_deframer* p) {
     CU(cudaMemset(p->st, 0, sizeof(DeframerState)));
     CU(cudaMemset(p->hist[0], 0, kWindow));
     CU(cudaMemset(p->hist[1], 0, kWindow));
+    CU(cudaDeviceSynchronize());      // device memsets are asynchronous, and the callers' streams do not wait for the default stream
     p->cur = 0;
     return 0;
 }

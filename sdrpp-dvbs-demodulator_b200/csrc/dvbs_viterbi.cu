@@ -489,6 +489,7 @@ struct dvbs2fec_dvbs_viterbi {
     int8_t* d_last_search = nullptr;      // first 2048 soft bits of the last block the search ran on
     int have_last_search = 0;
     int search_batch = 1;
+    long long n_tasks = 0, n_repeated = 0, n_passes = 0;      // diagnostics: decode tasks run, tasks repeated from a corrected start, check passes
     Pattern pat[kPatterns];
     SearchLayout lay;
     int search_img_stride = 0, search_steps = 0, search_out = 0;
@@ -530,6 +531,7 @@ int run_tasks(Vit* v, int ntasks) {
     acs_kernel<<<grid, 128, 0, st>>>(v->tasks, v->res, ntasks, 0, v->images, v->decpool, v->decoded);
     acs_kernel<<<grid, 128, 0, st>>>(v->tasks, v->res, ntasks, 1, v->images, v->decpool, v->decoded);
     v->h_res.resize(ntasks);
+    v->n_tasks += ntasks;
     for (int pass = 0;; ++pass) {
         int flag = 0;
         CU(cudaMemsetAsync(v->flag, 0, sizeof(int), st));
@@ -538,7 +540,9 @@ int run_tasks(Vit* v, int ntasks) {
         CU(cudaMemcpyAsync(&flag, v->flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(v->h_res.data(), v->res, sizeof(VResult) * ntasks, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        v->n_passes++;
         if (!flag) break;
+        v->n_repeated += flag;
         if (pass > ntasks) return api_fail(DVBS2FEC_ECUDA, "viterbi: start-state check does not settle");
         acs_kernel<<<grid, 128, 0, st>>>(v->tasks, v->res, ntasks, 2, v->images, v->decpool, v->decoded);
     }
@@ -854,6 +858,14 @@ int dvbs2fec_dvbs_viterbi_stats(dvbs2fec_dvbs_viterbi* v, float* ber, int* state
     if (phase) *phase = v->phase;
     if (shift) *shift = v->shift;
     if (invalid) *invalid = v->invalid;
+    return 0;
+}
+
+int dvbs2fec_dvbs_viterbi_counters(dvbs2fec_dvbs_viterbi* v, long long* tasks, long long* repeated, long long* passes) {
+    if (!v) return api_fail(DVBS2FEC_EINVAL, "handle is NULL");
+    if (tasks) *tasks = v->n_tasks;
+    if (repeated) *repeated = v->n_repeated;
+    if (passes) *passes = v->n_passes;
     return 0;
 }
 

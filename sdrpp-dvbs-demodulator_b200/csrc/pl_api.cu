@@ -156,6 +156,7 @@ int dvbs2fec_plsync_create(int device, dvbs2fec_plsync** out) {
     CU(cudaMemset(p->hst.p, 0, sizeof(PlHdrState)));
     CU(p->pst.reserve(1));
     CU(cudaMemset(p->pst.p, 0, sizeof(PllState)));
+    CU(cudaDeviceSynchronize());      // device memsets are asynchronous; the handle's streams do not wait for the default stream
     *out = p.release();
     return 0;
 }
