@@ -249,6 +249,7 @@ int setup_device_tables(dvbs2fec_handle* h, DevCtx& d) {
     if (!cd.row_level.p) {
         CU(cd.row_level.reserve(c.row_level.size()));
         CU(cudaMemcpy(cd.row_level.p, c.row_level.data(), c.row_level.size(), cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     }
     LdpcDev& L = d.ldpc;
     L.N = c.N; L.K = c.K; L.R = c.R; L.q = c.q;
@@ -276,7 +277,9 @@ int setup_device_tables(dvbs2fec_handle* h, DevCtx& d) {
         CU(d.gf_log[fi].reserve(gf.log.size()));
         CU(d.gf_exp[fi].reserve(gf.exp.size()));
         CU(cudaMemcpy(d.gf_log[fi].p, gf.log.data(), gf.log.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
         CU(cudaMemcpy(d.gf_exp[fi].p, gf.exp.data(), gf.exp.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     }
     BchTabDev& bt = d.bch[m * 100 + t];
     if (!bt.crc.p) {
@@ -284,12 +287,15 @@ int setup_device_tables(dvbs2fec_handle* h, DevCtx& d) {
         CU(bt.crc.reserve(bh.crc.size()));
         CU(bt.basis.reserve(bh.basis.size()));
         CU(cudaMemcpy(bt.crc.p, bh.crc.data(), bh.crc.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
         CU(cudaMemcpy(bt.basis.p, bh.basis.data(), bh.basis.size() * 2, cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     }
     if (!d.prbs.p) {
         const auto& seq = bb_prbs();
         CU(d.prbs.reserve(seq.size()));
         CU(cudaMemcpy(d.prbs.p, seq.data(), seq.size(), cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     }
     BchDev& B = d.bchd;
     B.gf.m = m; B.gf.N = gf.N; B.gf.log = d.gf_log[fi].p; B.gf.exp = d.gf_exp[fi].p;
@@ -321,6 +327,7 @@ int setup_device_tables(dvbs2fec_handle* h, DevCtx& d) {
             std::vector<uint32_t> tab = demap_lut(ch);
             CU(lut.reserve(tab.size()));
             CU(cudaMemcpy(lut.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+            CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
         }
         D.lut = lut.p;
     }
@@ -862,6 +869,7 @@ int dvbs2fec_set_pl_scrambling(dvbs2fec_handle* h, int codenum) {
             std::vector<uint8_t> rn = pl_scrambling_rn(codenum, 32400 + 36 * 22 + 8);
             CU(d.pl_rn.reserve(rn.size()));
             CU(cudaMemcpy(d.pl_rn.p, rn.data(), rn.size(), cudaMemcpyHostToDevice));
+            CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
         }
         d.demap.rn = codenum >= 0 ? d.pl_rn.p : nullptr;
     }

@@ -114,6 +114,7 @@ int dvbs2fec_dvbs_demod_process(dvbs2fec_dvbs_demod* p, int count, const float* 
     CU(reserve(p->d_soft, p->soft_cap, nsoft_max));
     CU(reserve(p->d_bits, p->bits_cap, nsoft_max, true));
     CU(cudaMemcpy(p->d_syms, syms, sizeof(float) * 2 * count, cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());      // a pageable copy returns once staged; the stages' own streams do not wait for the default stream
     const int nsoft = dvbs2fec_dvbs_sts_process_device(p->vit, count, p->d_syms, p->d_soft);      // :80
     if (nsoft <= 0) return nsoft;
     const int nbits = dvbs2fec_dvbs_viterbi_process_device(p->vit, nsoft, p->d_soft, p->d_bits);      // :81

@@ -367,6 +367,7 @@ int dvbs2fec_dvbs_outer_reset(dvbs2fec_dvbs_outer* p) {
     s.prbs_off = -1;
     s.prbs_next = -1;
     CU(cudaMemcpy(p->st.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     return 0;
 }
 
@@ -395,6 +396,7 @@ int dvbs2fec_dvbs_outer_create(int device, dvbs2fec_dvbs_outer** out) {
         if (i < 256) g.log[e] = (uint8_t)i;
     }
     CU(cudaMemcpy(p->gf.p, &g, sizeof g, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     // one period of the dispersal generator from its load value 0xa9 (dvbs_scrambling.h:16-28): entry o = the byte
     // prbs(8) returns after o clocks
     std::vector<uint8_t> bits(kPeriod + 8), tab(kPeriod + 1);
@@ -410,6 +412,7 @@ int dvbs2fec_dvbs_outer_create(int device, dvbs2fec_dvbs_outer** out) {
         tab[(size_t)o] = (uint8_t)b;
     }
     CU(cudaMemcpy(p->prbs.p, tab.data(), kPeriod, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     int rc = dvbs2fec_dvbs_outer_reset(p.get());
     if (rc) return rc;
     *out = p.release();

@@ -153,6 +153,7 @@ int dvbs2fec_plsync_create(int device, dvbs2fec_plsync** out) {
     std::unique_ptr<PlTables> t(new PlTables());
     build_tables(*t);
     CU(cudaMemcpy(p->tab.p, t.get(), sizeof(PlTables), cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     CU(cudaMemset(p->hst.p, 0, sizeof(PlHdrState)));
     CU(p->pst.reserve(1));
     CU(cudaMemset(p->pst.p, 0, sizeof(PllState)));
@@ -297,6 +298,7 @@ int dvbs2fec_plhdr_set_params(dvbs2fec_plsync* p, float loop_bw) {
     s.alpha = (4 * damp * bw) / den;
     s.beta = (4 * bw * bw) / den;
     CU(cudaMemcpy(p->hst.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     return 0;
 }
 
@@ -341,6 +343,7 @@ static int fed_tables(dvbs2fec_plsync* p, int pilots, int codenum) {
         std::vector<uint8_t> rn = pl_scrambling_rn(codenum, 131072);
         CU(p->rn.reserve(rn.size()));
         CU(cudaMemcpy(p->rn.p, rn.data(), rn.size(), cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
         p->rn_codenum = codenum;
     }
     return 0;
@@ -388,6 +391,7 @@ int dvbs2fec_pll_set_params(dvbs2fec_plsync* p, float loop_bw, int modcod, int s
     s.alpha = (4 * damp * bw) / den;
     s.beta = (4 * bw * bw) / den;
     CU(cudaMemcpy(p->pst.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     PllArgs& a = p->pll;
     a = PllArgs{};
     a.pilot_cnt = 0;
@@ -415,6 +419,7 @@ int dvbs2fec_pll_set_params(dvbs2fec_plsync* p, float loop_bw, int modcod, int s
         const std::vector<float> lut = demap_phase_lut(c);
         CU(p->perr.reserve(lut.size()));
         CU(cudaMemcpy(p->perr.p, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
         a.perr_lut = p->perr.p;
     }
     a.rn = p->rn.p;
@@ -432,6 +437,7 @@ int dvbs2fec_pll_reset(dvbs2fec_plsync* p) {
     s.phase = 0;
     s.freq = 0;
     CU(cudaMemcpy(p->pst.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     return 0;
 }
 
@@ -443,6 +449,7 @@ int dvbs2fec_pll_set_state(dvbs2fec_plsync* p, float phase, float freq) {
     s.phase = phase;
     s.freq = freq;
     CU(cudaMemcpy(p->pst.p, &s, sizeof s, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(nullptr));      // (a pageable copy returns once staged; non-blocking streams do not wait for the default stream)
     return 0;
 }
 

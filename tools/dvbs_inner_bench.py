@@ -17,7 +17,7 @@ import dvbs_stream, orclib
 from test_vit_oracle import OrcViterbi, RefViterbi
 from test_dvbs_oracle import OrcDeframer, RefDeframer, OrcOuter, RefOuter
 
-ap = argparse.ArgumentParser(); ap.add_argument("--out", default=None); ap.add_argument("--blocks", type=int, default=1024); a = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--out", default=None); ap.add_argument("--blocks", type=int, default=1056); a = ap.parse_args()
 have_ref = orclib.have_ref() and hasattr(orclib.ref(), "ref_vit_create")
 Vit, Def, Out = (RefViterbi, RefDeframer, RefOuter) if have_ref else (OrcViterbi, OrcDeframer, OrcOuter)
 res = dict(cpu_kind="reference" if have_ref else "oracle", viterbi=[], search=None, deframer=None, chain=[])
@@ -30,9 +30,9 @@ def timed(fn, reps):
 for rate in range(5):
     rng = np.random.default_rng(rate)
     per_block = [4096, 5462, 6144, 6827, 7168][rate]
-    base = dvbs_stream.inner_softs(rng.integers(0, 2, per_block * 66, dtype=np.uint8), rate, rng, sigma=[14.0, 8.0, 8.0, 5.0, 5.0][rate])
-    base = base[:64 * 8192]
-    s = np.tile(base, a.blocks // 64)      # (the joints are wrong code words: a few bad blocks, far below max_outsync)
+    base = dvbs_stream.inner_softs(rng.integers(0, 2, per_block * 68, dtype=np.uint8), rate, rng, sigma=[14.0, 8.0, 8.0, 5.0, 5.0][rate])
+    base = base[:66 * 8192]      # 66 blocks: the depuncturers' phase (periods of 3 and 6 soft bits) is the same at every joint
+    s = np.tile(base, a.blocks // 66)      # (the joints are wrong code words: a few bad blocks, far below max_outsync)
     n = len(s)
     d_in = torch.from_numpy(s).cuda(); d_out = torch.zeros(n, dtype=torch.uint8, device="cuda")
     g = pkg.DVBSViterbi()
@@ -40,9 +40,9 @@ for rate in range(5):
     first = d_out.cpu().numpy()[:nbits].copy()
     ms = timed(lambda: g.process_device(d_in.data_ptr(), n, d_out.data_ptr()), 5)
     st = g.stats()
-    cpu = Vit(); nc = 64 * 8192
+    cpu = Vit(); nc = 66 * 8192
     want = cpu.process(s[:nc]); t0 = time.perf_counter(); cpu.process(s[nc:2 * nc]); cpu_ms = (time.perf_counter() - t0) * 1e3 * n / nc
-    res["viterbi"].append(dict(rate=dvbs_stream.RATES[rate], blocks=a.blocks, gpu_ms=round(ms, 3), blocks_per_s=round(a.blocks / ms * 1e3),
+    res["viterbi"].append(dict(rate=dvbs_stream.RATES[rate], blocks=n // 8192, gpu_ms=round(ms, 3), blocks_per_s=round(n / 8192 / ms * 1e3),
                                decoded_mbit_s=round(nbits / ms / 1e3, 1), soft_bits_gb_s=round(n / ms / 1e6, 2), cpu_ms_1_core=round(cpu_ms, 1),
                                speedup=round(cpu_ms / ms, 1), locked=st[1] == 1 and st[2] == rate, equal_to_cpu_on_first_blocks=bool(np.array_equal(first[:len(want)], want)),
                                counters_tasks_repeated_passes=g.counters()))
