@@ -149,3 +149,24 @@ o2, e2 = od.process(bad[2 * 1632:], 4)
 o3, e3 = od.process(bad, 9, 204)
 print("dvbs outer", o1.shape, o2.shape, o3.shape, int(e1.sum() + e2.sum()), int(e3.sum()))
 od.close()
+# DVB-S inner half: TS deframer (window over two calls), Viterbi search + lock + decode at a continuous-depuncturer rate,
+# search on noise, the whole stage from symbols
+frames_, bits_ = None, np.unpackbits(ch)
+df = pkg.DVBSTSDeframer()
+f1 = df.work(bits_[:20001]); f2 = df.work(bits_[20001:])
+print("dvbs deframer", f1.shape, f2.shape, df.stats())
+df.close()
+vrng = np.random.default_rng(14)
+vit = pkg.DVBSViterbi(0.15, 2)
+sv = dvbs_stream.inner_softs(vrng.integers(0, 2, 5462 * 4, dtype=np.uint8), 1, vrng, sigma=8.0)[:3 * 8192]
+b1 = vit.process(sv)
+b2 = vit.process(np.clip(np.rint(vrng.normal(0, 40, 4 * 8192)), -127, 127).astype(np.int8))
+print("dvbs viterbi", len(b1), len(b2), vit.stats(), vit.counters())
+vit.close()
+x_, y_ = dvbs_stream.conv_encode(bits_)
+tx = dvbs_stream.puncture(x_, y_, 2).astype(np.float32) * 1.2 - 0.6
+tx = tx[:len(tx) // 2 * 2] + vrng.normal(0, 0.05, len(tx) // 2 * 2).astype(np.float32)
+dm = pkg.DVBSDemod(frame_stride=1632)
+t1 = dm.process((tx[0::2] + 1j * tx[1::2]).astype(np.complex64))
+print("dvbs chain", t1.shape, dm.stats())
+dm.close()
