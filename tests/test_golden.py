@@ -24,7 +24,7 @@ def sha_rows(a):
 
 
 def test_fixtures_present():
-    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 15
+    assert len(glob.glob(os.path.join(GOLD, "*.npz"))) >= 20
 
 
 @pytest.mark.parametrize("name", ["chain_s1_2", "chain_s8_9", "chain_s1_4", "chain_n1_2"])
@@ -144,3 +144,77 @@ def test_cuda_reproduces_reference_demapper(name):
     # 32APSK: device expf/logf, <= 1 LSB on <= 0.5 % of the LLRs
     assert diff.max() <= 1 and (diff != 0).mean() <= 0.005
     dec.close()
+
+
+# ---- row 8(f)-4: the DVB-S chain ---------------------------------------------------------------------------------------
+VIT_FIXTURES = ["dvbs_vit_r12_p90", "dvbs_vit_r23", "dvbs_vit_r56"]
+
+
+def _check_viterbi(g, make):
+    """make() -> (process(softs, fill) -> bits, stats() -> (ber, state, rate, phase, shift, invalid))"""
+    process, stats = make()
+    bits = np.unpackbits(g["bits"])
+    k = pos = 0
+    for n, nb, st in zip(g["calls"], g["nbits"], g["stats"]):
+        got = process(g["softs"][k * 8192:(k + n) * 8192], 1)
+        k += n
+        assert len(got) == nb and np.array_equal(got, bits[pos:pos + nb])
+        pos += nb
+        s = stats()
+        assert np.float32(s[0]).view(np.int32) == st[0] and s[1] == st[1] and s[5] == st[5]
+        if s[1]:
+            assert tuple(s[2:5]) == tuple(st[2:5])
+    assert g["stats"][-1][1] == 1 and g["stats"][-1][2] == g["rate"]
+
+
+@pytest.mark.parametrize("name", VIT_FIXTURES)
+def test_oracle_reproduces_reference_viterbi(name):
+    from test_vit_oracle import OrcViterbi
+
+    def make():
+        v = OrcViterbi()
+        return (lambda s, fill: v.process(s, fill=fill)), v.stats
+    _check_viterbi(load(name), make)
+
+
+def test_oracle_reproduces_reference_dvbs_outer():
+    from test_dvbs_oracle import OrcDeframer, OrcOuter
+    g = load("dvbs_outer")
+    bits = np.unpackbits(g["bits"])[:int(g["nbits"])]
+    d = OrcDeframer()
+    f1, s1 = d.work(bits[:int(g["cut"])])
+    f2, s2 = d.work(bits[int(g["cut"]):])
+    assert [len(f1), len(f2)] == g["nframes"].tolist() and [list(s1), list(s2)] == g["deframer_stats"].tolist()
+    frames = np.concatenate([f1, f2])
+    assert np.array_equal(frames, g["frames"])
+    o, e = OrcOuter().process(frames.reshape(-1), len(frames), 1632)
+    assert np.array_equal(o, g["ts_1632"]) and np.array_equal(e, g["err_1632"])
+    o, e = OrcOuter().process(frames.reshape(-1), len(g["err_204"]) // 8, 204)
+    assert np.array_equal(o, g["ts_204"]) and np.array_equal(e, g["err_204"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", VIT_FIXTURES)
+def test_cuda_reproduces_reference_viterbi(name):
+    def make():
+        v = pkg.DVBSViterbi()
+        return (lambda s, fill: v.process(s, out=np.full(len(s), fill, np.uint8))), v.stats
+    _check_viterbi(load(name), make)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_dvbs_outer():
+    g = load("dvbs_outer")
+    bits = np.unpackbits(g["bits"])[:int(g["nbits"])]
+    d = pkg.DVBSTSDeframer()
+    f1 = d.work(bits[:int(g["cut"])])
+    s1 = d.stats()[:2]
+    f2 = d.work(bits[int(g["cut"]):])
+    s2 = d.stats()[:2]
+    assert [len(f1), len(f2)] == g["nframes"].tolist() and [list(s1), list(s2)] == g["deframer_stats"].tolist()
+    frames = np.concatenate([f1, f2])
+    assert np.array_equal(frames, g["frames"])
+    o, e = pkg.DVBSOuterDecoder().process(frames.reshape(-1), len(frames), 1632)
+    assert np.array_equal(o, g["ts_1632"]) and np.array_equal(e, g["err_1632"])
+    o, e = pkg.DVBSOuterDecoder().process(frames.reshape(-1), len(g["err_204"]) // 8, 204)
+    assert np.array_equal(o, g["ts_204"]) and np.array_equal(e, g["err_204"])

@@ -120,6 +120,49 @@ def ts_parser_fixture(kind, kbch, seed):
                 stats=np.array(stats, np.int32))
 
 
+def dvbs_vit_fixture(rate, phase, lead, seed):
+    """the reference's Viterbi_DVBS (viterbi_all.cpp) on two blocks of noise, then a signal: calls of 2, 1, 3, 1 and 5 blocks;
+    decoded bits (packed) and ber / state / rate / phase / shift / invalid after every call"""
+    import dvbs_stream
+    from test_vit_oracle import RefViterbi
+    rng = np.random.default_rng(seed)
+    per = [4096, 5462, 6144, 6827, 7168][rate]
+    sig = dvbs_stream.inner_softs(rng.integers(0, 2, per * 11, dtype=np.uint8), rate, rng, sigma=[12.0, 9.0, 9.0, 6.0, 5.0][rate], phase=phase, lead=lead)
+    softs = np.concatenate([np.clip(np.rint(rng.normal(0, 40, 2 * 8192)), -127, 127).astype(np.int8), sig[:10 * 8192]])
+    v = RefViterbi()
+    calls, bits, nbits, stats = [2, 1, 3, 1, 5], [], [], []
+    k = 0
+    for n in calls:
+        o = v.process(softs[k * 8192:(k + n) * 8192], fill=1)
+        k += n
+        bits.append(o)
+        nbits.append(len(o))
+        st = v.stats()
+        stats.append([np.float32(st[0]).view(np.int32)] + list(st[1:]))
+    return dict(rate=rate, softs=softs, calls=np.array(calls), nbits=np.array(nbits), bits=np.packbits(np.concatenate(bits)),
+                stats=np.array(stats, np.int64))
+
+
+def dvbs_outer_fixture(seed):
+    """the reference's DVBS_TS_Deframer and its deinterleaver / DVBSReedSolomon (libcorrect) / descrambler on 24 frames with
+    byte errors (some packets beyond the code) behind 1234 bits of junk; frame stride 1632 and the module's own 204"""
+    import dvbs_stream
+    from test_dvbs_oracle import RefDeframer, RefOuter
+    rng = np.random.default_rng(seed)
+    ts, ch = dvbs_stream.outer_stream(24, rng)
+    bad = dvbs_stream.add_errors(ch, rng, per_packet=(0, 11))
+    bits = np.concatenate([rng.integers(0, 2, 1234, dtype=np.uint8), np.unpackbits(bad), rng.integers(0, 2, 6, dtype=np.uint8)])
+    d = RefDeframer()
+    f1, s1 = d.work(bits[:100001])
+    f2, s2 = d.work(bits[100001:])
+    frames = np.concatenate([f1, f2])
+    o1, e1 = RefOuter().process(frames.reshape(-1), len(frames), 1632)
+    n204 = (frames.size - 1632) // 204 + 1
+    o2, e2 = RefOuter().process(frames.reshape(-1), n204, 204)
+    return dict(bits=np.packbits(bits), nbits=len(bits), cut=100001, nframes=np.array([len(f1), len(f2)]), deframer_stats=np.array([s1, s2]),
+                frames=frames, ts_1632=o1, err_1632=e1, ts_204=o2, err_204=e2)
+
+
 def main():
     if not orclib.have_ref():
         raise SystemExit("oracle/_ref/libdvbs2_ref.so is missing: run `make -C oracle ref` in the build container")
@@ -139,6 +182,10 @@ def main():
     np.savez_compressed(os.path.join(OUT, "tsparse_odd_s14.npz"), **ts_parser_fixture("ts_odd", 3072, 5))
     np.savez_compressed(os.path.join(OUT, "tsparse_gse_n12.npz"), **ts_parser_fixture("gse", 32208, 8))
     np.savez_compressed(os.path.join(OUT, "tsparse_gsemix_s12.npz"), **ts_parser_fixture("gse_mixed", 7032, 21))
+    np.savez_compressed(os.path.join(OUT, "dvbs_vit_r12_p90.npz"), **dvbs_vit_fixture(0, 1, 1, 31))
+    np.savez_compressed(os.path.join(OUT, "dvbs_vit_r23.npz"), **dvbs_vit_fixture(1, 0, 4, 32))
+    np.savez_compressed(os.path.join(OUT, "dvbs_vit_r56.npz"), **dvbs_vit_fixture(3, 0, 7, 33))
+    np.savez_compressed(os.path.join(OUT, "dvbs_outer.npz"), **dvbs_outer_fixture(34))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
