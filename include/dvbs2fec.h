@@ -343,8 +343,9 @@ int dvbs2fec_dvbs_viterbi_process_device(dvbs2fec_dvbs_viterbi* v, int count, co
  * (0 / 1 = 0 / 90 degrees), puncturing shift and count of bad blocks; any pointer may be NULL */
 int dvbs2fec_dvbs_viterbi_stats(dvbs2fec_dvbs_viterbi* v, float* ber, int* state, int* rate, int* phase, int* shift, int* invalid);
 /* diagnostics since create: decode tasks run (one per block when locked, 52 per block while searching), tasks that had to
- * be repeated because the start state guessed for them was not the one their predecessor reached, check passes */
-int dvbs2fec_dvbs_viterbi_counters(dvbs2fec_dvbs_viterbi* v, long long* tasks, long long* repeated, long long* passes);
+ * be repeated because the start state guessed for them was not the one their predecessor reached, check passes, and
+ * tracebacks whose 32 parallel pieces did not join up and were walked step by step instead */
+int dvbs2fec_dvbs_viterbi_counters(dvbs2fec_dvbs_viterbi* v, long long* tasks, long long* repeated, long long* passes, long long* walks);
 /* DVBSymToSoftBlock::process: count symbols (re, im) -> clamp(re * 100), clamp(im * 100) in chunks of 8192 soft bits; what
  * does not fill a chunk waits in the handle; returns the soft bits written (out: 2 * count + 8192 bytes) */
 int dvbs2fec_dvbs_sts_process(dvbs2fec_dvbs_viterbi* v, int count, const float* syms, int8_t* out);

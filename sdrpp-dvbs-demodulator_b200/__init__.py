@@ -157,7 +157,7 @@ def lib():
     L.dvbs2fec_dvbs_viterbi_process.argtypes = [vp, C.c_int, vp, vp]
     L.dvbs2fec_dvbs_viterbi_process_device.argtypes = [vp, C.c_int, vp, vp]
     L.dvbs2fec_dvbs_viterbi_stats.argtypes = [vp, C.POINTER(C.c_float)] + [C.POINTER(C.c_int)] * 5
-    L.dvbs2fec_dvbs_viterbi_counters.argtypes = [vp] + [C.POINTER(C.c_longlong)] * 3
+    L.dvbs2fec_dvbs_viterbi_counters.argtypes = [vp] + [C.POINTER(C.c_longlong)] * 4
     L.dvbs2fec_dvbs_sts_process.argtypes = [vp, C.c_int, vp, vp]
     L.dvbs2fec_dvbs_sts_process_device.argtypes = [vp, C.c_int, vp, vp]
     L.dvbs2fec_dvbs_demod_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(vp)]
@@ -715,8 +715,8 @@ class DVBSViterbi:
         return (b.value,) + tuple(i.value for i in v)
 
     def counters(self):
-        """-> (decode tasks run, tasks repeated from a corrected start state, check passes)"""
-        v = [C.c_longlong() for _ in range(3)]
+        """-> (decode tasks run, tasks repeated from a corrected start state, check passes, tracebacks walked step by step)"""
+        v = [C.c_longlong() for _ in range(4)]
         _check(lib().dvbs2fec_dvbs_viterbi_counters(self._p, *[C.byref(i) for i in v]))
         return tuple(i.value for i in v)
 

@@ -14,8 +14,9 @@
 //    nothing changes.  The result is the sequential result, not an approximation.
 //  * a task = a warp: lane i owns butterfly i (states 2i, 2i+1 as the two 16-bit halves of one register), the two
 //    inputs come by shuffle, add-compare-select is a packed 16-bit minimum with the reference's 8-bit wrap-around kept
-//    by masking, decisions leave by ballot, the per-step renormalisation is a warp min-reduction; the traceback runs
-//    32 steps per coalesced load of decision words.
+//    by masking, decisions leave by ballot, the per-step renormalisation is a warp min-reduction; the traceback is cut
+//    into 32 pieces, one per lane, each started 128 steps early from an arbitrary state and accepted only if every
+//    piece began where the piece above it ended (otherwise the task is walked back step by step).
 //  * the lock search (52 candidate decodes per call: 2 phases x 26 rate / puncturing-shift branches) is the same kind
 //    of task; a CTA per block replays the reference's buffer writes in shared memory so that every candidate sees
 //    the stale bytes the reference's decoders read past their depunctured input (viterbi_all.cpp:89,107,127,167).
@@ -47,6 +48,7 @@ constexpr int kBuf = 8192;            // VIT_BUF_SIZE (dvbs/dvbs_defines.h)
 constexpr int kTest = 2048;           // TEST_BITS_LENGTH
 constexpr int kGuessSteps = 326;      // trellis steps the guess kernel runs (320 + the 6 behind the block)
 constexpr int kSearchTasks = 52;
+constexpr int kWarm = 128;            // traceback steps a lane runs above its piece before its bits count
 constexpr int kMaxSearchBlocks = 64, kMaxSyncBlocks = 2048;
 enum { R12, R23, R34, R56, R78 };
 const int kShifts[5] = {2, 6, 2, 12, 4};
@@ -241,7 +243,7 @@ __device__ __forceinline__ uint32_t acs_step(uint32_t y, uint32_t Pj, int lane, 
 }
 
 __global__ void __launch_bounds__(128) acs_kernel(const VTask* __restrict__ tasks, VResult* __restrict__ res, int ntasks, int mode,
-                                                  const uint8_t* __restrict__ images, uint2* __restrict__ decpool, uint8_t* __restrict__ decoded) {
+                                                  const uint8_t* __restrict__ images, uint2* __restrict__ decpool, uint8_t* __restrict__ decoded, int* __restrict__ walks) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= ntasks) return;
     const VTask t = tasks[warp];
@@ -272,20 +274,19 @@ __global__ void __launch_bounds__(128) acs_kernel(const VTask* __restrict__ task
             P = ((1u + a + b) >> 3) | ((1u + a + (255u ^ b)) >> 3) << 8 | ((1u + (255u ^ a) + b) >> 3) << 16 | ((1u + (255u ^ a) + (255u ^ b)) >> 3) << 24;
         }
         const int cnt = min(32, t.nsteps - base);
-        uint32_t my0 = 0, my1 = 0, w0, w1;
+        uint32_t w0, w1;      // bit i of w0 / w1: decision of state 2 i / 2 i + 1; lane 0 stores them (the store pipe has room, the integer pipe has not)
         if (cnt == 32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 y = acs_step(y, __shfl_sync(0xFFFFFFFFu, P, j), lane, selx, selm, w0, w1);
-                if (lane == j) { my0 = w0; my1 = w1; }
+                if (lane == 0) dec[base + j] = make_uint2(w0, w1);
             }
         } else {
             for (int j = 0; j < cnt; ++j) {
                 y = acs_step(y, __shfl_sync(0xFFFFFFFFu, P, j), lane, selx, selm, w0, w1);
-                if (lane == j) { my0 = w0; my1 = w1; }
+                if (lane == 0) dec[base + j] = make_uint2(w0, w1);
             }
         }
-        if (s < t.nsteps) dec[s] = make_uint2(my0, my1);      // bit i of .x / .y: decision of state 2 i / 2 i + 1
     }
     __syncwarp();
     // find_endstate (:203-220): the first state with the smallest metric -- 0 after the renormalisation
@@ -305,20 +306,58 @@ __global__ void __launch_bounds__(128) acs_kernel(const VTask* __restrict__ task
     }
     int retval = 0;
     uint8_t* out = decoded + t.out;
-    for (int n0 = (t.fs - 1) & ~31; n0 >= 0; n0 -= 32) {
-        const int n = n0 + lane;
-        uint2 w = make_uint2(0, 0);
-        if (n < t.fs) w = dec[n + 6];
-        const int jtop = min(31, t.fs - 1 - n0);
-        uint32_t mybit = 0;
-        for (int j = jtop; j >= 0; --j) {
-            const uint32_t wx = __shfl_sync(0xFFFFFFFFu, w.x, j), wy = __shfl_sync(0xFFFFFFFFu, w.y, j);
-            const int k = (((state & 1) ? wy : wx) >> (state >> 1)) & 1;
-            state = (state >> 1) | (k << 5);
-            if (lane == j) mybit = k;
-            if (n0 + j == t.fs - 6) retval = state;
+    // Traceback in 32 pieces, one per lane.  The lane of the top piece starts from the end state; every other lane starts
+    // kWarm steps above its piece from state 0 -- tracebacks from different states run into the same path within a few
+    // constraint lengths -- and the pieces are right if every lane arrived, at the top of its piece, at the state the lane
+    // above ended in (then they are the sequential traceback, by induction from the top).  If one did not: the walk below.
+    const int PL = ((t.fs + 31) / 32 + 15) & ~15;
+    const int T = (t.fs - 1) / PL;
+    const int seg_lo = lane * PL, seg_hi = min(seg_lo + PL, t.fs);
+    const bool active = lane <= T;
+    int st = state, warm_state = -1, retv = 0;
+    auto back = [&](int m) {
+        const uint2 w = dec[m + 6];
+        const int k = (((st & 1) ? w.y : w.x) >> (st >> 1)) & 1;
+        st = (st >> 1) | (k << 5);
+        return (uint32_t)k;
+    };
+    if (active && lane < T) {
+        const int nw = min(seg_hi - 1 + kWarm, t.fs - 1);
+        st = nw == t.fs - 1 ? state : 0;
+        for (int m = nw; m >= seg_hi; --m) back(m);
+        warm_state = st;
+    }
+    if (active)
+        for (int c = (seg_hi - 1) & ~15; c >= seg_lo; c -= 16) {
+            uint32_t r[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 15; i >= 0; --i)
+                if (c + i < seg_hi) {
+                    r[i >> 2] |= back(c + i) << (8 * (i & 3));
+                    if (c + i == t.fs - 6) retv = st;
+                }
+            *reinterpret_cast<uint4*>(out + c) = make_uint4(r[0], r[1], r[2], r[3]);      // (the task's bits end on a 16-byte boundary of their own)
         }
-        if (n < t.fs) out[n] = (uint8_t)mybit;
+    const int above = __shfl_down_sync(0xFFFFFFFFu, st, 1);
+    const bool ok = !active || lane == T || warm_state == above;
+    if (__all_sync(0xFFFFFFFFu, ok)) retval = __shfl_sync(0xFFFFFFFFu, retv, (t.fs - 6) / PL);
+    else {
+        for (int n0 = (t.fs - 1) & ~31; n0 >= 0; n0 -= 32) {
+            const int n = n0 + lane;
+            uint2 w = make_uint2(0, 0);
+            if (n < t.fs) w = dec[n + 6];
+            const int jtop = min(31, t.fs - 1 - n0);
+            uint32_t mybit = 0;
+            for (int j = jtop; j >= 0; --j) {
+                const uint32_t wx = __shfl_sync(0xFFFFFFFFu, w.x, j), wy = __shfl_sync(0xFFFFFFFFu, w.y, j);
+                const int k = (((state & 1) ? wy : wx) >> (state >> 1)) & 1;
+                state = (state >> 1) | (k << 5);
+                if (lane == j) mybit = k;
+                if (n0 + j == t.fs - 6) retval = state;
+            }
+            if (n < t.fs) out[n] = (uint8_t)mybit;
+        }
+        if (lane == 0) atomicAdd(walks, 1);
     }
     if (lane == 0) {
         res[warp].retval = retval;
@@ -528,8 +567,8 @@ int run_tasks(Vit* v, int ntasks) {
     CU(reserve(v->res, v->res_cap, (size_t)ntasks));
     CU(cudaMemcpyAsync(v->tasks, v->h_tasks.data(), sizeof(VTask) * ntasks, cudaMemcpyHostToDevice, st));
     const int grid = (ntasks + 3) / 4;
-    acs_kernel<<<grid, 128, 0, st>>>(v->tasks, v->res, ntasks, 0, v->images, v->decpool, v->decoded);
-    acs_kernel<<<grid, 128, 0, st>>>(v->tasks, v->res, ntasks, 1, v->images, v->decpool, v->decoded);
+    acs_kernel<<<grid, 128, 0, st>>>(v->tasks, v->res, ntasks, 0, v->images, v->decpool, v->decoded, v->flag + 1);
+    acs_kernel<<<grid, 128, 0, st>>>(v->tasks, v->res, ntasks, 1, v->images, v->decpool, v->decoded, v->flag + 1);
     v->h_res.resize(ntasks);
     v->n_tasks += ntasks;
     for (int pass = 0;; ++pass) {
@@ -544,7 +583,7 @@ int run_tasks(Vit* v, int ntasks) {
         if (!flag) break;
         v->n_repeated += flag;
         if (pass > ntasks) return api_fail(DVBS2FEC_ECUDA, "viterbi: start-state check does not settle");
-        acs_kernel<<<grid, 128, 0, st>>>(v->tasks, v->res, ntasks, 2, v->images, v->decpool, v->decoded);
+        acs_kernel<<<grid, 128, 0, st>>>(v->tasks, v->res, ntasks, 2, v->images, v->decpool, v->decoded, v->flag + 1);
     }
     CU(cudaGetLastError());
     return 0;
@@ -775,7 +814,9 @@ int dvbs2fec_dvbs_viterbi_create(int device, float ber_threshold, int max_outsyn
     v->search_out = 2 * outb;
     CU(cudaMemcpyToSymbol(cSearch, &L, sizeof L));
     CU(cudaMalloc(&v->d_last_search, kTest));
-    CU(cudaMalloc(&v->flag, sizeof(int)));
+    CU(cudaMalloc(&v->flag, 2 * sizeof(int)));
+    CU(cudaMemset(v->flag, 0, 2 * sizeof(int)));      // [0] tasks that started wrong in this pass, [1] tracebacks that fell back to the walk
+    CU(cudaDeviceSynchronize());
     CU(cudaMalloc(&v->sts_carry[0], kBuf));
     CU(cudaMalloc(&v->sts_carry[1], kBuf));
     int rc = dvbs2fec_dvbs_viterbi_reset(v.get());
@@ -861,8 +902,14 @@ int dvbs2fec_dvbs_viterbi_stats(dvbs2fec_dvbs_viterbi* v, float* ber, int* state
     return 0;
 }
 
-int dvbs2fec_dvbs_viterbi_counters(dvbs2fec_dvbs_viterbi* v, long long* tasks, long long* repeated, long long* passes) {
+int dvbs2fec_dvbs_viterbi_counters(dvbs2fec_dvbs_viterbi* v, long long* tasks, long long* repeated, long long* passes, long long* walks) {
     if (!v) return api_fail(DVBS2FEC_EINVAL, "handle is NULL");
+    if (walks) {
+        int w = 0;
+        CU(cudaSetDevice(v->device));
+        CU(cudaMemcpy(&w, v->flag + 1, sizeof(int), cudaMemcpyDeviceToHost));
+        *walks = w;
+    }
     if (tasks) *tasks = v->n_tasks;
     if (repeated) *repeated = v->n_repeated;
     if (passes) *passes = v->n_passes;
