@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(256) search_image_kernel(const int8_t* __restr
             uint8_t* img = out + phase * cSearch.per_phase + cSearch.img[c];
             if (r == R12) {       // decoder input = ber_soft_buffer + shift, running 12 / 13 bytes into the buffer behind
                 for (int p = tid; p < nread; p += 256) img[p] = buf[p + sh];
+                __syncthreads();      // the next candidate writes where this one read its last bytes
                 continue;
             }
             int lead = 0, a = 0, oo;

@@ -164,7 +164,7 @@ b2 = vit.process(np.clip(np.rint(vrng.normal(0, 40, 4 * 8192)), -127, 127).astyp
 print("dvbs viterbi", len(b1), len(b2), vit.stats(), vit.counters())
 vit.close()
 x_, y_ = dvbs_stream.conv_encode(bits_)
-tx = dvbs_stream.puncture(x_, y_, 2).astype(np.float32) * 1.2 - 0.6
+tx = dvbs_stream.puncture(x_, y_, 0).astype(np.float32) * 1.2 - 0.6
 tx = tx[:len(tx) // 2 * 2] + vrng.normal(0, 0.05, len(tx) // 2 * 2).astype(np.float32)
 dm = pkg.DVBSDemod(frame_stride=1632)
 t1 = dm.process((tx[0::2] + 1j * tx[1::2]).astype(np.complex64))
