@@ -163,10 +163,10 @@ b1 = vit.process(sv)
 b2 = vit.process(np.clip(np.rint(vrng.normal(0, 40, 4 * 8192)), -127, 127).astype(np.int8))
 print("dvbs viterbi", len(b1), len(b2), vit.stats(), vit.counters())
 vit.close()
-x_, y_ = dvbs_stream.conv_encode(bits_)
-tx = dvbs_stream.puncture(x_, y_, 0).astype(np.float32) * 1.2 - 0.6
-tx = tx[:len(tx) // 2 * 2] + vrng.normal(0, 0.05, len(tx) // 2 * 2).astype(np.float32)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_gpu_vit import dvbs_symbols  # noqa: E402
+_, csyms = dvbs_symbols(30, 0, np.random.default_rng(400), lead=14)      # (a short stream would be spent on the reference's first, wrong lock)
 dm = pkg.DVBSDemod(frame_stride=1632)
-t1 = dm.process((tx[0::2] + 1j * tx[1::2]).astype(np.complex64))
+t1 = dm.process(csyms)
 print("dvbs chain", t1.shape, dm.stats())
 dm.close()
