@@ -168,3 +168,40 @@ def test_demod_chain_matches_oracle_and_recovers_the_packets(case):
         good = sum(p.tobytes() in sent for p in got_all[24:])
         assert good >= len(got_all) - 24 - 8
     g.close()
+
+
+def test_demod_chain_reset_stats_and_errors():
+    """reset() gives the behaviour of a fresh handle; the module's statistics; ENOSPC when the TS output does not fit; bad
+    arguments are refused without touching the state"""
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    ts, syms = dvbs_symbols(30, 0, rng, lead=14)
+    g = pkg.DVBSDemod(frame_stride=1632)
+    first = g.process(syms)
+    st = g.stats()
+    assert len(first) > 100 and st["viterbi_lock"] == 1 and st["viterbi_rate"] == 0 and st["frames_done"] * 8 == len(first)
+    assert st["deframer_err"] == 0 and st["rs_avg"] == 0.0 and 0 <= st["viterbi_ber"] < 0.15
+    g.reset()
+    assert np.array_equal(g.process(syms), first)
+    g.reset()
+    L = pkg.lib()
+    x = np.ascontiguousarray(syms).view(np.float32).reshape(-1)
+    small = np.zeros(1504, np.uint8)
+    rc = L.dvbs2fec_dvbs_demod_process(g._p, len(syms), x.ctypes.data_as(C.c_void_p), small.ctypes.data_as(C.c_void_p), len(small))
+    assert rc == -28      # DVBS2FEC_ENOSPC
+    assert L.dvbs2fec_dvbs_demod_process(g._p, -1, None, None, 0) == -22
+    h = C.c_void_p()
+    assert L.dvbs2fec_dvbs_demod_create(0, 0.15, 20, 100, C.byref(h)) == -22      # frame stride is 204 or 1632
+    g.close()
+
+
+def test_deframer_argument_errors():
+    import ctypes as C
+    L = pkg.lib()
+    d = pkg.DVBSTSDeframer()
+    one = np.zeros(8, np.uint8)
+    assert L.dvbs2fec_dvbs_deframer_work(d._p, one.ctypes.data_as(C.c_void_p), -1, one.ctypes.data_as(C.c_void_p), 1) == -22
+    assert L.dvbs2fec_dvbs_deframer_work(d._p, None, 8, one.ctypes.data_as(C.c_void_p), 1) == -22
+    assert L.dvbs2fec_dvbs_deframer_work_device(d._p, one.ctypes.data_as(C.c_void_p), 1 << 24, one.ctypes.data_as(C.c_void_p), 1, None, None) == -22
+    assert d.work(np.ones(5000, np.uint8)).shape == (0, 1632)
+    d.close()
