@@ -115,6 +115,11 @@ int dvbs2fec_decode_plframes_idx(dvbs2fec_handle* h, const uint8_t* idx, int n, 
  * caller must keep d_llr, d_bb_out and d_results alive until its stream has passed the enqueued work. */
 int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n, uint8_t* d_bb_out,
                                  dvbs2fec_result* d_results, void* cuda_stream);
+/* same from PLFRAME symbols on the device (dvbs2fec_plframe_symbols complex floats per frame, as PL sync / the payload
+ * phase loop leave them: dvbs2fec_plsync_process_device, dvbs2fec_pll_process_device): demapper, LDPC, BCH, descrambler
+ * without a host copy of the symbols (S2BBToSoft::process onwards, module_dvbs2_demod.cpp:334-366) */
+int dvbs2fec_decode_plframes_device(dvbs2fec_handle* h, const float* d_plframes, int n, uint8_t* d_bb_out,
+                                    dvbs2fec_result* d_results, void* cuda_stream);
 /* number of kernel launches the last decode_batch* call on this handle enqueued */
 int dvbs2fec_last_launch_count(const dvbs2fec_handle* h);
 /* measurement aid: with profiling on, every kernel launch of decode_batch_device is bracketed by CUDA

@@ -87,6 +87,7 @@ def lib():
     L.dvbs2fec_decode_batch.argtypes = [vp, vp, C.c_int, vp, vp]
     L.dvbs2fec_decode_plframes.argtypes = [vp, vp, C.c_int, vp, vp]
     L.dvbs2fec_decode_batch_device.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.dvbs2fec_decode_plframes_device.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.dvbs2fec_quantize_plframes.argtypes = [vp, vp, C.c_int, vp]
     L.dvbs2fec_decode_plframes_idx.argtypes = [vp, vp, C.c_int, vp, vp]
     L.dvbs2fec_submit_plframe_idx.argtypes = [vp, vp, C.c_uint64]
@@ -335,6 +336,10 @@ class DVBS2Decoder:
     def decode_batch_device(self, d_llr_ptr, n, d_bb_ptr, d_res_ptr, stream_ptr=0):
         """Device pointers on this decoder's first device; enqueues on ``stream_ptr`` and returns."""
         _check(lib().dvbs2fec_decode_batch_device(self._h, d_llr_ptr, n, d_bb_ptr, d_res_ptr, stream_ptr))
+
+    def decode_plframes_device(self, d_plframes_ptr, n, d_bb_ptr, d_res_ptr, stream_ptr=0):
+        """PLFRAME symbols on the device (plframe_symbols complex floats per frame) -> BBFRAMEs on the device"""
+        _check(lib().dvbs2fec_decode_plframes_device(self._h, d_plframes_ptr, n, d_bb_ptr, d_res_ptr, stream_ptr))
 
     def set_profiling(self, on):
         _check(lib().dvbs2fec_set_profiling(self._h, int(on)))

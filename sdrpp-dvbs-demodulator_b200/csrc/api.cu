@@ -1067,6 +1067,31 @@ int dvbs2fec_decode_batch_device(dvbs2fec_handle* h, const int8_t* d_llr, int n,
     return rc;
 }
 
+// PLFRAME symbols already on the device (e.g. what dvbs2fec_pll_process_device left there): demapper, LDPC, BCH and
+// descrambler enqueued on the caller's stream, nothing crosses PCIe.  Shares the device entry point's scratch.
+int dvbs2fec_decode_plframes_device(dvbs2fec_handle* h, const float* d_plframes, int n, uint8_t* d_bb_out,
+                                    dvbs2fec_result* d_results, void* cuda_stream) {
+    if (!h || !h->configured || !d_plframes || n < 0) return fail(DVBS2FEC_EINVAL, "bad arguments");
+    DevCtx& d = *h->devs[0];
+    Slot& s = d.slot[2 * kSlots];
+    std::lock_guard<std::mutex> serial(d.dev_mu);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (d.dev_used) CU(cudaStreamWaitEvent(st, s.done, 0));
+    const int chunk = std::min(n, std::max(h->cfg.max_batch, 1));
+    int rc = reserve_slot(h, d, s, chunk, 0, false);
+    if (rc) return rc;
+    const size_t kb = h->code->kbch / 8;
+    h->last_launches = 0;
+    for (int f0 = 0; f0 < n && !rc; f0 += chunk) {
+        int m = std::min(chunk, n - f0);
+        rc = enqueue_chain(h, d, s, d_plframes + (size_t)f0 * h->plsyms * 2, nullptr, m, d_bb_out ? d_bb_out + (size_t)f0 * kb : nullptr,
+                           d_results ? d_results + f0 : nullptr, st, &h->last_launches, (uint64_t)f0);
+    }
+    CU(cudaEventRecord(s.done, st));
+    d.dev_used = true;
+    return rc;
+}
+
 // Copy into a staging batch with non-temporal stores: the CPU never reads these bytes again (the copy engine does), so
 // they need not displace the producer's working set from its caches, and the lines are written without being read
 // first.  Measured with tools/mixed_stream on the 4-GPU box: see profiles/r02_mixed_stream_*.json.

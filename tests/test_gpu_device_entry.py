@@ -132,3 +132,60 @@ def test_device_entry_on_two_streams_and_between_sync_calls():
         assert np.array_equal(b_bb[: n - 7], want_bb[: n - 7]) and np.array_equal(b_res["bch_corr"][: n - 7], want_res["bch_corr"][: n - 7])
         assert np.array_equal(c_bb, want_bb[: len(c_bb)]) and np.array_equal(c_res["ldpc_iters"], want_res["ldpc_iters"][: len(c_bb)])
     dec.close()
+
+
+def test_symbols_stay_on_the_device_from_pl_sync_to_the_bbframe():
+    """PL sync (K7) -> payload phase loop (K8) -> demapper, LDPC, BCH, descrambler (dvbs2fec_decode_plframes_device), every
+    buffer a device buffer and one stream: the BBFRAMEs are the transmitted ones (after the loop has pulled in) and equal
+    to what the host-buffer entry points give for the same symbols"""
+    import plstream
+    rng = np.random.default_rng(77)
+    modcod, short, n, codenum = 4, True, 6, 3
+    dec = pkg.DVBS2Decoder(max_batch=16)
+    dec.setDemodParams(modcod, short, False, 25)
+    pay = rng.integers(0, 256, (n, dec.kbch // 8), dtype=np.uint8)
+    pls = modcod << 2 | 2
+    rn = plstream.pl_rn(codenum)
+    frames = []
+    for i in range(n):
+        sym = pkg.modulate(modcod, short, False, pkg.encode_fecframe(modcod, short, pay[i])).view(np.complex64)
+        frames.append(np.concatenate([plstream.plheader(pls), sym[90:] * np.array([1, 1j, -1, -1j])[rn[:len(sym) - 90]]]))
+    x = np.concatenate([0.3 * (rng.normal(size=1500) + 1j * rng.normal(size=1500))] + frames + [frames[0][:200]]).astype(np.complex64)
+    x = x * np.exp(1j * (0.4 + 2 * np.pi * 1.5e-5 * np.arange(len(x))))
+    sigma = 0.667 * np.sqrt(0.5 / 10 ** 1.4)
+    x = (x + sigma * (rng.normal(size=len(x)) + 1j * rng.normal(size=len(x)))).astype(np.complex64)
+    # host-buffer entry points, stage by stage
+    h = pkg.S2PLSyncBlock(90, False)
+    h.pll_set_params(0.004, modcod, short, False, codenum)
+    fr = h.process(x).reshape(-1, h.raw_frame_size)
+    out, _ = h.pll_process(fr)
+    bb_host, res_host = dec.decode_plframes(out.view(np.float32).reshape(len(fr), -1))
+    h.close()
+    # the same on device buffers
+    g = pkg.S2PLSyncBlock(90, False)
+    g.pll_set_params(0.004, modcod, short, False, codenum)
+    rfs = g.raw_frame_size
+    assert rfs == dec.plframe_symbols
+    st = torch.cuda.Stream()
+    d_x = torch.from_numpy(x.view(np.float32).copy()).cuda()
+    d_fr = torch.zeros((n + 2) * rfs * 2, dtype=torch.float32, device="cuda")
+    d_pl = torch.zeros_like(d_fr)
+    d_n = torch.zeros(1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    g.process_device(d_x.data_ptr(), len(x), d_fr.data_ptr(), n + 2, d_n.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    nfr = int(d_n.item())
+    assert nfr == len(fr) >= n - 1
+    d_bb = torch.zeros((nfr, dec.kbch // 8), dtype=torch.uint8, device="cuda")
+    d_res = torch.zeros((nfr, 16), dtype=torch.uint8, device="cuda")
+    g.pll_process_device(d_fr.data_ptr(), nfr, rfs, d_pl.data_ptr(), 0, st.cuda_stream)
+    dec.decode_plframes_device(d_pl.data_ptr(), nfr, d_bb.data_ptr(), d_res.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    bb = d_bb.cpu().numpy()
+    res = d_res.cpu().numpy().view(pkg.RESULT_DTYPE).reshape(-1)
+    assert np.array_equal(bb, bb_host) and np.array_equal(res["ldpc_iters"], res_host["ldpc_iters"])
+    assert np.array_equal(res["bch_corr"], res_host["bch_corr"])
+    good = [i for i in range(nfr) if any(np.array_equal(bb[i], p) for p in pay)]
+    assert len(good) >= nfr - 1 and (res["bch_corr"][1:] >= 0).all()
+    g.close()
+    dec.close()
