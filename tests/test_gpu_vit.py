@@ -205,3 +205,23 @@ def test_deframer_argument_errors():
     assert L.dvbs2fec_dvbs_deframer_work_device(d._p, one.ctypes.data_as(C.c_void_p), 1 << 24, one.ctypes.data_as(C.c_void_p), 1, None, None) == -22
     assert d.work(np.ones(5000, np.uint8)).shape == (0, 1632)
     d.close()
+
+
+def test_viterbi_calls_longer_than_the_internal_batches():
+    """2100 locked blocks in one call (the decode batch is 2048 blocks) and 150 blocks of noise (search batches grow to 64
+    blocks): equal to the oracle"""
+    rng = np.random.default_rng(808)
+    bits = rng.integers(0, 2, 4096 * 2101, dtype=np.uint8)
+    s = dvbs_stream.inner_softs(bits, 0, rng, sigma=14.0)[:2100 * 8192]
+    g = pkg.DVBSViterbi()
+    got = g.process(s)
+    want = OrcViterbi().process(s)
+    assert np.array_equal(got, want) and g.stats()[1:3] == (1, 0)
+    g.reset()
+    noise = np.clip(np.rint(rng.normal(0, 40, 150 * 8192)), -127, 127).astype(np.int8)
+    o = OrcViterbi()
+    assert len(g.process(noise)) == len(o.process(noise)) == 0
+    assert same_stats(g.stats(), o.stats())
+    tail = s[:8 * 8192]
+    assert np.array_equal(g.process(tail), o.process(tail)) and same_stats(g.stats(), o.stats())
+    g.close()
