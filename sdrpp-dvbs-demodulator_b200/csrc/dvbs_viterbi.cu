@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -49,7 +50,7 @@ constexpr int kTest = 2048;           // TEST_BITS_LENGTH
 constexpr int kGuessSteps = 326;      // trellis steps the guess kernel runs (320 + the 6 behind the block)
 constexpr int kSearchTasks = 52;
 constexpr int kWarm = 128;            // traceback steps a lane runs above its piece before its bits count
-constexpr int kMaxSearchBlocks = 64, kMaxSyncBlocks = 2048;
+constexpr int kMaxSearchBlocks = 64, kMaxSyncBlocks = 8192;
 enum { R12, R23, R34, R56, R78 };
 const int kShifts[5] = {2, 6, 2, 12, 4};
 const float kRatio[5] = {2.5f, 3.5f, 5.0f, 8.0f, 10.0f};
@@ -235,10 +236,10 @@ __device__ __forceinline__ uint32_t acs_step(uint32_t y, uint32_t Pj, int lane, 
     const uint32_t mq = 63u * 0x10001u - mp;                                         // (63 - metric) | metric << 16
     const uint32_t q0 = (x0 + mp) & 0x00FF00FFu;                                     // m0 | m2 << 16, each wrapped to 8 bits as the reference's
     const uint32_t q1 = (x1 + mq) & 0x00FF00FFu;                                     // m1 | m3 << 16
-    const uint32_t diff = q0 + 0x01000100u - q1;                                     // bit 8 / 24: m0 >= m1 / m2 >= m3
-    w0 = __ballot_sync(0xFFFFFFFFu, (diff & 0x100u) != 0);
-    w1 = __ballot_sync(0xFFFFFFFFu, (diff & 0x1000000u) != 0);
     uint32_t yn = __vminu2(q0, q1);
+    const uint32_t e = yn ^ q1;                                                      // a half is 0 where m1 (m3) was taken: m0 >= m1 (m2 >= m3)
+    w0 = __ballot_sync(0xFFFFFFFFu, (e & 0xFFFFu) == 0);
+    w1 = __ballot_sync(0xFFFFFFFFu, (e & 0xFFFF0000u) == 0);
     const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, min(yn & 0xFFFFu, yn >> 16));  // renormalize (:25-38)
     return yn - m * 0x10001u;
 }
@@ -529,6 +530,7 @@ struct dvbs2fec_dvbs_viterbi {
     int8_t* d_last_search = nullptr;      // first 2048 soft bits of the last block the search ran on
     int have_last_search = 0;
     int search_batch = 1;
+    int max_sync_blocks = kMaxSyncBlocks;      // DVBS2FEC_VIT_MAX_BATCH overrides (tests: batches cut inside a call)
     long long n_tasks = 0, n_repeated = 0, n_passes = 0;      // diagnostics: decode tasks run, tasks repeated from a corrected start, check passes
     Pattern pat[kPatterns];
     SearchLayout lay;
@@ -792,6 +794,7 @@ int dvbs2fec_dvbs_viterbi_create(int device, float ber_threshold, int max_outsyn
     v->device = device;
     v->thr = ber_threshold;
     v->max_outsync = (float)max_outsync;
+    if (const char* e = getenv("DVBS2FEC_VIT_MAX_BATCH")) v->max_sync_blocks = std::max(1, std::min(atoi(e), kMaxSyncBlocks));
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
     build_patterns(v->pat);
@@ -856,7 +859,7 @@ int dvbs2fec_dvbs_viterbi_process_device(dvbs2fec_dvbs_viterbi* v, int count, co
             v->search_batch = v->state == 1 ? 1 : std::min(v->search_batch * 4, kMaxSearchBlocks);
         }
         if (v->state == 1 && pos < nb) {
-            const int n = std::min(nb - pos, kMaxSyncBlocks);
+            const int n = std::min(nb - pos, v->max_sync_blocks);
             int accepted = 0;
             int rc = run_sync(v, d_in + (size_t)pos * kBuf, n, d_out, &oidx, &accepted);
             if (rc) return rc;

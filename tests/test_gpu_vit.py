@@ -207,12 +207,13 @@ def test_deframer_argument_errors():
     d.close()
 
 
-def test_viterbi_calls_longer_than_the_internal_batches():
-    """2100 locked blocks in one call (the decode batch is 2048 blocks) and 150 blocks of noise (search batches grow to 64
-    blocks): equal to the oracle"""
+def test_viterbi_calls_longer_than_the_internal_batches(monkeypatch):
+    """700 locked blocks in one call with the decode batch limited to 256 blocks (8192 by default), and 150 blocks of
+    noise (search batches grow to 64 blocks): equal to the oracle"""
     rng = np.random.default_rng(808)
-    bits = rng.integers(0, 2, 4096 * 2101, dtype=np.uint8)
-    s = dvbs_stream.inner_softs(bits, 0, rng, sigma=14.0)[:2100 * 8192]
+    bits = rng.integers(0, 2, 4096 * 701, dtype=np.uint8)
+    s = dvbs_stream.inner_softs(bits, 0, rng, sigma=14.0)[:700 * 8192]
+    monkeypatch.setenv("DVBS2FEC_VIT_MAX_BATCH", "256")
     g = pkg.DVBSViterbi()
     got = g.process(s)
     want = OrcViterbi().process(s)

@@ -49,6 +49,18 @@ for rate in range(5):
     print(res["viterbi"][-1], flush=True)
     g.close()
 
+# call size: a task is a warp, so the kernel needs a few thousand blocks in a call to fill the GPU
+res["viterbi_call_size"] = []
+rng = np.random.default_rng(0)
+base = dvbs_stream.inner_softs(rng.integers(0, 2, 4096 * 68, dtype=np.uint8), 0, rng, sigma=14.0)[:66 * 8192]
+for blocks in (66, 264, 528, 1056, 2112, 4224, 8184):
+    s = np.tile(base, blocks // 66); n = len(s)
+    d_in = torch.from_numpy(s).cuda(); d_out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    g = pkg.DVBSViterbi(); g.process_device(d_in.data_ptr(), n, d_out.data_ptr())
+    ms = timed(lambda: g.process_device(d_in.data_ptr(), n, d_out.data_ptr()), 5)
+    res["viterbi_call_size"].append(dict(rate="1/2", blocks=blocks, gpu_ms=round(ms, 3), blocks_per_s=round(blocks / ms * 1e3), decoded_mbit_s=round(blocks * 4096 / ms / 1e3, 1)))
+    print(res["viterbi_call_size"][-1], flush=True); g.close()
+
 # the search on noise: nothing locks, every block runs the 52 candidates
 rng = np.random.default_rng(9)
 nb = 256
