@@ -23,6 +23,9 @@ Vit, Def, Out = (RefViterbi, RefDeframer, RefOuter) if have_ref else (OrcViterbi
 res = dict(cpu_kind="reference" if have_ref else "oracle", viterbi=[], search=None, deframer=None, chain=[])
 
 def timed(fn, reps):
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 0.05:      # the host work between the sections lets the GPU clock down: warm up first
+        fn()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(reps): fn()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / reps * 1e3
