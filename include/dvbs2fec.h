@@ -342,7 +342,9 @@ int dvbs2fec_dvbs_viterbi_reset(dvbs2fec_dvbs_viterbi* v);
  * every 6826 at rate 5/6) keep the caller's content.  Unlike the reference the input is not rotated in place.  Host
  * buffers, synchronous. */
 int dvbs2fec_dvbs_viterbi_process(dvbs2fec_dvbs_viterbi* v, int count, const int8_t* in, uint8_t* out);
-/* same on device buffers (no PCIe traffic but the per-block BER counts); synchronous: the lock state machine runs on the host */
+/* same on device buffers (no PCIe traffic but the per-block BER counts); synchronous: the lock state machine runs on the host.
+ * The work runs on a stream of the handle's: d_in must be complete when the call is made, d_out is complete when it returns.
+ * A handle is used by one thread at a time (as the reference's object is). */
 int dvbs2fec_dvbs_viterbi_process_device(dvbs2fec_dvbs_viterbi* v, int count, const int8_t* d_in, uint8_t* d_out);
 /* Viterbi_DVBS::ber(), getState() (0 searching, 1 locked), rate() (0..4 = 1/2, 2/3, 3/4, 5/6, 7/8) and the lock's phase
  * (0 / 1 = 0 / 90 degrees), puncturing shift and count of bad blocks; any pointer may be NULL */
