@@ -218,3 +218,70 @@ def test_cuda_reproduces_reference_dvbs_outer():
     assert np.array_equal(o, g["ts_1632"]) and np.array_equal(e, g["err_1632"])
     o, e = pkg.DVBSOuterDecoder().process(frames.reshape(-1), len(g["err_204"]) // 8, 204)
     assert np.array_equal(o, g["ts_204"]) and np.array_equal(e, g["err_204"])
+
+
+# ---- rows 8(f)-2 / 8(f)-3: PL sync, PLHEADER demodulation, coarse frequency error, payload phase loop ----------------------
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def test_oracle_reproduces_reference_pl_front_end():
+    from test_plsync_oracle import OrcSync, f32
+    from test_pll_oracle import OrcPll
+    g = load("plfront_s36p")
+    slots, pilots, codenum, pls, cut = int(g["slots"]), bool(g["pilots"]), int(g["codenum"]), int(g["pls"]), int(g["cut"])
+    o = orclib.oracle()
+    s = OrcSync(slots, pilots)
+    y1 = s.process(g["x"][:cut]); st1 = s.stats()
+    y2 = s.process(g["x"][cut:]); st2 = s.stats()
+    assert [len(y1), len(y2)] == g["nsym"].tolist() and np.array_equal(np.array([st1, st2], np.float64), g["sync_stats"])
+    fr = np.concatenate([y1, y2]).reshape(-1, s.rfs)
+    assert np.array_equal(_sha(fr), g["frames_sha"])
+    import plstream
+    rn = plstream.pl_rn(codenum)
+    hh = o.orc_plhdr_create(0.004)
+    pll = OrcPll(0.004, "qpsk", slots, pilots, pls, codenum)
+    for k in range(len(fr)):
+        hdr, res, loop = np.zeros(180, np.float32), np.zeros(3, np.int32), np.zeros(2, np.float32)
+        o.orc_plhdr_process(hh, s.rfs, f32(fr[k]), hdr, res, loop)
+        assert np.array_equal(hdr.view(np.uint32), g["hdr"][k].view(np.uint32)) and list(res) == g["hdr_res"][k].tolist()
+        assert np.array_equal(loop.view(np.uint32), g["hdr_loop"][k].view(np.uint32))
+        fed = o.orc_coarse_fed(f32(fr[k]), s.rfs, int(pilots), pls, rn)
+        assert np.float32(fed).view(np.uint32) == g["fed"][k].view(np.uint32)
+        out, st = pll.process(fr[k])
+        assert np.array_equal(out.view(np.uint32), g["pll_out"][k].view(np.uint32))
+        assert np.array_equal(st.view(np.uint32), g["pll_state"][k].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_pl_front_end():
+    """PL sync and the coarse frequency error bit for bit; PLHEADER symbols to 1e-4 with the PLS fields exact; the payload
+    phase loop frame by frame from the reference's loop state, with the tolerances of tests/test_gpu_pll.py"""
+    g = load("plfront_s36p")
+    slots, pilots, codenum, pls, cut = int(g["slots"]), bool(g["pilots"]), int(g["codenum"]), int(g["pls"]), int(g["cut"])
+    b = pkg.S2PLSyncBlock(slots, pilots)
+    y1 = b.process(g["x"][:cut]); st1 = (b.current_position, b.best_match)
+    y2 = b.process(g["x"][cut:]); st2 = (b.current_position, b.best_match)
+    assert [len(y1), len(y2)] == g["nsym"].tolist()
+    assert st1 == (int(g["sync_stats"][0][1]), g["sync_stats"][0][2]) and st2 == (int(g["sync_stats"][1][1]), g["sync_stats"][1][2])
+    assert b.raw_frame_size == int(g["sync_stats"][0][0])
+    fr = np.concatenate([y1, y2]).reshape(-1, b.raw_frame_size)
+    assert np.array_equal(_sha(fr), g["frames_sha"])
+    b.plhdr_set_params(0.004)
+    hdr, res, loop = b.plhdr_process(fr)
+    assert np.abs(hdr.view(np.float32).reshape(len(fr), 180) - g["hdr"]).max() < 1e-4
+    assert np.array_equal(res[:, :3], g["hdr_res"]) and np.abs(loop - g["hdr_loop"][-1]).max() < 1e-4
+    fed = b.coarse_fed(fr, pilots, pls, codenum)
+    assert np.array_equal(np.asarray(fed, np.float32).view(np.uint32), g["fed"].view(np.uint32))
+    b.pll_set_params(0.004, 4, True, pilots, codenum)
+    total = g["pll_out"].shape[1]
+    assert b.pll_frame_symbols == total
+    ws = np.zeros(3, np.float32)
+    for k in range(len(fr)):
+        b.pll_set_state(float(ws[0]), float(ws[1]))
+        got, st = b.pll_process(fr[k:k + 1])
+        ws = g["pll_state"][k]
+        dev = np.abs(got[0, :total] - g["pll_out"][k])
+        assert dev[:64].max() < 5e-6 and np.median(dev) < 1e-4 and np.mean(dev > 1e-3) < 0.02
+        assert abs((st[0, 0] - ws[0] + np.pi) % (2 * np.pi) - np.pi) < 2e-2 and abs(st[0, 1] - ws[1]) < 1e-4 and abs(st[0, 2] - ws[2]) < 1e-4
+    b.close()

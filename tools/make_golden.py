@@ -120,6 +120,39 @@ def ts_parser_fixture(kind, kbch, seed):
                 stats=np.array(stats, np.int32))
 
 
+def plfront_fixture(seed):
+    """the reference's PL front end (dvbs2_pl_sync.cpp, dvbs2_plhdr_demod.cpp, dvbs2_fed.h, dvbs2_pll.cpp) on a stream of
+    five short QPSK 1/2 PLFRAMEs with pilots behind 777 symbols of junk, Gold code 5, a carrier offset: frames as PL sync
+    delivers them over two calls, and per frame the PLHEADER demodulator's output, the coarse frequency error and the
+    payload phase loop's output and state"""
+    import plstream
+    from test_plsync_oracle import RefSync, f32
+    from test_pll_oracle import RefPll
+    rng = np.random.default_rng(seed)
+    slots, pilots, codenum = 36, True, 5
+    pls = (4 << 2) | 2 | 1
+    x = plstream.stream(pls, slots, pilots, 5, rng, esn0_db=9.0, lead=777, cfo=1e-4, phase=0.3, codenum=codenum)
+    r = orclib.ref()
+    s = RefSync(slots, pilots)
+    cut = 9000
+    y1 = s.process(x[:cut]); st1 = s.stats()
+    y2 = s.process(x[cut:]); st2 = s.stats()
+    rfs = s.rfs
+    fr = np.concatenate([y1, y2]).reshape(-1, rfs)
+    n = len(fr)
+    hh = r.ref_plhdr_create(0.004)
+    hdr, res, loop, fed = np.zeros((n, 180), np.float32), np.zeros((n, 3), np.int32), np.zeros((n, 2), np.float32), np.zeros(n, np.float32)
+    pll = RefPll(0.004, "qpsk", slots, pilots, pls, codenum)
+    pout, pst = np.zeros((n, pll.total), np.complex64), np.zeros((n, 3), np.float32)
+    for k in range(n):
+        r.ref_plhdr_process(hh, rfs, f32(fr[k]), hdr[k], res[k], loop[k])
+        fed[k] = r.ref_coarse_fed(f32(fr[k]), rfs, int(pilots), pls, codenum)
+        pout[k], pst[k] = pll.process(fr[k])
+    return dict(slots=slots, pilots=int(pilots), codenum=codenum, pls=pls, x=x, cut=cut, nsym=np.array([len(y1), len(y2)]),
+                sync_stats=np.array([st1, st2], np.float64), nframes=n,
+                frames_sha=np.frombuffer(hashlib.sha256(np.ascontiguousarray(fr).tobytes()).digest(), np.uint8), hdr=hdr, hdr_res=res, hdr_loop=loop, fed=fed, pll_out=pout, pll_state=pst)
+
+
 def dvbs_vit_fixture(rate, phase, lead, seed):
     """the reference's Viterbi_DVBS (viterbi_all.cpp) on two blocks of noise, then a signal: calls of 2, 1, 3, 1 and 5 blocks;
     decoded bits (packed) and ber / state / rate / phase / shift / invalid after every call"""
@@ -182,6 +215,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "tsparse_odd_s14.npz"), **ts_parser_fixture("ts_odd", 3072, 5))
     np.savez_compressed(os.path.join(OUT, "tsparse_gse_n12.npz"), **ts_parser_fixture("gse", 32208, 8))
     np.savez_compressed(os.path.join(OUT, "tsparse_gsemix_s12.npz"), **ts_parser_fixture("gse_mixed", 7032, 21))
+    np.savez_compressed(os.path.join(OUT, "plfront_s36p.npz"), **plfront_fixture(35))
     np.savez_compressed(os.path.join(OUT, "dvbs_vit_r12_p90.npz"), **dvbs_vit_fixture(0, 1, 1, 31))
     np.savez_compressed(os.path.join(OUT, "dvbs_vit_r23.npz"), **dvbs_vit_fixture(1, 0, 4, 32))
     np.savez_compressed(os.path.join(OUT, "dvbs_vit_r56.npz"), **dvbs_vit_fixture(3, 0, 7, 33))
