@@ -240,7 +240,9 @@ def test_oracle_reproduces_reference_pl_front_end():
     import plstream
     rn = plstream.pl_rn(codenum)
     hh = o.orc_plhdr_create(0.004)
-    pll = OrcPll(0.004, "qpsk", slots, pilots, pls, codenum)
+    import test_pll_oracle
+    test_pll_oracle.CONST["32apsk89"] = (5, 5, 2.54, 4.33)      # MODCOD 27's ring ratios
+    pll = OrcPll(0.004, "32apsk89", slots, pilots, pls, codenum)
     for k in range(len(fr)):
         hdr, res, loop = np.zeros(180, np.float32), np.zeros(3, np.int32), np.zeros(2, np.float32)
         o.orc_plhdr_process(hh, s.rfs, f32(fr[k]), hdr, res, loop)
@@ -273,7 +275,7 @@ def test_cuda_reproduces_reference_pl_front_end():
     assert np.array_equal(res[:, :3], g["hdr_res"]) and np.abs(loop - g["hdr_loop"][-1]).max() < 1e-4
     fed = b.coarse_fed(fr, pilots, pls, codenum)
     assert np.array_equal(np.asarray(fed, np.float32).view(np.uint32), g["fed"].view(np.uint32))
-    b.pll_set_params(0.004, 4, True, pilots, codenum)
+    b.pll_set_params(0.004, int(g["modcod"]), True, pilots, codenum)
     total = g["pll_out"].shape[1]
     assert b.pll_frame_symbols == total
     ws = np.zeros(3, np.float32)

@@ -122,16 +122,18 @@ def ts_parser_fixture(kind, kbch, seed):
 
 def plfront_fixture(seed):
     """the reference's PL front end (dvbs2_pl_sync.cpp, dvbs2_plhdr_demod.cpp, dvbs2_fed.h, dvbs2_pll.cpp) on a stream of
-    five short QPSK 1/2 PLFRAMEs with pilots behind 777 symbols of junk, Gold code 5, a carrier offset: frames as PL sync
+    five short 32APSK 8/9 PLFRAMEs (36 slots) with pilots behind 777 symbols of junk, Gold code 5, a carrier offset: frames as PL sync
     delivers them over two calls, and per frame the PLHEADER demodulator's output, the coarse frequency error and the
     payload phase loop's output and state"""
     import plstream
     from test_plsync_oracle import RefSync, f32
+    import test_pll_oracle
     from test_pll_oracle import RefPll
     rng = np.random.default_rng(seed)
-    slots, pilots, codenum = 36, True, 5
-    pls = (4 << 2) | 2 | 1
-    x = plstream.stream(pls, slots, pilots, 5, rng, esn0_db=9.0, lead=777, cfo=1e-4, phase=0.3, codenum=codenum)
+    slots, pilots, codenum, modcod = 36, True, 5, 27
+    pls = (modcod << 2) | 2 | 1
+    x = plstream.stream(pls, slots, pilots, 5, rng, esn0_db=16.0, lead=777, cfo=1e-4, phase=0.3, codenum=codenum, bits=3)
+    test_pll_oracle.CONST["32apsk89"] = (5, 5, 2.54, 4.33)      # MODCOD 27's ring ratios (modcod_to_cfg.cpp:124-125)
     r = orclib.ref()
     s = RefSync(slots, pilots)
     cut = 9000
@@ -142,13 +144,13 @@ def plfront_fixture(seed):
     n = len(fr)
     hh = r.ref_plhdr_create(0.004)
     hdr, res, loop, fed = np.zeros((n, 180), np.float32), np.zeros((n, 3), np.int32), np.zeros((n, 2), np.float32), np.zeros(n, np.float32)
-    pll = RefPll(0.004, "qpsk", slots, pilots, pls, codenum)
+    pll = RefPll(0.004, "32apsk89", slots, pilots, pls, codenum)
     pout, pst = np.zeros((n, pll.total), np.complex64), np.zeros((n, 3), np.float32)
     for k in range(n):
         r.ref_plhdr_process(hh, rfs, f32(fr[k]), hdr[k], res[k], loop[k])
         fed[k] = r.ref_coarse_fed(f32(fr[k]), rfs, int(pilots), pls, codenum)
         pout[k], pst[k] = pll.process(fr[k])
-    return dict(slots=slots, pilots=int(pilots), codenum=codenum, pls=pls, x=x, cut=cut, nsym=np.array([len(y1), len(y2)]),
+    return dict(slots=slots, pilots=int(pilots), codenum=codenum, pls=pls, modcod=modcod, x=x, cut=cut, nsym=np.array([len(y1), len(y2)]),
                 sync_stats=np.array([st1, st2], np.float64), nframes=n,
                 frames_sha=np.frombuffer(hashlib.sha256(np.ascontiguousarray(fr).tobytes()).digest(), np.uint8), hdr=hdr, hdr_res=res, hdr_loop=loop, fed=fed, pll_out=pout, pll_state=pst)
 
