@@ -279,6 +279,30 @@ int dvbs2fec_pll_process_multi_device(int nstreams, dvbs2fec_plsync* const* objs
 /* diagnostic: evaluation rounds the last call needed (two per block of 32 symbols is the minimum) */
 int dvbs2fec_pll_rounds(dvbs2fec_plsync* p);
 
+/* ---- the decode stage of the DVB-S2 module in one call: DVBS2Demod::process (dvbs2/module_dvbs2_demod.cpp:300-367) behind
+ *      its sample-domain front end.  count clock-recovered symbols (re, im) -> PL sync -> per frame: coarse frequency
+ *      error, payload phase loop (with PL descrambling), PLHEADER demodulation, demapper, LDPC, BCH, BB descrambler ->
+ *      BBFRAMEs of kbch / 8 bytes, in stream order.  Symbols cross PCIe once; everything between them and the BBFRAMEs
+ *      stays on the device, on one stream, stage after stage in the reference's order.  One device (a stream of symbols
+ *      is a recurrence).  Left to the caller: feeding fed_err to its frequency shifter (:302-313).  Not reproduced: the
+ *      module's wait for 16 frames before it decodes (SURVEY.md note N1) -- every frame a call completes is decoded by it. ---- */
+typedef struct dvbs2fec_s2_demod dvbs2fec_s2_demod;
+int dvbs2fec_s2_demod_create(const dvbs2fec_config* cfg, dvbs2fec_s2_demod** out);
+void dvbs2fec_s2_demod_destroy(dvbs2fec_s2_demod* p);
+/* DVBS2Demod::setDemodParams (:118-168) and the loop bandwidths / Gold code DVBS2Demod::init hands its blocks (:59-65);
+ * the PL sync state starts over, the phase loops keep their state (as the reference's do) */
+int dvbs2fec_s2_demod_set_params(dvbs2fec_s2_demod* p, int modcod, int shortframes, int pilots, int max_trials, float pll_loop_bw,
+                                 float plhdr_loop_bw, int codenum);
+/* S2PLSyncBlock::reset + S2PLLBlock::reset */
+int dvbs2fec_s2_demod_reset(dvbs2fec_s2_demod* p);
+int dvbs2fec_s2_demod_bbframe_bytes(const dvbs2fec_s2_demod* p);            /* kbch / 8 */
+int dvbs2fec_s2_demod_max_frames(const dvbs2fec_s2_demod* p, int count);    /* frames a call with count symbols can complete */
+/* returns the frames completed and decoded (<= max_frames, which must be at least dvbs2fec_s2_demod_max_frames(count));
+ * bb_out: max_frames * kbch / 8 bytes; optional per frame: results, fed_err (dvbs2_pilot_coarse_fed's value), plhdr (four
+ * ints: detect_modcod, detect_shortframes, detect_pilots, PLS index).  Host buffers, synchronous. */
+int dvbs2fec_s2_demod_process(dvbs2fec_s2_demod* p, int count, const float* syms, uint8_t* bb_out, int max_frames,
+                              dvbs2fec_result* results, float* fed_err, int32_t* plhdr);
+
 /* ---- DVB-S legacy chain, the byte-domain half: the body of the frame loop of
  *      DVBSDemod::process (dvbs/module_dvbs_demod.cpp:91-106) -- convolutional deinterleaver
  *      (DVBSInterleaving::deinterleave, dvbs/dvbs_interleaving.h:57-70), eight RS(204,188) decodes (DVBSReedSolomon::decode,

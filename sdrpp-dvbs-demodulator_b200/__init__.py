@@ -161,6 +161,14 @@ def lib():
     L.dvbs2fec_dvbs_viterbi_counters.argtypes = [vp] + [C.POINTER(C.c_longlong)] * 4
     L.dvbs2fec_dvbs_sts_process.argtypes = [vp, C.c_int, vp, vp]
     L.dvbs2fec_dvbs_sts_process_device.argtypes = [vp, C.c_int, vp, vp]
+    L.dvbs2fec_s2_demod_create.argtypes = [vp, C.POINTER(vp)]
+    L.dvbs2fec_s2_demod_destroy.argtypes = [vp]
+    L.dvbs2fec_s2_demod_destroy.restype = None
+    L.dvbs2fec_s2_demod_set_params.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
+    L.dvbs2fec_s2_demod_reset.argtypes = [vp]
+    L.dvbs2fec_s2_demod_bbframe_bytes.argtypes = [vp]
+    L.dvbs2fec_s2_demod_max_frames.argtypes = [vp, C.c_int]
+    L.dvbs2fec_s2_demod_process.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
     L.dvbs2fec_dvbs_demod_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(vp)]
     L.dvbs2fec_dvbs_demod_destroy.argtypes = [vp]
     L.dvbs2fec_dvbs_demod_destroy.restype = None
@@ -771,3 +779,46 @@ class DVBSDemod:
         _check(lib().dvbs2fec_dvbs_demod_stats(self._p, C.byref(b), C.byref(i[0]), C.byref(i[1]), C.byref(r), C.byref(i[2]), C.byref(i[3]), C.byref(i[4])))
         return dict(viterbi_ber=b.value, viterbi_lock=i[0].value, viterbi_rate=i[1].value, rs_avg=r.value, deframer_err=i[2].value,
                     frames_found=i[3].value, frames_done=i[4].value)
+
+
+class DVBS2DemodStage:
+    """The decode stage of dsp::dvbs2::DVBS2Demod::process (dvbs2/module_dvbs2_demod.cpp:300-367) behind its sample-domain
+    front end, on the device: symbols -> PL sync -> coarse FED, phase loop, PLHEADER demodulation, demapper, LDPC, BCH,
+    descrambler -> BBFRAMEs."""
+
+    def __init__(self, device=None, max_batch=1024, max_trials=25):
+        cfg = Config()
+        if device is not None:
+            cfg.n_devices, cfg.devices[0] = 1, device
+        cfg.max_batch, cfg.max_trials = max_batch, max_trials
+        self._p = C.c_void_p()
+        _check(lib().dvbs2fec_s2_demod_create(C.byref(cfg), C.byref(self._p)))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().dvbs2fec_s2_demod_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setDemodParams(self, modcod, shortframes, pilots, max_trials=25, pll_loop_bw=0.004, plhdr_loop_bw=0.004, codenum=0):
+        _check(lib().dvbs2fec_s2_demod_set_params(self._p, modcod, int(shortframes), int(pilots), max_trials, pll_loop_bw, plhdr_loop_bw, codenum))
+        self.kb = lib().dvbs2fec_s2_demod_bbframe_bytes(self._p)
+
+    def reset(self):
+        _check(lib().dvbs2fec_s2_demod_reset(self._p))
+
+    def process(self, syms):
+        """complex symbols -> (bbframes [n][kbch / 8], results [n], coarse frequency errors [n], PLHEADER fields [n][4])"""
+        x = np.ascontiguousarray(syms, np.complex64)
+        m = lib().dvbs2fec_s2_demod_max_frames(self._p, len(x))
+        bb = np.zeros((m, self.kb), np.uint8)
+        res = np.zeros(m, RESULT_DTYPE)
+        fed = np.zeros(m, np.float32)
+        hdr = np.zeros((m, 4), np.int32)
+        n = _check(lib().dvbs2fec_s2_demod_process(self._p, len(x), _ptr(x), _ptr(bb), m, _ptr(res), _ptr(fed), _ptr(hdr)))
+        return bb[:n], res[:n], fed[:n], hdr[:n]

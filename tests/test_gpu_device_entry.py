@@ -189,3 +189,68 @@ def test_symbols_stay_on_the_device_from_pl_sync_to_the_bbframe():
     assert len(good) >= nfr - 1 and (res["bch_corr"][1:] >= 0).all()
     g.close()
     dec.close()
+
+
+@pytest.mark.parametrize("case", [(4, True, False, 3, 0), (4, True, True, 0, 1), (12, True, False, 7, 2)])
+def test_s2_demod_stage_in_one_call(case):
+    """dvbs2fec_s2_demod_process (symbols -> BBFRAMEs, the module's process() behind its sample-domain front end) over two
+    calls cut inside a frame: the same frames, BBFRAME bytes, results, coarse frequency errors and PLHEADER fields as the
+    stages called one after the other through their host-buffer entry points; and the transmitted payloads come back"""
+    import plstream
+    modcod, short, pilots, codenum, seed = case
+    rng = np.random.default_rng(500 + seed)
+    n = 6
+    dec = pkg.DVBS2Decoder(max_batch=16)
+    dec.setDemodParams(modcod, short, pilots, 25)
+    info = pkg.modcod_info(modcod, short, pilots)
+    pay = rng.integers(0, 256, (n, dec.kbch // 8), dtype=np.uint8)
+    pls = modcod << 2 | int(short) << 1 | int(pilots)
+    rn = plstream.pl_rn(codenum)
+    frames = []
+    for i in range(n):
+        sym = pkg.modulate(modcod, short, pilots, pkg.encode_fecframe(modcod, short, pay[i])).view(np.complex64).copy()
+        body = sym[90:]
+        if pilots:      # the in-tree modulator leaves the pilot blocks empty: unmodulated pilots (1 + j) / sqrt 2, scaled as the payload
+            k = np.arange(len(body)) % (1440 + 36)
+            body[k >= 1440] = (1 + 1j) / np.sqrt(2) * np.abs(body[0])
+        frames.append(np.concatenate([plstream.plheader(pls) * np.abs(body[0]), body * np.array([1, 1j, -1, -1j])[rn[:len(body)]]]))
+    x = np.concatenate([0.3 * (rng.normal(size=1500) + 1j * rng.normal(size=1500))] + frames + [frames[0][:300]]).astype(np.complex64)
+    x = x * np.exp(1j * (0.4 + 2 * np.pi * 1.5e-5 * np.arange(len(x))))
+    sigma = np.abs(frames[0][100]) * np.sqrt(0.5 / 10 ** (1.4 if modcod == 4 else 1.8))
+    x = (x + sigma * (rng.normal(size=len(x)) + 1j * rng.normal(size=len(x)))).astype(np.complex64)
+    cut = len(x) // 2 + 1234
+    # stage by stage, host buffers
+    slots = info["nldpc"] // info["bits"] // 90
+    h = pkg.S2PLSyncBlock(slots, pilots)
+    h.plhdr_set_params(0.004)
+    h.pll_set_params(0.004, modcod, short, pilots, codenum)
+    want = []
+    for seg in (x[:cut], x[cut:]):
+        fr = h.process(seg).reshape(-1, h.raw_frame_size)
+        if not len(fr):
+            want.append(None)
+            continue
+        fed = h.coarse_fed(fr, pilots, pls, codenum)
+        out, _ = h.pll_process(fr)
+        _, hres, _ = h.plhdr_process(fr)
+        bb, res = dec.decode_plframes(out.view(np.float32).reshape(len(fr), -1))
+        want.append((bb, res, np.asarray(fed, np.float32), hres))
+    h.close()
+    g = pkg.DVBS2DemodStage(max_batch=16)
+    g.setDemodParams(modcod, short, pilots, 25, 0.004, 0.004, codenum)
+    got_bb = []
+    for seg, w in zip((x[:cut], x[cut:]), want):
+        bb, res, fed, hres = g.process(seg)
+        if w is None:
+            assert len(bb) == 0
+            continue
+        assert np.array_equal(bb, w[0]) and np.array_equal(res["ldpc_iters"], w[1]["ldpc_iters"]) and np.array_equal(res["bch_corr"], w[1]["bch_corr"])
+        assert np.array_equal(fed.view(np.uint32), w[2].view(np.uint32)) and np.array_equal(hres, w[3])
+        got_bb.append(bb)
+    got_bb = np.concatenate(got_bb)
+    assert len(got_bb) >= n - 1
+    good = sum(any(np.array_equal(b, p) for p in pay) for b in got_bb)
+    assert good >= len(got_bb) - 1      # (the first frame: the loop is still pulling in)
+    assert len(g.process(np.zeros(0, np.complex64))[0]) == 0
+    g.close()
+    dec.close()
