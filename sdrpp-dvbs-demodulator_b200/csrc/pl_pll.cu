@@ -205,6 +205,116 @@ __device__ __forceinline__ void pll_stream(const PllArgs& a) {
     }
 }
 
+// ---- the same idea a CTA wide (second generation) -------------------------------------------------------------------------
+// 256 symbols per block, a thread each.  The two halves of a round cost very different things: the loop updates are a chain
+// of two dependent additions per symbol that ONE thread walks at a handful of cycles per symbol; the evaluation (sin/cos,
+// rotation, double-precision cell index, look-up or atan2) is several hundred cycles of latency however many symbols are
+// evaluated at once.  So the block is made as wide as the evaluation can be (eight warps), the walk keeps what it computed
+// (phase, frequency and error sum BEFORE every symbol, in shared memory), and a round only redoes what can have changed:
+// the walk resumes at the first symbol whose error changed, and only symbols from there on are evaluated again.  The fixed
+// point is the same as the warp-wide kernel's and the sequential walk's -- per-symbol operations and their order are
+// untouched -- and is reached in fewer, cheaper rounds per symbol.
+constexpr int kWide = 256;
+struct WideShared {
+    float e[kWide];                                       // the error every symbol currently feeds the loop
+    float ph[kWide + 1], fr[kWide + 1], es[kWide + 1];    // loop phase / frequency / error sum before symbol k; [nv] = after the block
+    int jmin[2];                                          // first symbol whose error changed in this round
+    int slow;                                             // the walk left the range where clamp and wrap are no-ops: use advance()
+};
+
+// one thread: loop updates for symbols [j, nv) from the state kept at j; returns false if a fast walk left the range
+__device__ __forceinline__ bool wide_walk(WideShared& S, int j, int nv, float alpha, float beta, bool slow) {
+    const float pi = 3.1415926535f;
+    const float fmax = __fmul_rn(0.01f, pi), fmin = __fmul_rn(-0.01f, pi);
+    float ph = S.ph[j], fr = S.fr[j], es = S.es[j];
+    if (slow) {
+        for (int k = j; k < nv; ++k) {
+            const float ek = S.e[k];
+            es = __fadd_rn(es, ek);
+            advance(ph, fr, alpha, beta, ek);
+            S.ph[k + 1] = ph; S.fr[k + 1] = fr; S.es[k + 1] = es;
+        }
+        return true;
+    }
+    float flo = fr, fhi = fr, plo = ph, phi = ph;
+#pragma unroll 8
+    for (int k = j; k < nv; ++k) {
+        const float ek = S.e[k];
+        es = __fadd_rn(es, ek);
+        fr = __fadd_rn(fr, __fmul_rn(beta, ek));
+        ph = __fadd_rn(ph, __fadd_rn(fr, __fmul_rn(alpha, ek)));
+        flo = fminf(flo, fr); fhi = fmaxf(fhi, fr);
+        plo = fminf(plo, ph); phi = fmaxf(phi, ph);
+        S.ph[k + 1] = ph; S.fr[k + 1] = fr; S.es[k + 1] = es;
+    }
+    return flo >= fmin && fhi <= fmax && plo >= -pi && phi <= pi;      // (NaN: false)
+}
+
+__device__ __forceinline__ void pll_stream_wide(const PllArgs& a) {
+    __shared__ WideShared S;
+    const int tid = threadIdx.x;
+    float phase = a.st->phase, freq = a.st->freq;
+    const float alpha = a.st->alpha, beta = a.st->beta;
+    float err_avg = a.st->error;
+    unsigned rounds = 0;
+    for (int f = 0; f < a.nframes; ++f) {
+        const float2* in = a.frames + (size_t)f * a.rfs;
+        float2* out = a.out + (size_t)f * a.rfs;
+        float errsum = 0.f;
+        for (int base = 0; base < a.total; base += kWide) {
+            const int nv = min(kWide, a.total - base), i = base + tid;
+            const bool valid = tid < nv;
+            const float2 x = valid ? in[i] : make_float2(0.f, 0.f);
+            float e_cur = 0.f;
+            float2 o = make_float2(0.f, 0.f);
+            S.e[tid] = 0.f;
+            if (tid == 0) { S.ph[0] = phase; S.fr[0] = freq; S.es[0] = errsum; S.slow = 0; }
+            int j = 0;
+            bool slow = false;
+            for (int round = 0;; ++round) {
+                __syncthreads();      // errors of the previous round (or the zeros) are in place
+                if (tid == 0) {
+                    S.jmin[round & 1] = INT_MAX;
+                    if (!wide_walk(S, j, nv, alpha, beta, slow)) S.slow = 1;
+                }
+                __syncthreads();
+                if (!slow && S.slow) {      // once per block at most: start over with the full advance()
+                    slow = true;
+                    j = 0;
+                    continue;
+                }
+                if (valid && tid >= j) {
+                    const float e_new = symbol_error(a, i, x, S.ph[tid], o);
+                    if (__float_as_uint(e_new) != __float_as_uint(e_cur)) {
+                        e_cur = e_new;
+                        S.e[tid] = e_new;
+                        atomicMin(&S.jmin[round & 1], tid);
+                    }
+                }
+                ++rounds;
+                __syncthreads();
+                j = S.jmin[round & 1];
+                if (j == INT_MAX) break;      // every symbol got the error it already had: the sequential solution
+            }
+            phase = S.ph[nv]; freq = S.fr[nv]; errsum = S.es[nv];
+            if (valid) out[i] = o;
+            __syncthreads();      // S is reused by the next block
+        }
+        err_avg = __fdiv_rn(errsum, a.divisor);
+        if (tid == 0 && a.state_out) {
+            a.state_out[3 * f] = phase;
+            a.state_out[3 * f + 1] = freq;
+            a.state_out[3 * f + 2] = err_avg;
+        }
+    }
+    if (tid == 0) {
+        a.st->phase = phase;
+        a.st->freq = freq;
+        a.st->error = err_avg;
+        a.st->rounds = rounds;
+    }
+}
+
 // The same loop walked one symbol at a time by one thread, as the reference walks it: the yardstick for the speculative
 // kernel (tests: both produce the same bits) and for its timing.
 __global__ void __launch_bounds__(32) pll_sequential_kernel(const __grid_constant__ PllArgs a) {
@@ -236,20 +346,22 @@ __global__ void __launch_bounds__(32) pll_sequential_kernel(const __grid_constan
 }
 
 __global__ void __launch_bounds__(32) pll_kernel(const __grid_constant__ PllArgs a) { pll_stream(a); }
-// several independent streams (transponders) at once: a warp each
-__global__ void __launch_bounds__(32) pll_multi_kernel(const PllArgs* jobs) { pll_stream(jobs[blockIdx.x]); }
+__global__ void __launch_bounds__(kWide) pll_wide_kernel(const __grid_constant__ PllArgs a) { pll_stream_wide(a); }
+// several independent streams (transponders) at once: a CTA each
+__global__ void __launch_bounds__(kWide) pll_multi_kernel(const PllArgs* jobs) { pll_stream_wide(jobs[blockIdx.x]); }
 
 }  // namespace
 
-int pll_launch(const PllArgs& a, bool sequential, cudaStream_t stream) {
+int pll_launch(const PllArgs& a, int mode, cudaStream_t stream) {
     if (a.nframes > 0) {
-        if (sequential) pll_sequential_kernel<<<1, 32, 0, stream>>>(a);
-        else pll_kernel<<<1, 32, 0, stream>>>(a);
+        if (mode == 1) pll_sequential_kernel<<<1, 32, 0, stream>>>(a);
+        else if (mode == 2) pll_kernel<<<1, 32, 0, stream>>>(a);
+        else pll_wide_kernel<<<1, kWide, 0, stream>>>(a);
     }
     return (int)cudaGetLastError();
 }
 int pll_launch_multi(const PllArgs* d_jobs, int njobs, cudaStream_t stream) {
-    if (njobs > 0) pll_multi_kernel<<<njobs, 32, 0, stream>>>(d_jobs);
+    if (njobs > 0) pll_multi_kernel<<<njobs, kWide, 0, stream>>>(d_jobs);
     return (int)cudaGetLastError();
 }
 
