@@ -83,10 +83,9 @@ struct PllArgs {
     int states;
     float pts[64];
 };
-// mode 0: a CTA speculating 256 symbols at a time (default); 1: one thread, one symbol at a time (the yardstick the tests
-// hold the speculative kernels against); 2: one warp speculating 32 symbols at a time (the first generation)
-int pll_launch(const PllArgs& a, int mode, cudaStream_t stream);
-// njobs independent streams, one CTA each; d_jobs in device memory
+// sequential: one thread, one symbol at a time (the yardstick the tests hold the speculative kernel against)
+int pll_launch(const PllArgs& a, bool sequential, cudaStream_t stream);
+// njobs independent streams, one warp each; d_jobs in device memory
 int pll_launch_multi(const PllArgs* d_jobs, int njobs, cudaStream_t stream);
 
 }  // namespace s2

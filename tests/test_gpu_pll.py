@@ -75,16 +75,15 @@ def test_pll_matches_oracle(case):
                                   ("16apsk", True, True, 16.0, 6e-3, 3), ("32apsk", True, False, 14.0, -1e-3, 4),
                                   ("qpsk", False, True, -1.0, 2e-2, 5)])
 def test_speculative_kernel_equals_the_sequential_walk(case):
-    """the speculative kernels (a CTA taking 256 symbols at a time: the default; a warp taking 32: the first generation)
-    against one device thread walking the loop symbol by symbol with the same device functions: the same bits -- in lock,
-    out of lock (noise, cycle slips), with the phase wrapping every few hundred symbols and the frequency riding on its
-    clamp (carrier offsets beyond 0.01 pi per symbol)"""
+    """the 32-symbols-at-a-time kernel against one device thread walking the loop symbol by symbol with the same device
+    functions: the same bits -- in lock, out of lock (noise, cycle slips), with the phase wrapping every few hundred
+    symbols and the frequency riding on its clamp (carrier offsets beyond 0.01 pi per symbol)"""
     name, short, pilots, esn0, cfo, seed = case
     slots, modcod = SLOTS[(name, short)], MODCOD[name]
     rng = np.random.default_rng(300 + seed)
     pls, fr = frames_for(name, slots, pilots, 3, rng, esn0, cfo, seed, modcod=modcod, short=short)
     res = []
-    for seq in (1, 0, 2):
+    for seq in (1, 0):
         g = pkg.S2PLSyncBlock(slots, pilots)
         g.pll_set_params(0.01, modcod, short, pilots, seed)
         g.pll_set_sequential(seq)
@@ -92,9 +91,8 @@ def test_speculative_kernel_equals_the_sequential_walk(case):
         b, sb = g.pll_process(fr[2:])
         res.append((np.concatenate([a, b]), np.concatenate([sa, sb])))
         g.close()
-    for k in (1, 2):
-        assert np.array_equal(res[0][0].view(np.uint32), res[k][0].view(np.uint32)), k
-        assert np.array_equal(res[0][1].view(np.uint32), res[k][1].view(np.uint32)), k
+    assert np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32))
+    assert np.array_equal(res[0][1].view(np.uint32), res[1][1].view(np.uint32))
 
 
 def test_pll_reset_and_reconfiguration():
