@@ -51,4 +51,25 @@ for name, modcod, short, esn0 in (("QPSK 1/2 normal", 4, False, 6.0), ("8PSK 3/5
                     phase_loop_share=round(pll_ms / ms, 2), mean_ldpc_iters=float(np.where(r["ldpc_iters"] < 0, 25, r["ldpc_iters"]).mean())))
     print(res[-1], flush=True)
     g.close(); p.close()
+# several transponders: a handle, a host thread and a stream each (ctypes releases the GIL for the call); the phase loops of
+# different transponders run side by side on the device
+import threading
+multi = []
+for nt in (1, 4, 16):
+    hs = []
+    for _ in range(nt):
+        g = pkg.DVBS2DemodStage(max_batch=64); g.setDemodParams(4, True, False, 25, 0.004, 0.004, 0); g.process(x); g.reset(); hs.append(g)
+    def work(g):
+        for _ in range(3):
+            g.reset(); g.process(x)
+    th = [threading.Thread(target=work, args=(g,)) for g in hs]
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for t in th: t.start()
+    for t in th: t.join()
+    ms = (time.perf_counter() - t0) / 3 * 1e3
+    multi.append(dict(workload="QPSK 1/2 short, one handle + host thread per transponder", transponders=nt, ms_per_round=round(ms, 2),
+                      msym_s_total=round(nt * len(x) / ms / 1e3, 1), frames_per_s_total=round(nt * len(bb) / ms * 1e3)))
+    print(multi[-1], flush=True)
+    for g in hs: g.close()
+res.append(dict(multi_transponder=multi))
 if a.out: json.dump(res, open(a.out, "w"), indent=1)
