@@ -21,4 +21,4 @@ ncu --set full --clock-control none --import-source on -k regex:acs_kernel -s 5 
 python tools/pll_bench.py --out $O/pll_bench_$R.json > $O/pll_bench_$R.log 2>&1
 python tools/s2_stage_bench.py --out $O/s2_stage_bench_$R.json > $O/s2_stage_bench_$R.log 2>&1
 tools/mixed_stream --gpus 1 --out $O/mixed_stream_${R}_1gpu.json > $O/mixed_stream_${R}_1gpu.log 2>&1
-tail -3 $O/san_mem_$R.log $O/san_race_$R.log $O/parity_campaign_$R.log
+tail -n 3 $O/san_mem_$R.log $O/san_race_$R.log $O/parity_campaign_$R.log
