@@ -302,6 +302,12 @@ int dvbs2fec_s2_demod_max_frames(const dvbs2fec_s2_demod* p, int count);    /* f
  * ints: detect_modcod, detect_shortframes, detect_pilots, PLS index).  Host buffers, synchronous. */
 int dvbs2fec_s2_demod_process(dvbs2fec_s2_demod* p, int count, const float* syms, uint8_t* bb_out, int max_frames,
                               dvbs2fec_result* results, float* fed_err, int32_t* plhdr);
+/* the same with the BBFRAME parser behind it (BBFrameTSParser::work as main.cpp:538 calls it on the module's output; K6
+ * on the device, its state kept in the handle): 188-byte TS packets / GRE-wrapped GSE PDUs out, at most ts_cap bytes (the
+ * parser's buffer_outsize); returns the bytes written, *nframes (optional) = frames decoded.  The per-frame outputs are
+ * optional; with any of them max_frames must be at least dvbs2fec_s2_demod_max_frames(count). */
+int dvbs2fec_s2_demod_process_ts(dvbs2fec_s2_demod* p, int count, const float* syms, uint8_t* ts_out, int ts_cap, int max_frames,
+                                 int* nframes, dvbs2fec_result* results, float* fed_err, int32_t* plhdr);
 
 /* ---- DVB-S legacy chain, the byte-domain half: the body of the frame loop of
  *      DVBSDemod::process (dvbs/module_dvbs_demod.cpp:91-106) -- convolutional deinterleaver

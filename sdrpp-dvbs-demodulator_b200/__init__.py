@@ -169,6 +169,7 @@ def lib():
     L.dvbs2fec_s2_demod_bbframe_bytes.argtypes = [vp]
     L.dvbs2fec_s2_demod_max_frames.argtypes = [vp, C.c_int]
     L.dvbs2fec_s2_demod_process.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]
+    L.dvbs2fec_s2_demod_process_ts.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_int), vp, vp, vp]
     L.dvbs2fec_dvbs_demod_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(vp)]
     L.dvbs2fec_dvbs_demod_destroy.argtypes = [vp]
     L.dvbs2fec_dvbs_demod_destroy.restype = None
@@ -822,3 +823,11 @@ class DVBS2DemodStage:
         hdr = np.zeros((m, 4), np.int32)
         n = _check(lib().dvbs2fec_s2_demod_process(self._p, len(x), _ptr(x), _ptr(bb), m, _ptr(res), _ptr(fed), _ptr(hdr)))
         return bb[:n], res[:n], fed[:n], hdr[:n]
+
+    def process_ts(self, syms, ts_cap=65536 * 10):
+        """complex symbols -> (TS / GSE output bytes of BBFrameTSParser::work on the decoded BBFRAMEs, frames decoded)"""
+        x = np.ascontiguousarray(syms, np.complex64)
+        out = np.zeros(ts_cap, np.uint8)
+        nfr = C.c_int()
+        n = _check(lib().dvbs2fec_s2_demod_process_ts(self._p, len(x), _ptr(x), _ptr(out), ts_cap, 0, C.byref(nfr), None, None, None))
+        return out[:n], nfr.value

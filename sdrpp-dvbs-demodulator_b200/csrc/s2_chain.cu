@@ -48,6 +48,7 @@ struct dvbs2fec_s2_demod {
     int device = 0;
     dvbs2fec_handle* fec = nullptr;
     dvbs2fec_plsync* pl = nullptr;
+    dvbs2fec_ts_parser* ts = nullptr;      // BBFRAME -> TS / GSE (K6), for dvbs2fec_s2_demod_process_ts
     cudaStream_t stream = nullptr;
     int modcod = 0, shortframes = 0, pilots = 0, codenum = 0, rfs = 0, kb = 0;
     float* d_x = nullptr; size_t x_cap = 0;
@@ -58,7 +59,9 @@ struct dvbs2fec_s2_demod {
     dvbs2fec_result* d_res = nullptr; size_t res_cap = 0;
     float* d_fed = nullptr; size_t fed_cap = 0;
     int32_t* d_hdr = nullptr; size_t hdr_cap = 0;
+    uint8_t* d_ts = nullptr; size_t ts_cap = 0;
     int* d_n = nullptr;
+    int last_frames = 0;
 };
 
 extern "C" {
@@ -71,9 +74,10 @@ void dvbs2fec_s2_demod_destroy(dvbs2fec_s2_demod* p) {
         cudaStreamDestroy(p->stream);
     }
     dvbs2fec_plsync_destroy(p->pl);
+    dvbs2fec_ts_destroy(p->ts);
     dvbs2fec_destroy(p->fec);
     cudaFree(p->d_x); cudaFree(p->d_fr); cudaFree(p->d_pl); cudaFree(p->d_hsym); cudaFree(p->d_bb); cudaFree(p->d_res);
-    cudaFree(p->d_fed); cudaFree(p->d_hdr); cudaFree(p->d_n);
+    cudaFree(p->d_fed); cudaFree(p->d_hdr); cudaFree(p->d_ts); cudaFree(p->d_n);
     delete p;
 }
 
@@ -93,6 +97,7 @@ int dvbs2fec_s2_demod_create(const dvbs2fec_config* cfg, dvbs2fec_s2_demod** out
     p->device = dev;
     int rc = dvbs2fec_create(&c, &p->fec);
     if (!rc) rc = dvbs2fec_plsync_create(dev, &p->pl);
+    if (!rc) rc = dvbs2fec_ts_create(dev, &p->ts);
     if (rc) return rc;
     CU(cudaSetDevice(dev));
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
@@ -118,6 +123,8 @@ int dvbs2fec_s2_demod_set_params(dvbs2fec_s2_demod* p, int modcod, int shortfram
     p->modcod = modcod; p->shortframes = !!shortframes; p->pilots = !!pilots; p->codenum = codenum;
     p->rfs = dvbs2fec_plsync_raw_frame_size(p->pl);
     p->kb = dvbs2fec_kbch(p->fec) / 8;
+    rc = dvbs2fec_ts_set_frame_size(p->ts, p->kb * 8);      // BBFrameTSParser::setFrameSize (main.cpp, on a MODCOD change)
+    if (rc) return rc;
     if (p->rfs != plsyms || dvbs2fec_pll_frame_symbols(p->pl) > p->rfs) return api_fail(DVBS2FEC_EINVAL, "frame sizes of the stages disagree");
     return 0;
 }
@@ -134,13 +141,13 @@ int dvbs2fec_s2_demod_reset(dvbs2fec_s2_demod* p) {
 int dvbs2fec_s2_demod_bbframe_bytes(const dvbs2fec_s2_demod* p) { return p ? p->kb : 0; }
 int dvbs2fec_s2_demod_max_frames(const dvbs2fec_s2_demod* p, int count) { return p && p->rfs ? count / p->rfs + 2 : 0; }
 
-int dvbs2fec_s2_demod_process(dvbs2fec_s2_demod* p, int count, const float* syms, uint8_t* bb_out, int max_frames, dvbs2fec_result* results,
-                              float* fed_err, int32_t* plhdr) {
-    if (!p || !p->rfs) return api_fail(DVBS2FEC_EINVAL, "set_params has not been called");
-    if (count < 0 || (count && !syms) || !bb_out) return api_fail(DVBS2FEC_EINVAL, "bad arguments");
+}  // extern "C"
+
+namespace {
+// symbols in host memory -> BBFRAMEs, results, frequency errors and PLHEADER fields on the device (enqueued, not waited for);
+// returns the number of frames
+int stage_to_device(dvbs2fec_s2_demod* p, int count, const float* syms) {
     const int room = count / p->rfs + 2;      // fewer than two frames are ever carried over
-    if (max_frames < room) return api_fail(DVBS2FEC_EINVAL, "max_frames < count / raw_frame_size + 2 (dvbs2fec_s2_demod_max_frames)");
-    if (!count) return 0;
     CU(cudaSetDevice(p->device));
     cudaStream_t st = p->stream;
     const size_t fsz = (size_t)room * p->rfs * 2;
@@ -168,12 +175,62 @@ int dvbs2fec_s2_demod_process(dvbs2fec_s2_demod* p, int count, const float* syms
     if (!rc) rc = dvbs2fec_plhdr_process_device(p->pl, n, p->d_fr, p->d_hsym, p->d_hdr, st);                // :315
     if (!rc) rc = dvbs2fec_decode_plframes_device(p->fec, p->d_pl, n, p->d_bb, p->d_res, st);               // :316, 334-366
     if (rc) return rc;
-    CU(cudaMemcpyAsync(bb_out, p->d_bb, (size_t)n * p->kb, cudaMemcpyDeviceToHost, st));
+    return n;
+}
+
+int copy_side_outputs(dvbs2fec_s2_demod* p, int n, dvbs2fec_result* results, float* fed_err, int32_t* plhdr) {
+    cudaStream_t st = p->stream;
     if (results) CU(cudaMemcpyAsync(results, p->d_res, sizeof(dvbs2fec_result) * n, cudaMemcpyDeviceToHost, st));
     if (fed_err) CU(cudaMemcpyAsync(fed_err, p->d_fed, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     if (plhdr) CU(cudaMemcpyAsync(plhdr, p->d_hdr, sizeof(int32_t) * 4 * n, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int dvbs2fec_s2_demod_process(dvbs2fec_s2_demod* p, int count, const float* syms, uint8_t* bb_out, int max_frames, dvbs2fec_result* results,
+                              float* fed_err, int32_t* plhdr) {
+    if (!p || !p->rfs) return api_fail(DVBS2FEC_EINVAL, "set_params has not been called");
+    if (count < 0 || (count && !syms) || !bb_out) return api_fail(DVBS2FEC_EINVAL, "bad arguments");
+    if (max_frames < count / p->rfs + 2) return api_fail(DVBS2FEC_EINVAL, "max_frames < count / raw_frame_size + 2 (dvbs2fec_s2_demod_max_frames)");
+    if (!count) return 0;
+    const int n = stage_to_device(p, count, syms);
+    if (n <= 0) return n;
+    cudaStream_t st = p->stream;
+    CU(cudaMemcpyAsync(bb_out, p->d_bb, (size_t)n * p->kb, cudaMemcpyDeviceToHost, st));
+    int rc = copy_side_outputs(p, n, results, fed_err, plhdr);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(st));
     return n;
+}
+
+int dvbs2fec_s2_demod_process_ts(dvbs2fec_s2_demod* p, int count, const float* syms, uint8_t* ts_out, int ts_cap, int max_frames, int* nframes,
+                                 dvbs2fec_result* results, float* fed_err, int32_t* plhdr) {
+    if (!p || !p->rfs) return api_fail(DVBS2FEC_EINVAL, "set_params has not been called");
+    if (count < 0 || (count && !syms) || !ts_out || ts_cap <= 0) return api_fail(DVBS2FEC_EINVAL, "bad arguments");
+    if ((results || fed_err || plhdr) && max_frames < count / p->rfs + 2)
+        return api_fail(DVBS2FEC_EINVAL, "max_frames < count / raw_frame_size + 2 (dvbs2fec_s2_demod_max_frames)");
+    if (nframes) *nframes = 0;
+    if (!count) return 0;
+    const int n = stage_to_device(p, count, syms);
+    if (n <= 0) return n;
+    if (nframes) *nframes = n;
+    cudaStream_t st = p->stream;
+    CU(reserve(p->d_ts, p->ts_cap, (size_t)ts_cap));
+    int rc = dvbs2fec_ts_work_device(p->ts, p->d_bb, n, p->d_ts, ts_cap, p->d_n, st);      // main.cpp:538: ts_parser.work(...)
+    if (rc) return rc;
+    int produced = 0;
+    CU(cudaMemcpyAsync(&produced, p->d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    rc = copy_side_outputs(p, n, results, fed_err, plhdr);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
+    if (produced < 0) return api_fail(produced, "TS / GSE output does not fit ts_cap");
+    if (produced) {
+        CU(cudaMemcpyAsync(ts_out, p->d_ts, (size_t)produced, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return produced;
 }
 
 }  // extern "C"

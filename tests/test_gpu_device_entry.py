@@ -254,3 +254,46 @@ def test_s2_demod_stage_in_one_call(case):
     assert len(g.process(np.zeros(0, np.complex64))[0]) == 0
     g.close()
     dec.close()
+
+
+def test_s2_demod_stage_with_ts_output():
+    """symbols -> TS packets in one call (the BBFRAME parser behind the stage, its state carried over calls): the same bytes
+    as BBFrameTSParser.work on the BBFRAMEs the plain stage call delivers, and the transmitted packets come back"""
+    import bbstream
+    import plstream
+    modcod, short, codenum = 4, True, 2
+    rng = np.random.default_rng(606)
+    info = pkg.modcod_info(modcod, short, False)
+    packets = bbstream.ts_packets(200, rng)
+    frames_bb, _ = bbstream.ts_bbframes(info["kbch"], packets)
+    frames_bb = frames_bb[:7]
+    pls = modcod << 2 | 2
+    rn = plstream.pl_rn(codenum)
+    frames = []
+    for bbf in frames_bb:
+        sym = pkg.modulate(modcod, short, False, pkg.encode_fecframe(modcod, short, bbf)).view(np.complex64).copy()
+        body = sym[90:]
+        frames.append(np.concatenate([plstream.plheader(pls) * np.abs(body[0]), body * np.array([1, 1j, -1, -1j])[rn[:len(body)]]]))
+    x = np.concatenate([0.3 * (rng.normal(size=900) + 1j * rng.normal(size=900))] + frames + [frames[0][:300]]).astype(np.complex64)
+    x = x * np.exp(1j * (0.1 + 2 * np.pi * 1e-5 * np.arange(len(x))))
+    sigma = np.abs(frames[0][100]) * np.sqrt(0.5 / 10 ** 1.4)
+    x = (x + sigma * (rng.normal(size=len(x)) + 1j * rng.normal(size=len(x)))).astype(np.complex64)
+    cut = len(x) // 2 + 77
+    a = pkg.DVBS2DemodStage(max_batch=16)
+    a.setDemodParams(modcod, short, False, 25, 0.004, 0.004, codenum)
+    b = pkg.DVBS2DemodStage(max_batch=16)
+    b.setDemodParams(modcod, short, False, 25, 0.004, 0.004, codenum)
+    parser = pkg.BBFrameTSParser()
+    parser.setFrameSize(info["kbch"])
+    got_all = []
+    for seg in (x[:cut], x[cut:]):
+        bb, _, _, _ = a.process(seg)
+        want = parser.work(bb, len(bb)) if len(bb) else np.zeros(0, np.uint8)
+        got, nfr = b.process_ts(seg)
+        assert nfr == len(bb) and np.array_equal(got, want)
+        got_all.append(got)
+    ts = np.concatenate(got_all).reshape(-1, 188)
+    sent = {p.tobytes() for p in packets}
+    assert len(ts) >= 5 * (info["kbch"] // 8 - 10) // 188 and sum(p.tobytes() in sent for p in ts) >= len(ts) - 20
+    for h in (a, b, parser):
+        h.close()
