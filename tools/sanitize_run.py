@@ -170,3 +170,21 @@ dm = pkg.DVBSDemod(frame_stride=1632)
 t1 = dm.process(csyms)
 print("dvbs chain", t1.shape, dm.stats())
 dm.close()
+# the DVB-S2 stage in one call (K7 -> K8 -> K1..K3 -> K6 on one stream), two calls cut inside a frame
+import bbstream  # noqa: E402
+import plstream  # noqa: E402
+srng = np.random.default_rng(15)
+sinfo = pkg.modcod_info(4, True, False)
+sbb, _ = bbstream.ts_bbframes(sinfo["kbch"], bbstream.ts_packets(60, srng))
+sfr = []
+for bbf in sbb[:3]:
+    sym = pkg.modulate(4, True, False, pkg.encode_fecframe(4, True, bbf)).view(np.complex64).copy()
+    sfr.append(np.concatenate([plstream.plheader(4 << 2 | 2) * np.abs(sym[90]), sym[90:] * np.array([1, 1j, -1, -1j])[plstream.pl_rn(1)[:len(sym) - 90]]]))
+sx = np.concatenate([0.3 * (srng.normal(size=500) + 1j * srng.normal(size=500))] + sfr + [sfr[0][:200]]).astype(np.complex64)
+sx = (sx + 0.03 * (srng.normal(size=len(sx)) + 1j * srng.normal(size=len(sx)))).astype(np.complex64)
+stg = pkg.DVBS2DemodStage(max_batch=8)
+stg.setDemodParams(4, True, False, 6, 0.004, 0.004, 1)
+t_a, n_a = stg.process_ts(sx[:9000])
+t_b, n_b = stg.process_ts(sx[9000:])
+print("s2 stage", len(t_a), n_a, len(t_b), n_b)
+stg.close()
