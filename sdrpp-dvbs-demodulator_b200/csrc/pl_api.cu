@@ -131,7 +131,7 @@ struct dvbs2fec_plsync {
     Buf<uint8_t> pll_jobs;
     PllArgs pll{};            // configuration part; buffers are filled in per call
     bool pll_ready = false;
-    bool pll_sequential = false;
+    int pll_sequential = 0;      // 0: pipelined speculative kernel, 1: sequential walk, 2: one-warp speculative kernel
 };
 
 extern "C" {
@@ -455,7 +455,7 @@ int dvbs2fec_pll_set_state(dvbs2fec_plsync* p, float phase, float freq) {
 
 int dvbs2fec_pll_set_sequential(dvbs2fec_plsync* p, int on) {
     if (!p) return api_fail(DVBS2FEC_EINVAL, "handle is NULL");
-    p->pll_sequential = on != 0;
+    p->pll_sequential = (on == 1 || on == 2) ? on : 0;
     return 0;
 }
 

@@ -205,6 +205,142 @@ __device__ __forceinline__ void pll_stream(const PllArgs& a) {
     }
 }
 
+// ---- the blocks of a stream in a pipeline (second generation) --------------------------------------------------------------
+// A block settles in about four rounds, but only the first of them moves its end state by much: the later ones correct a
+// table cell here and there and confirm.  So the next block need not wait: kPipe warps take the blocks of a stream in turn,
+// every warp publishes the end state of its block after EVERY round, and the warp behind it starts from whatever is
+// published, repeats its rounds whenever that changes, and is done when its errors reproduce themselves from a start state
+// its predecessor has declared final.  What comes out of a block is computed from the final start state and confirmed by a
+// round of its own: the sequential result, as before; the rounds of neighbouring blocks now overlap in time.
+constexpr int kPipe = 4;
+struct Mail {
+    float ph, fr, es;     // loop state after the block
+    int blk;              // which block (global index over the frames of the call)
+    int seq;              // odd while being written
+    int fin;              // the state is the final one
+};
+struct PipeShared {
+    Mail mail[kPipe];
+    unsigned rounds;
+    int broken;           // a wait ran into its bound: give up instead of hanging
+};
+
+__device__ __forceinline__ bool mail_read(volatile Mail* m, int want_blk, float& ph, float& fr, float& es, int& fin) {
+    const int s0 = m->seq;
+    if (s0 & 1) return false;
+    __threadfence_block();
+    const int blk = m->blk;
+    ph = m->ph; fr = m->fr; es = m->es; fin = m->fin;
+    __threadfence_block();
+    return blk == want_blk && m->seq == s0;
+}
+
+__device__ __forceinline__ void pll_stream_pipe(const PllArgs& a) {
+    __shared__ PipeShared S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned full = 0xFFFFFFFFu;
+    const float alpha = a.st->alpha, beta = a.st->beta;
+    const float ph0 = a.st->phase, fr0 = a.st->freq, err0 = a.st->error;
+    if (threadIdx.x < kPipe) { S.mail[threadIdx.x].blk = -1000000; S.mail[threadIdx.x].seq = 0; S.mail[threadIdx.x].fin = 0; }
+    if (threadIdx.x == 0) { S.rounds = 0; S.broken = 0; }
+    __syncthreads();
+    const int bpf = (a.total + 31) / 32, nblocks = a.nframes * bpf;
+    unsigned rounds = 0;
+    volatile Mail* mine = &S.mail[warp];
+    volatile Mail* prev = &S.mail[(warp + kPipe - 1) % kPipe];
+    volatile Mail* next = &S.mail[(warp + 1) % kPipe];
+    volatile int* broken = &S.broken;
+    for (int g = warp; g < nblocks && !*broken; g += kPipe) {
+        const int f = g / bpf, base = (g - f * bpf) * 32;
+        const int nv = min(32, a.total - base), i = base + lane;
+        const bool valid = lane < nv;
+        const float2 x = valid ? a.frames[(size_t)f * a.rfs + i] : make_float2(0.f, 0.f);
+        // my slot still holds the end state of block g - kPipe, which block g - kPipe + 1 (the next warp's) starts from
+        if (g >= kPipe) {
+            for (long long spin = 0;; ++spin) {
+                const int nb = next->blk, nf = next->fin, ns = next->seq;
+                if (!(ns & 1) && (nb > g - kPipe + 1 || (nb == g - kPipe + 1 && nf))) break;
+                if (spin > (1ll << 24) || *broken) { *broken = 1; break; }
+                __nanosleep(40);
+            }
+        }
+        float e_cur = 0.f;
+        float2 o = make_float2(0.f, 0.f);
+        ScanOut sc;
+        float uph = 0.f, ufr = 0.f, ues = 0.f;      // the start state the last round used
+        bool have = false, done = false;
+        int seq = mine->seq;
+        while (!done && !*broken) {
+            float sph = ph0, sfr = fr0, ses = 0.f;
+            int pfin = 1;
+            if (g > 0) {
+                bool ok = false;
+                for (long long spin = 0; !ok; ++spin) {
+                    ok = mail_read(prev, g - 1, sph, sfr, ses, pfin);
+                    if (base == 0) ses = 0.f;      // a frame starts: S2PLLBlock::process sums the error per frame
+                    // nothing new and my errors already agree with it: wait for the predecessor to move or to finish
+                    if (ok && have && !pfin && __float_as_uint(sph) == __float_as_uint(uph) && __float_as_uint(sfr) == __float_as_uint(ufr) &&
+                        __float_as_uint(ses) == __float_as_uint(ues))
+                        ok = false;
+                    if (spin > (1ll << 24) || *broken) { *broken = 1; break; }
+                    if (!ok) __nanosleep(40);      // (a spinning warp's fences and loads are in the working warps' way)
+                }
+                if (*broken) break;
+            }
+            const bool same_start = have && __float_as_uint(sph) == __float_as_uint(uph) && __float_as_uint(sfr) == __float_as_uint(ufr) &&
+                                    __float_as_uint(ses) == __float_as_uint(ues);
+            bool same = have && same_start;      // same start, and the last round found the errors it was given: nothing to redo
+            if (!same) {
+                sc = (nv == 32) ? scan_block<true>(sph, sfr, ses, alpha, beta, e_cur, nv, lane)
+                                : scan_block<false>(sph, sfr, ses, alpha, beta, e_cur, nv, lane);
+                if (lane == 0) {      // where the loop ends with these errors: the next block can start on it while they are checked
+                    mine->seq = ++seq;
+                    __threadfence_block();
+                    mine->ph = sc.ph_end; mine->fr = sc.fr_end; mine->es = sc.es_end; mine->blk = g; mine->fin = 0;
+                    __threadfence_block();
+                    mine->seq = ++seq;
+                }
+                const float e_new = valid ? symbol_error(a, i, x, sc.ph_in, o) : 0.f;
+                same = __all_sync(full, __float_as_uint(e_new) == __float_as_uint(e_cur));
+                ++rounds;
+                uph = sph; ufr = sfr; ues = ses;
+                have = same;      // `have`: the errors in e_cur reproduce themselves from (uph, ufr, ues)
+                if (!same) e_cur = e_new;
+            }
+            done = same && pfin;
+            if (done && lane == 0) {      // the state published behind the last scan is the final one
+                mine->seq = ++seq;
+                __threadfence_block();
+                mine->ph = sc.ph_end; mine->fr = sc.fr_end; mine->es = sc.es_end; mine->blk = g; mine->fin = 1;
+                __threadfence_block();
+                mine->seq = ++seq;
+            }
+            __syncwarp();
+        }
+        if (*broken) break;
+        if (valid) a.out[(size_t)f * a.rfs + i] = o;
+        if (lane == 0 && base + 32 >= a.total) {      // the frame's last block
+            const float err_avg = __fdiv_rn(sc.es_end, a.divisor);
+            if (a.state_out) {
+                a.state_out[3 * f] = sc.ph_end;
+                a.state_out[3 * f + 1] = sc.fr_end;
+                a.state_out[3 * f + 2] = err_avg;
+            }
+            if (g == nblocks - 1) {
+                a.st->phase = sc.ph_end;
+                a.st->freq = sc.fr_end;
+                a.st->error = err_avg;
+            }
+        }
+    }
+    if (lane == 0) atomicAdd(&S.rounds, rounds);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.st->rounds = S.broken ? 0xFFFFFFFFu : S.rounds;
+        if (nblocks == 0) a.st->error = err0;
+    }
+}
+
 // The same loop walked one symbol at a time by one thread, as the reference walks it: the yardstick for the speculative
 // kernel (tests: both produce the same bits) and for its timing.
 __global__ void __launch_bounds__(32) pll_sequential_kernel(const __grid_constant__ PllArgs a) {
@@ -236,20 +372,22 @@ __global__ void __launch_bounds__(32) pll_sequential_kernel(const __grid_constan
 }
 
 __global__ void __launch_bounds__(32) pll_kernel(const __grid_constant__ PllArgs a) { pll_stream(a); }
-// several independent streams (transponders) at once: a warp each
-__global__ void __launch_bounds__(32) pll_multi_kernel(const PllArgs* jobs) { pll_stream(jobs[blockIdx.x]); }
+__global__ void __launch_bounds__(32 * kPipe) pll_pipe_kernel(const __grid_constant__ PllArgs a) { pll_stream_pipe(a); }
+// several independent streams (transponders) at once: a CTA of kPipe warps each
+__global__ void __launch_bounds__(32 * kPipe) pll_multi_kernel(const PllArgs* jobs) { pll_stream_pipe(jobs[blockIdx.x]); }
 
 }  // namespace
 
-int pll_launch(const PllArgs& a, bool sequential, cudaStream_t stream) {
+int pll_launch(const PllArgs& a, int mode, cudaStream_t stream) {
     if (a.nframes > 0) {
-        if (sequential) pll_sequential_kernel<<<1, 32, 0, stream>>>(a);
-        else pll_kernel<<<1, 32, 0, stream>>>(a);
+        if (mode == 1) pll_sequential_kernel<<<1, 32, 0, stream>>>(a);
+        else if (mode == 2) pll_kernel<<<1, 32, 0, stream>>>(a);
+        else pll_pipe_kernel<<<1, 32 * kPipe, 0, stream>>>(a);
     }
     return (int)cudaGetLastError();
 }
 int pll_launch_multi(const PllArgs* d_jobs, int njobs, cudaStream_t stream) {
-    if (njobs > 0) pll_multi_kernel<<<njobs, 32, 0, stream>>>(d_jobs);
+    if (njobs > 0) pll_multi_kernel<<<njobs, 32 * kPipe, 0, stream>>>(d_jobs);
     return (int)cudaGetLastError();
 }
 

@@ -83,9 +83,11 @@ struct PllArgs {
     int states;
     float pts[64];
 };
-// sequential: one thread, one symbol at a time (the yardstick the tests hold the speculative kernel against)
-int pll_launch(const PllArgs& a, bool sequential, cudaStream_t stream);
-// njobs independent streams, one warp each; d_jobs in device memory
+// mode 0: four warps taking the blocks of 32 symbols in turn, each starting from what its predecessor has published (default);
+// 1: one thread, one symbol at a time (the yardstick the tests hold the speculative kernels against); 2: one warp, block
+// after block (the first generation)
+int pll_launch(const PllArgs& a, int mode, cudaStream_t stream);
+// njobs independent streams, one CTA each; d_jobs in device memory
 int pll_launch_multi(const PllArgs* d_jobs, int njobs, cudaStream_t stream);
 
 }  // namespace s2

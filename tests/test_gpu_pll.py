@@ -65,9 +65,10 @@ def test_pll_matches_oracle(case):
         assert np.all(got[0, o.total:] == 0)                      # symbols behind the ones process() handles: untouched
         dphi = abs((st[0, 0] - ws[0] + np.pi) % (2 * np.pi) - np.pi)
         assert dphi < 2e-2 and abs(st[0, 1] - ws[1]) < 1e-4 and abs(st[0, 2] - ws[2]) < 1e-4, (f, st[0], ws)
-    # the speculation settles fast: within sight of the two rounds per 32 symbols that are the minimum
+    # the speculation settles fast: within sight of the two rounds per 32 symbols that are the minimum (the pipelined kernel
+    # also runs rounds on start states its predecessor has not finished with: about 5.5 per block instead of 4.1)
     blocks = nframes * ((o.total + 31) // 32)
-    assert rounds <= (8 if name == "32apsk" else 5.5) * blocks, (rounds, blocks)
+    assert rounds <= (12 if name == "32apsk" else 8) * blocks, (rounds, blocks)
     g.close()
 
 
@@ -83,7 +84,7 @@ def test_speculative_kernel_equals_the_sequential_walk(case):
     rng = np.random.default_rng(300 + seed)
     pls, fr = frames_for(name, slots, pilots, 3, rng, esn0, cfo, seed, modcod=modcod, short=short)
     res = []
-    for seq in (1, 0):
+    for seq in (1, 0, 2):
         g = pkg.S2PLSyncBlock(slots, pilots)
         g.pll_set_params(0.01, modcod, short, pilots, seed)
         g.pll_set_sequential(seq)
@@ -91,8 +92,9 @@ def test_speculative_kernel_equals_the_sequential_walk(case):
         b, sb = g.pll_process(fr[2:])
         res.append((np.concatenate([a, b]), np.concatenate([sa, sb])))
         g.close()
-    assert np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32))
-    assert np.array_equal(res[0][1].view(np.uint32), res[1][1].view(np.uint32))
+    for k in (1, 2):      # the pipelined kernel (default) and the one-warp kernel
+        assert np.array_equal(res[0][0].view(np.uint32), res[k][0].view(np.uint32)), k
+        assert np.array_equal(res[0][1].view(np.uint32), res[k][1].view(np.uint32)), k
 
 
 def test_pll_reset_and_reconfiguration():
