@@ -258,7 +258,7 @@ int dvbs2fec_pll_reset(dvbs2fec_plsync* p);
 /* hand the loop a state (a host-side loop that ran so far, or a test): pcl.phase, pcl.freq */
 int dvbs2fec_pll_set_state(dvbs2fec_plsync* p, float phase, float freq);
 /* 0 (default): four warps take the blocks of 32 symbols in turn, each speculating its block from the state its predecessor
- * has published so far; 1: walk the loop one symbol at a time in one thread, as the reference does (the yardstick: the
+ * published a tick earlier; 1: walk the loop one symbol at a time in one thread, as the reference does (the yardstick: the
  * speculative kernels produce the same bits -- tests/test_gpu_pll.py -- and are several times faster); 2: one warp, block
  * after block (the first speculative kernel) */
 int dvbs2fec_pll_set_sequential(dvbs2fec_plsync* p, int on);

