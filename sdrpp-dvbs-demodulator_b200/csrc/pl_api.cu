@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -144,6 +145,7 @@ int dvbs2fec_plsync_create(int device, dvbs2fec_plsync** out) {
     if (device < 0 || device >= ndev) return api_fail(DVBS2FEC_EINVAL, "device out of range");
     std::unique_ptr<dvbs2fec_plsync> p(new dvbs2fec_plsync());
     p->device = device;
+    if (const char* e = getenv("DVBS2FEC_PLL_MODE")) p->pll_sequential = (atoi(e) == 1 || atoi(e) == 2) ? atoi(e) : 0;      // A/B measurements
     p->h_st.current_position = -1;   // (dvbs2_pl_sync.h:38-40)
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
