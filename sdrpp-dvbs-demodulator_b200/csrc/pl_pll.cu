@@ -238,7 +238,7 @@ __device__ __forceinline__ void pll_stream_pipe(const PllArgs& a) {
     bool valid = false, have = false;
     float2 x = make_float2(0.f, 0.f), o = make_float2(0.f, 0.f);
     float e_cur = 0.f, uph = 0.f, ufr = 0.f, ues = 0.f;
-    ScanOut sc = {0.f, 0.f, 0.f, 0.f};
+    ScanOut sc = {0.f, 0.f, 0.f, 0.f}, pub = {0.f, 0.f, 0.f, 0.f};      // the last walk; what the record says about the block's end
     auto open_block = [&]() {
         if (g >= nblocks) return;
         f = g / bpf; base = (g - f * bpf) * 32;
@@ -281,11 +281,19 @@ __device__ __forceinline__ void pll_stream_pipe(const PllArgs& a) {
                 ++rounds;
                 uph = sph; ufr = sfr; ues = ses;
                 have = same;      // the errors in e_cur reproduce themselves from (uph, ufr, ues)
-                if (!same) e_cur = e_new;
+                if (!same) {
+                    e_cur = e_new;
+                    // Walk once more with the new errors, for the record only: where the block ends with them is, more
+                    // often than not, where it will end for good, and the block behind gets to see that a tick earlier.
+                    const ScanOut s2 = (nv == 32) ? scan_block<true>(sph, sfr, ses, alpha, beta, e_cur, nv, lane)
+                                                  : scan_block<false>(sph, sfr, ses, alpha, beta, e_cur, nv, lane);
+                    pub = s2;
+                } else
+                    pub = sc;
             }
             done = same && pfin;
             if (lane == 0) {
-                const Rec r = {sc.ph_end, sc.fr_end, sc.es_end, g, done ? 1 : 0};
+                const Rec r = {pub.ph_end, pub.fr_end, pub.es_end, g, done ? 1 : 0};
                 S.mail[warp] = r;
                 if (done) S.fmail[warp] = r;
             }
