@@ -257,7 +257,7 @@ int dvbs2fec_pll_set_params(dvbs2fec_plsync* p, float loop_bw, int modcod, int s
 int dvbs2fec_pll_reset(dvbs2fec_plsync* p);
 /* hand the loop a state (a host-side loop that ran so far, or a test): pcl.phase, pcl.freq */
 int dvbs2fec_pll_set_state(dvbs2fec_plsync* p, float phase, float freq);
-/* 0 (default): four warps take the blocks of 32 symbols in turn, each speculating its block from the state its predecessor
+/* 0 (default): six warps take the blocks of 32 symbols in turn, each speculating its block from the state its predecessor
  * published a tick earlier; 1: walk the loop one symbol at a time in one thread, as the reference does (the yardstick: the
  * speculative kernels produce the same bits -- tests/test_gpu_pll.py -- and are several times faster); 2: one warp, block
  * after block (the first speculative kernel) */
@@ -273,7 +273,7 @@ int dvbs2fec_pll_process(dvbs2fec_plsync* p, int nframes, int frame_stride, cons
 /* same on device buffers, asynchronous on `stream`; d_state optional (3 floats per frame) */
 int dvbs2fec_pll_process_device(dvbs2fec_plsync* p, int nframes, int frame_stride, const float* d_frames, float* d_out,
                                 float* d_state, void* stream);
-/* Several independent streams (transponders) in one launch, a CTA of four warps each: objs[k] processes nframes frames from
+/* Several independent streams (transponders) in one launch, a CTA of six warps each: objs[k] processes nframes frames from
  * d_frames[k] into d_out[k] (device buffers, same frame_stride; all objects on the same device and configured).
  * Frames of one stream are a recurrence and cannot overlap; streams can. */
 int dvbs2fec_pll_process_multi_device(int nstreams, dvbs2fec_plsync* const* objs, int nframes, int frame_stride,

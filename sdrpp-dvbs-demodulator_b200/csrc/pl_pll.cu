@@ -215,7 +215,7 @@ __device__ __forceinline__ void pll_stream(const PllArgs& a) {
 // and confirmed by a round of its own: by induction from the first block, the sequential result, as before.  Reads and
 // writes of the records are in different halves of a tick, with a CTA barrier between the halves: no warp ever waits for
 // another one except at those barriers.
-constexpr int kPipe = 4, kLocal = 1;
+constexpr int kPipe = 6, kLocal = 1;
 struct Rec { float ph, fr, es; int blk, fin; };      // loop state after block `blk`
 struct PipeShared {
     Rec mail[kPipe];      // what a warp's current block looked like after its last round

@@ -83,7 +83,7 @@ struct PllArgs {
     int states;
     float pts[64];
 };
-// mode 0: four warps taking the blocks of 32 symbols in turn, each starting from what its predecessor has published (default);
+// mode 0: six warps taking the blocks of 32 symbols in turn, each starting from what its predecessor has published (default);
 // 1: one thread, one symbol at a time (the yardstick the tests hold the speculative kernels against); 2: one warp, block
 // after block (the first generation)
 int pll_launch(const PllArgs& a, int mode, cudaStream_t stream);
